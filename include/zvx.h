@@ -1,0 +1,139 @@
+/* zvx.h -- C ABI of the B200-native zerovox mel-decoder + vocoder hot path (libzvx.so).
+ *
+ * The reference has no FFI layer: its boundary for this path is the C++ class API in
+ * /root/reference/src/zerovox.h plus the GGUF tensor naming of utils/zv2gguf.py.  These
+ * entry points are what a reference-side shim binds (see INTEGRATION.md and
+ * zerovox.cpp_b200/host/zerovox_b200.h); each cites the reference interface it replaces.
+ * Plain pointers and sizes only -- no torch, no ggml types.  All functions return 0 on
+ * success and a non-zero code on failure; zvx_last_error() gives the message (the C++
+ * shims rethrow it as std::runtime_error, matching stylettsdec.cpp:447-448,465-466 and
+ * hifigan.cpp:353-354,362-363).  One zvx_ctx per GPU; calls on one ctx are serialised by
+ * the caller (the reference classes are not re-entrant either).
+ */
+#ifndef ZVX_H
+#define ZVX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct zvx_ctx zvx_ctx;
+
+/* dtype codes equal ggml_type (ggml.h): GGML_TYPE_F32 = 0, GGML_TYPE_F16 = 1 */
+enum { ZVX_F32 = 0, ZVX_F16 = 1 };
+
+/* One weight tensor, as found by walking the GGUF / ggml weight context.
+ * Replaces: checked_get_tensor(ctx_w, name)          /root/reference/src/utils.cpp:9-17
+ * `ne` is ggml order (ne[0] fastest), `data` a HOST pointer (tensor->data on the CPU
+ * backend); the library copies and repacks, the caller keeps ownership. */
+typedef struct zvx_tensor_desc {
+    const char *name;
+    int32_t     dtype;
+    int32_t     n_dims;
+    int64_t     ne[4];
+    const void *data;
+} zvx_tensor_desc;
+
+/* Topology arguments = the constructor arguments of the two reference classes.
+ * Replaces: StyleTTSDecoder::StyleTTSDecoder(...)    /root/reference/src/zerovox.h:314-320
+ *           HiFiGAN::HiFiGAN(...)                    /root/reference/src/zerovox.h:366-376
+ * (values used by ZeroVOXModel: /root/reference/src/zerovox.cpp:117-138) */
+typedef struct zvx_config {
+    int32_t device;                 /* CUDA device ordinal */
+    int32_t dim_in;                 /* emb_dim + punct_emb_dim (528) */
+    int32_t style_dim;              /* 528 */
+    int32_t residual_dim;           /* 64 */
+    int32_t num_mels;               /* 80 = decoder dim_out = vocoder in_channels */
+    int32_t hop_size;               /* 300 */
+    int32_t kernel_size;            /* 7: vocoder input/output conv */
+    int32_t num_upsamples;          /* 4 */
+    int32_t upsample_scales[8];     /* 5,5,4,3 */
+    int32_t num_resblocks;          /* 3 */
+    int32_t num_resblock_dilations; /* 3 */
+    int32_t resblock_dilations[32]; /* [num_resblocks][num_resblock_dilations] = 1,3,5 x3 */
+    int32_t with_decoder;           /* build the StyleTTS decoder part (needs its tensors) */
+    int32_t with_vocoder;           /* build the HiFi-GAN part */
+} zvx_config;
+
+/* Fill cfg with the values ZeroVOXModel passes (zerovox.cpp:117-138). */
+void zvx_default_config(zvx_config *cfg);
+
+/* Upload + repack weights, allocate device state.  Replaces the two constructors above
+ * (graph build + ggml_gallocr_alloc_graph, stylettsdec.cpp:345-448, hifigan.cpp:223-354).
+ * A missing tensor fails like checked_get_tensor (utils.cpp:12-15). */
+int zvx_create(zvx_ctx **out, const zvx_config *cfg, const zvx_tensor_desc *weights, int32_t n_weights);
+void zvx_destroy(zvx_ctx *ctx);
+
+/* Message of the last failure on ctx (or of the last failed zvx_create when ctx == NULL). */
+const char *zvx_last_error(const zvx_ctx *ctx);
+
+/* Replaces StyleTTSDecoder::eval            /root/reference/src/stylettsdec.cpp:457-470
+ * enc_seq [L][dim_in] frame-major, style [style_dim], mel out [L][num_mels]; HOST pointers.
+ * InstanceNorm/AdaIN statistics span exactly L frames. */
+int zvx_decode(zvx_ctx *ctx, const float *enc_seq, const float *style, int32_t L, float *mel);
+
+/* Replaces HiFiGAN::eval                    /root/reference/src/hifigan.cpp:358-377
+ * mel [L][num_mels] -> wav [L*hop_size]; HOST pointers. */
+int zvx_vocode(zvx_ctx *ctx, const float *mel, int32_t L, float *wav);
+
+/* Batched form of decoder->eval + meldec->eval (ZeroVOXModel::eval, zerovox.cpp:330-334)
+ * for B independent utterances of lengths L[b].  HOST pointers; mel may be NULL (or
+ * individual entries NULL) when the caller only wants the waveform. */
+int zvx_synth_batch(zvx_ctx *ctx, int32_t B, const float *const *enc_seq, const float *const *style,
+                    const int32_t *L, float *const *mel, float *const *wav);
+
+/* Same computation with inputs/outputs already resident in device memory, packed back to
+ * back: d_enc [sum L][dim_in], d_style [B][style_dim], d_mel [sum L][num_mels] (may be
+ * NULL), d_wav [sum L * hop].  L is a HOST array.  Asynchronous on the ctx stream unless
+ * sync != 0.  Used by bench.py for the HBM-resident `value` measurement. */
+int zvx_synth_batch_device(zvx_ctx *ctx, int32_t B, const float *d_enc, const float *d_style, const int32_t *L,
+                           float *d_mel, float *d_wav, int32_t sync);
+int zvx_vocode_batch_device(zvx_ctx *ctx, int32_t B, const float *d_mel, const int32_t *L, float *d_wav,
+                            int32_t sync);
+
+/* Stream / accounting helpers */
+void *zvx_stream(zvx_ctx *ctx);                 /* cudaStream_t all work is enqueued on */
+int   zvx_synchronize(zvx_ctx *ctx);
+int64_t zvx_kernel_launches(const zvx_ctx *ctx); /* kernels launched by this ctx so far */
+int   zvx_reserve(zvx_ctx *ctx, int64_t total_frames, int32_t max_batch);
+
+/* ---- test / debug surface (used by tests/ only) ---------------------------------- */
+/* 0: tcgen05 implicit-GEMM kernels (the product path); 1: plain-CUDA validation kernels */
+void zvx_set_debug_kernels(zvx_ctx *ctx, int32_t use_validation_kernels);
+
+/* Run ONE convolution through the selected kernel on packed utterances.
+ * x [sum rows][Cin] fp32 host, w (OC, IC, K) fp16 host (K fastest), bias [OC] or NULL,
+ * out [sum rows * out_mul][OC] fp32 host, out16 same shape fp16 host or NULL.
+ * pro_mode / slope / mu / rstd / g / b as in the fused prologue; res optional residual. */
+typedef struct zvx_conv_test {
+    int32_t B;
+    const int32_t *rows;        /* [B] rows per utterance */
+    int32_t Cin, Cout, K, dilation, pad;
+    int32_t pro_mode;           /* 0 raw fp16 (x16 given), 1 cvt, 2 lrelu, 3 norm, 4 mel */
+    float   pro_slope;
+    const float *x;             /* fp32 input (modes 1-4) */
+    const uint16_t *x16;        /* fp16 input (mode 0) */
+    const uint16_t *w;
+    const float *bias;
+    const float *mu, *rstd, *g, *b;   /* [B][Cin] (norm) / [Cin] (mel: mu, rstd only) */
+    const float *res;           /* [sum rows][Cout] or NULL */
+    float   scale;              /* 0 = no scale */
+    float   out16_slope;
+    float  *out;                /* fp32 out */
+    uint16_t *out16;            /* fp16(lrelu(out)) or NULL */
+    int32_t use_validation_kernel;
+} zvx_conv_test;
+int zvx_test_conv(zvx_ctx *ctx, const zvx_conv_test *t);
+
+/* Copy an internal activation of the LAST run to the host (fp32): "mel", "v0" (vocoder
+ * input conv), "stage0".."stage3" need zvx_set_debug_stop(ctx, stage+1). */
+int zvx_debug_fetch(zvx_ctx *ctx, const char *what, float *dst, int64_t n_floats);
+void zvx_set_debug_stop(zvx_ctx *ctx, int32_t stop_after_stages); /* -1: run everything */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZVX_H */

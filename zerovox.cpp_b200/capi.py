@@ -1,0 +1,272 @@
+"""ctypes binding of libzvx.so (include/zvx.h) -- the only way Python reaches the CUDA path.
+
+There is no CPU fallback: if the shared library is missing or no sm_100 device is
+present, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import gguf_io
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libzvx.so")
+
+ZVX_F32, ZVX_F16 = 0, 1
+
+
+class TensorDesc(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("dtype", C.c_int32), ("n_dims", C.c_int32), ("ne", C.c_int64 * 4),
+                ("data", C.c_void_p)]
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("dim_in", C.c_int32), ("style_dim", C.c_int32), ("residual_dim", C.c_int32),
+                ("num_mels", C.c_int32), ("hop_size", C.c_int32), ("kernel_size", C.c_int32),
+                ("num_upsamples", C.c_int32), ("upsample_scales", C.c_int32 * 8), ("num_resblocks", C.c_int32),
+                ("num_resblock_dilations", C.c_int32), ("resblock_dilations", C.c_int32 * 32),
+                ("with_decoder", C.c_int32), ("with_vocoder", C.c_int32)]
+
+
+class ConvTest(C.Structure):
+    _fields_ = [("B", C.c_int32), ("rows", C.POINTER(C.c_int32)),
+                ("Cin", C.c_int32), ("Cout", C.c_int32), ("K", C.c_int32), ("dilation", C.c_int32), ("pad", C.c_int32),
+                ("pro_mode", C.c_int32), ("pro_slope", C.c_float),
+                ("x", C.c_void_p), ("x16", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p),
+                ("mu", C.c_void_p), ("rstd", C.c_void_p), ("g", C.c_void_p), ("b", C.c_void_p),
+                ("res", C.c_void_p), ("scale", C.c_float), ("out16_slope", C.c_float),
+                ("out", C.c_void_p), ("out16", C.c_void_p), ("use_validation_kernel", C.c_int32)]
+
+
+EXPORTS = [
+    "zvx_default_config", "zvx_create", "zvx_destroy", "zvx_last_error", "zvx_decode", "zvx_vocode",
+    "zvx_synth_batch", "zvx_synth_batch_device", "zvx_vocode_batch_device", "zvx_stream", "zvx_synchronize",
+    "zvx_kernel_launches", "zvx_reserve", "zvx_set_debug_kernels", "zvx_test_conv", "zvx_debug_fetch",
+    "zvx_set_debug_stop",
+]
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """dlopen libzvx.so; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} not built: run __graft_entry__.build() (nvcc, sm_100a). "
+                           "There is no CPU fallback for the hot path.")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, f32p = C.c_void_p, C.c_int32, C.c_int64, C.POINTER(C.c_float)
+    lib.zvx_default_config.argtypes = [C.POINTER(Config)]
+    lib.zvx_default_config.restype = None
+    lib.zvx_create.argtypes = [C.POINTER(vp), C.POINTER(Config), C.POINTER(TensorDesc), i32]
+    lib.zvx_create.restype = i32
+    lib.zvx_destroy.argtypes = [vp]
+    lib.zvx_destroy.restype = None
+    lib.zvx_last_error.argtypes = [vp]
+    lib.zvx_last_error.restype = C.c_char_p
+    lib.zvx_decode.argtypes = [vp, vp, vp, i32, vp]
+    lib.zvx_decode.restype = i32
+    lib.zvx_vocode.argtypes = [vp, vp, i32, vp]
+    lib.zvx_vocode.restype = i32
+    lib.zvx_synth_batch.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(i32), C.POINTER(vp), C.POINTER(vp)]
+    lib.zvx_synth_batch.restype = i32
+    lib.zvx_synth_batch_device.argtypes = [vp, i32, vp, vp, C.POINTER(i32), vp, vp, i32]
+    lib.zvx_synth_batch_device.restype = i32
+    lib.zvx_vocode_batch_device.argtypes = [vp, i32, vp, C.POINTER(i32), vp, i32]
+    lib.zvx_vocode_batch_device.restype = i32
+    lib.zvx_stream.argtypes = [vp]
+    lib.zvx_stream.restype = vp
+    lib.zvx_synchronize.argtypes = [vp]
+    lib.zvx_synchronize.restype = i32
+    lib.zvx_kernel_launches.argtypes = [vp]
+    lib.zvx_kernel_launches.restype = i64
+    lib.zvx_reserve.argtypes = [vp, i64, i32]
+    lib.zvx_reserve.restype = i32
+    lib.zvx_set_debug_kernels.argtypes = [vp, i32]
+    lib.zvx_set_debug_kernels.restype = None
+    lib.zvx_set_debug_stop.argtypes = [vp, i32]
+    lib.zvx_set_debug_stop.restype = None
+    lib.zvx_test_conv.argtypes = [vp, C.POINTER(ConvTest)]
+    lib.zvx_test_conv.restype = i32
+    lib.zvx_debug_fetch.argtypes = [vp, C.c_char_p, vp, i64]
+    lib.zvx_debug_fetch.restype = i32
+    _lib = lib
+    return lib
+
+
+class ZvxError(RuntimeError):
+    pass
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One zvx_ctx (= one GPU).  Mirrors the life cycle of the reference's
+    StyleTTSDecoder + HiFiGAN pair (/root/reference/src/zerovox.cpp:119-138)."""
+
+    def __init__(self, weights: Dict[str, np.ndarray], device: int = 0, with_decoder: bool = True,
+                 with_vocoder: bool = True):
+        self.lib = load_library()
+        self.cfg = Config()
+        self.lib.zvx_default_config(C.byref(self.cfg))
+        self.cfg.device = device
+        self.cfg.with_decoder = int(with_decoder)
+        self.cfg.with_vocoder = int(with_vocoder)
+        descs = (TensorDesc * len(weights))()
+        keep = []
+        for i, (name, arr) in enumerate(weights.items()):
+            arr = np.ascontiguousarray(arr)
+            keep.append(arr)
+            if arr.dtype == np.float32:
+                dt = ZVX_F32
+            elif arr.dtype == np.float16:
+                dt = ZVX_F16
+            else:
+                raise ValueError(f"{name}: unsupported dtype {arr.dtype}")
+            descs[i].name = name.encode()
+            descs[i].dtype = dt
+            ne = tuple(reversed(arr.shape))
+            descs[i].n_dims = len(ne)
+            for k in range(4):
+                descs[i].ne[k] = ne[k] if k < len(ne) else 1
+            descs[i].data = arr.ctypes.data
+        h = C.c_void_p()
+        rc = self.lib.zvx_create(C.byref(h), C.byref(self.cfg), descs, len(weights))
+        if rc != 0:
+            raise ZvxError((self.lib.zvx_last_error(None) or b"?").decode())
+        self.h = h
+        self.dim_in = self.cfg.dim_in
+        self.style_dim = self.cfg.style_dim
+        self.num_mels = self.cfg.num_mels
+        self.hop = self.cfg.hop_size
+
+    @classmethod
+    def from_gguf(cls, path: str, device: int = 0, **kw) -> "Context":
+        _, tensors = gguf_io.read_gguf(path)
+        return cls(tensors, device=device, **kw)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.zvx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise ZvxError((self.lib.zvx_last_error(self.h) or b"?").decode())
+
+    # ---- reference-shaped entry points -------------------------------------------
+    def decode(self, enc_seq: np.ndarray, style: np.ndarray) -> np.ndarray:
+        enc_seq = np.ascontiguousarray(enc_seq, np.float32)
+        style = np.ascontiguousarray(style, np.float32)
+        L = enc_seq.shape[0]
+        mel = np.empty((L, self.num_mels), np.float32)
+        self._check(self.lib.zvx_decode(self.h, _ptr(enc_seq), _ptr(style), L, _ptr(mel)))
+        return mel
+
+    def vocode(self, mel: np.ndarray) -> np.ndarray:
+        mel = np.ascontiguousarray(mel, np.float32)
+        L = mel.shape[0]
+        wav = np.empty(L * self.hop, np.float32)
+        self._check(self.lib.zvx_vocode(self.h, _ptr(mel), L, _ptr(wav)))
+        return wav
+
+    def synth_batch(self, enc_list: Sequence[np.ndarray], style_list: Sequence[np.ndarray], want_mel: bool = True):
+        B = len(enc_list)
+        encs = [np.ascontiguousarray(e, np.float32) for e in enc_list]
+        stys = [np.ascontiguousarray(s, np.float32) for s in style_list]
+        Ls = (C.c_int32 * B)(*[e.shape[0] for e in encs])
+        mels = [np.empty((e.shape[0], self.num_mels), np.float32) for e in encs] if want_mel else None
+        wavs = [np.empty(e.shape[0] * self.hop, np.float32) for e in encs]
+        vp = C.c_void_p
+        pe = (vp * B)(*[e.ctypes.data for e in encs])
+        ps = (vp * B)(*[s.ctypes.data for s in stys])
+        pm = (vp * B)(*[m.ctypes.data for m in mels]) if want_mel else None
+        pw = (vp * B)(*[w.ctypes.data for w in wavs])
+        self._check(self.lib.zvx_synth_batch(self.h, B, pe, ps, Ls, pm, pw))
+        return mels, wavs
+
+    def synth_batch_ptrs(self, B: int, enc_ptrs, style_ptrs, lengths, mel_ptrs, wav_ptrs):
+        """Raw-pointer form (host pointers as ints) for bench.py: no numpy allocation in the timed region."""
+        self._check(self.lib.zvx_synth_batch(self.h, B, enc_ptrs, style_ptrs, lengths, mel_ptrs, wav_ptrs))
+
+    def synth_batch_device(self, B: int, d_enc: int, d_style: int, lengths, d_mel: int, d_wav: int, sync: bool = False):
+        self._check(self.lib.zvx_synth_batch_device(self.h, B, d_enc, d_style, lengths, d_mel or None, d_wav, int(sync)))
+
+    def synchronize(self):
+        self._check(self.lib.zvx_synchronize(self.h))
+
+    def stream(self) -> int:
+        return int(self.lib.zvx_stream(self.h) or 0)
+
+    def kernel_launches(self) -> int:
+        return int(self.lib.zvx_kernel_launches(self.h))
+
+    def reserve(self, total_frames: int, max_batch: int):
+        self._check(self.lib.zvx_reserve(self.h, total_frames, max_batch))
+
+    # ---- test / debug surface -------------------------------------------------------
+    def set_debug_kernels(self, on: bool):
+        self.lib.zvx_set_debug_kernels(self.h, int(on))
+
+    def set_debug_stop(self, stages: int):
+        self.lib.zvx_set_debug_stop(self.h, int(stages))
+
+    def debug_fetch(self, what: str, n: int) -> np.ndarray:
+        out = np.empty(n, np.float32)
+        self._check(self.lib.zvx_debug_fetch(self.h, what.encode(), _ptr(out), n))
+        return out
+
+    def test_conv(self, rows: List[int], x: np.ndarray, w: np.ndarray, bias=None, dilation=1, pad=0, pro_mode=1,
+                  pro_slope=0.0, mu=None, rstd=None, g=None, b=None, res=None, scale=0.0, out16_slope=0.0,
+                  want16=False, validation=False):
+        """x [sum rows, Cin] (fp32, or fp16 for pro_mode 0); w (OC, IC, K) fp16."""
+        t = ConvTest()
+        B = len(rows)
+        rows_a = (C.c_int32 * B)(*rows)
+        t.B = B
+        t.rows = rows_a
+        w = np.ascontiguousarray(w, np.float16)
+        OC, IC, K = w.shape
+        t.Cin, t.Cout, t.K, t.dilation, t.pad = IC, OC, K, dilation, pad
+        t.pro_mode, t.pro_slope = pro_mode, pro_slope
+        keep = [w]
+        if pro_mode == 0:
+            x = np.ascontiguousarray(x, np.float16)
+            t.x16 = x.ctypes.data
+        else:
+            x = np.ascontiguousarray(x, np.float32)
+            t.x = x.ctypes.data
+        keep.append(x)
+        t.w = w.ctypes.data
+
+        def f32(a):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, np.float32)
+            keep.append(a)
+            return a.ctypes.data
+
+        t.bias, t.mu, t.rstd, t.g, t.b, t.res = f32(bias), f32(mu), f32(rstd), f32(g), f32(b), f32(res)
+        t.scale, t.out16_slope = scale, out16_slope
+        R = int(sum(rows))
+        out = np.empty((R, OC), np.float32)
+        t.out = out.ctypes.data
+        out16 = np.empty((R, OC), np.float16) if want16 else None
+        t.out16 = out16.ctypes.data if want16 else None
+        t.use_validation_kernel = int(validation)
+        self._check(self.lib.zvx_test_conv(self.h, C.byref(t)))
+        return (out, out16) if want16 else out

@@ -1,0 +1,492 @@
+// conv_umma.cu -- 1-D convolution as an implicit GEMM on the sm_100a tensor cores.
+//
+// Replaces, for every conv on the hot path, the reference sequence
+//   ggml_conv_1d = IM2COL(F32->F16) + MUL_MAT(F16 x F16, fp32 accumulate)
+//     /root/reference/ggml/src/ggml.c:3769-3786, ggml-cpu/ggml-cpu.c:9890-9961, :7377-7554
+//   + cont(transpose) + add(repeat(bias)) + cont(transpose)     (e.g. hifigan.cpp:138-140)
+// and the elementwise op that feeds it (leaky_relu / InstanceNorm-affine / AdaIN /
+// mel normalisation) and follows it (bias, residual add, MRF branch sum, 1/sqrt2, 1/3).
+//
+// One CTA computes a [128 time steps] x [NC output channels] tile:
+//     D[t, oc] = sum_taps sum_ic  A[t + off(tap), ic] * W[tap][oc, ic]
+//   * A operand: warps 0-3 read a halo tile (128 + (ntaps-1)*dilation rows) of the
+//     channels-last activation ONCE per 64-channel chunk, apply the fused prologue, round
+//     to fp16 and store it to shared memory in the UMMA K-major no-swizzle ("interleave")
+//     canonical layout with an 8-row-group stride of 128 B, i.e. row r of 8-channel group j
+//     lives at j*LBO + r*16.  Rows are uniformly 16 B apart, so each tap is just the same
+//     tile re-addressed through the matrix descriptor's start address (+ tap*dilation*16 B):
+//     no im2col, no per-tap reload (SURVEY.md H-b).
+//   * B operand: weights are pre-packed at load time into per-(N-chunk, K-chunk, tap)
+//     blocks that are already in the same canonical layout; one thread streams them
+//     into a ring of stages with cp.async.bulk (TMA bulk copy) completing on mbarriers.
+//   * MMA: one thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=NC, K=16),
+//     fp16 x fp16 -> fp32 accumulators in tensor memory; tcgen05.commit releases the
+//     smem stages and finally signals the epilogue.
+//   * Epilogue: warps 0-3 read the accumulator with tcgen05.ld (one row per thread) and
+//     apply bias / residual / branch-sum / scale, writing fp32 and/or the next conv's
+//     fp16 pre-activated operand.
+#include "zvx_common.cuh"
+#include "zvx_internal.h"
+
+namespace zvx {
+
+constexpr int TILE_M      = 128;
+constexpr int KCHUNK      = 64;
+constexpr int N_PRODUCERS = 128;
+constexpr int N_THREADS   = 192;
+constexpr int MAX_A_STAGES = 4;
+constexpr int MAX_B_STAGES = 8;
+constexpr int SMEM_HEADER  = 256;
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+// Bounded wait: a pipeline bug must not hang the GPU -- flag it and abort the launch.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int *err_flag)
+{
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 6000000000LL) {
+            if (err_flag) atomicExch(err_flag, 1);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before_sync()
+{
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after_sync()
+{
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit
+// layout): start>>4 [0,14), LBO>>4 [16,30) = byte distance between the two 8-element
+// K groups of one MMA, SBO>>4 [32,46) = byte distance between 8-row groups, version 1
+// at [46,48), layout type 0 (interleave) at [61,64).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+// kind::f16 instruction descriptor: D fp32 (bit 4), A/B fp16 K-major, N>>3 at [17,23), M>>4 at [24,29)
+__device__ __forceinline__ uint32_t make_idesc(int N)
+{
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b)
+{
+    __half2 h = __halves2half2(__float2half_rn(a), __float2half_rn(b));
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+
+// ------------------------------------------------------------------ the kernel
+template <int MODE>
+__global__ void __launch_bounds__(N_THREADS) conv_umma_kernel(const ConvParams p)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t *bars       = reinterpret_cast<uint64_t *>(smem);
+    uint64_t *a_full     = bars;                                  // [MAX_A_STAGES]
+    uint64_t *a_empty    = bars + MAX_A_STAGES;                   // [MAX_A_STAGES]
+    uint64_t *b_full     = bars + 2 * MAX_A_STAGES;               // [MAX_B_STAGES]
+    uint64_t *b_empty    = bars + 2 * MAX_A_STAGES + MAX_B_STAGES;
+    uint64_t *acc_full   = bars + 2 * MAX_A_STAGES + 2 * MAX_B_STAGES;
+    uint32_t *tmem_slot  = reinterpret_cast<uint32_t *>(smem + 240);
+
+    const int tid  = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+
+    const int Cin    = p.Cin;
+    const int NC     = p.NC;
+    const int ntaps  = p.ntaps;
+    const int kc_max = Cin < KCHUNK ? Cin : KCHUNK;
+    const int nkc    = (Cin + KCHUNK - 1) / KCHUNK;
+    const uint32_t lbo_a         = (uint32_t)p.a_rows * 16u;
+    const uint32_t a_stage_bytes = (uint32_t)(kc_max >> 3) * lbo_a;
+    const uint32_t lbo_b         = (uint32_t)NC * 16u;
+    const uint32_t b_stage_bytes = (uint32_t)kc_max * NC * 2u;
+    const uint32_t smem_base     = smem_u32(smem);
+    const uint32_t a_base        = smem_base + SMEM_HEADER;
+    const uint32_t b_base        = a_base + p.a_stages * a_stage_bytes;
+
+    // ---- which tile of which utterance ----
+    const int tile    = blockIdx.x;
+    const int u       = find_segment(p.tile_start, p.B, tile);
+    const int t0      = (tile - __ldg(p.tile_start + u)) * TILE_M;
+    const int seg_f0  = __ldg(p.seg_start + u);
+    const int seg_len = (__ldg(p.seg_start + u + 1) - seg_f0) * p.rate_in;
+    const size_t seg_row0 = (size_t)seg_f0 * p.rate_in;
+    const int nchunk  = blockIdx.y;
+
+    if (tid == 0) {
+        for (int s = 0; s < p.a_stages; ++s) {
+            mbar_init(smem_u32(a_full + s), N_PRODUCERS);
+            mbar_init(smem_u32(a_empty + s), 1);
+        }
+        for (int s = 0; s < p.b_stages; ++s) {
+            mbar_init(smem_u32(b_full + s), 1);
+            mbar_init(smem_u32(b_empty + s), 1);
+        }
+        mbar_init(smem_u32(acc_full), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        // =================== A producers ===================
+        const int need_rows = TILE_M + (ntaps - 1) * p.tap_step;
+        for (int c = 0; c < nkc; ++c) {
+            const int sa = c % p.a_stages;
+            const uint32_t ph = (uint32_t)(c / p.a_stages) & 1u;
+            mbar_wait(smem_u32(a_empty + sa), ph ^ 1u, p.err_flag);
+
+            const int kc   = min(KCHUNK, Cin - c * KCHUNK);
+            const int G    = kc >> 3;                 // 8-channel groups in this chunk: 8, 4 or 2
+            const int lg   = (G == 8) ? 3 : (G == 4) ? 2 : 1;
+            const int j    = tid & (G - 1);
+            const int r0   = tid >> lg;
+            const int rstep = N_PRODUCERS >> lg;
+            const int ch   = c * KCHUNK + j * 8;      // channel (relative to x_ch_off) of this thread's group
+
+            ProCh pc[8];
+            if (MODE == PRO_NORM || MODE == PRO_MEL) {
+                const float *mu = p.p_mu + (size_t)u * p.p_stat_stride + ch;
+                const float *rs = p.p_rstd + (size_t)u * p.p_stat_stride + ch;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    pc[i].mu = __ldg(mu + i);
+                    pc[i].rstd = __ldg(rs + i);
+                }
+                if (MODE == PRO_NORM) {
+                    const float *g = p.p_g + (size_t)u * p.p_gb_stride + ch;
+                    const float *b = p.p_b + (size_t)u * p.p_gb_stride + ch;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        pc[i].g = __ldg(g + i);
+                        pc[i].b = __ldg(b + i);
+                    }
+                }
+            }
+
+            const uint32_t dst0 = a_base + sa * a_stage_bytes + (uint32_t)j * lbo_a;
+            for (int rho = r0; rho < need_rows; rho += rstep) {
+                const int t_in = t0 + p.tap_off0 + rho;
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                if (t_in >= 0 && t_in < seg_len) {
+                    const size_t e = (seg_row0 + (size_t)t_in) * (size_t)p.ldx + p.x_ch_off + ch;
+                    if (MODE == PRO_F16) {
+                        v = *reinterpret_cast<const uint4 *>(reinterpret_cast<const __half *>(p.x) + e);
+                    } else {
+                        const float4 *src = reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(p.x) + e);
+                        const float4 f0 = src[0];
+                        const float4 f1 = src[1];
+                        float f[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) f[i] = prologue_apply(MODE, f[i], p.pro_slope, pc[i]);
+                        v.x = pack_half2(f[0], f[1]);
+                        v.y = pack_half2(f[2], f[3]);
+                        v.z = pack_half2(f[4], f[5]);
+                        v.w = pack_half2(f[6], f[7]);
+                    }
+                }
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst0 + (uint32_t)rho * 16u), "r"(v.x),
+                             "r"(v.y), "r"(v.z), "r"(v.w)
+                             : "memory");
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(smem_u32(a_full + sa));
+        }
+
+        // =================== epilogue ===================
+        mbar_wait(smem_u32(acc_full), 0u, p.err_flag);
+        tc_fence_after_sync();
+        const int  t     = t0 + tid;
+        const bool valid = t < seg_len;
+        const size_t orow = (seg_row0 + (size_t)t) * (size_t)p.out_mul + p.out_add;
+        const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+        for (int col = 0; col < NC; col += 16) {
+            uint32_t r[16];
+            tmem_ld16(trow + (uint32_t)col, r);
+            if (!valid) continue;
+            const int oc = nchunk * NC + col;
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+            if (p.bias) {
+                const float4 *b4 = reinterpret_cast<const float4 *>(p.bias + oc);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 b = __ldg(b4 + q);
+                    v[4 * q + 0] = __fadd_rn(v[4 * q + 0], b.x);
+                    v[4 * q + 1] = __fadd_rn(v[4 * q + 1], b.y);
+                    v[4 * q + 2] = __fadd_rn(v[4 * q + 2], b.z);
+                    v[4 * q + 3] = __fadd_rn(v[4 * q + 3], b.w);
+                }
+            }
+            if (p.res) {
+                const float4 *r4 = reinterpret_cast<const float4 *>(p.res + orow * (size_t)p.ldres + p.res_ch_off + oc);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 b = r4[q];
+                    v[4 * q + 0] = __fadd_rn(v[4 * q + 0], b.x);
+                    v[4 * q + 1] = __fadd_rn(v[4 * q + 1], b.y);
+                    v[4 * q + 2] = __fadd_rn(v[4 * q + 2], b.z);
+                    v[4 * q + 3] = __fadd_rn(v[4 * q + 3], b.w);
+                }
+            }
+            if (p.acc_in) {
+                const float4 *r4 =
+                    reinterpret_cast<const float4 *>(p.acc_in + orow * (size_t)p.ldo32 + p.o32_ch_off + oc);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 b = r4[q];
+                    v[4 * q + 0] = __fadd_rn(b.x, v[4 * q + 0]);
+                    v[4 * q + 1] = __fadd_rn(b.y, v[4 * q + 1]);
+                    v[4 * q + 2] = __fadd_rn(b.z, v[4 * q + 2]);
+                    v[4 * q + 3] = __fadd_rn(b.w, v[4 * q + 3]);
+                }
+            }
+            if (p.has_scale) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = __fmul_rn(v[i], p.scale);
+            }
+            if (p.out32) {
+                float4 *o4 = reinterpret_cast<float4 *>(p.out32 + orow * (size_t)p.ldo32 + p.o32_ch_off + oc);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) o4[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            }
+            if (p.out16) {
+                uint4 *o4 = reinterpret_cast<uint4 *>(p.out16 + orow * (size_t)p.ldo16 + p.o16_ch_off + oc);
+                uint32_t h[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    h[i] = pack_half2(lrelu_f(v[2 * i], p.out16_slope), lrelu_f(v[2 * i + 1], p.out16_slope));
+                o4[0] = make_uint4(h[0], h[1], h[2], h[3]);
+                o4[1] = make_uint4(h[4], h[5], h[6], h[7]);
+            }
+        }
+    } else if (warp == 4) {
+        // =================== MMA issuer (one thread) ===================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(NC);
+            int it = 0;
+            uint32_t first = 1;
+            for (int c = 0; c < nkc; ++c) {
+                const int sa = c % p.a_stages;
+                const uint32_t pha = (uint32_t)(c / p.a_stages) & 1u;
+                const int kc = min(KCHUNK, Cin - c * KCHUNK);
+                mbar_wait(smem_u32(a_full + sa), pha, p.err_flag);
+                tc_fence_after_sync();
+                const uint32_t a_stage = a_base + sa * a_stage_bytes;
+                for (int a = 0; a < ntaps; ++a, ++it) {
+                    const int sb = it % p.b_stages;
+                    const uint32_t phb = (uint32_t)(it / p.b_stages) & 1u;
+                    mbar_wait(smem_u32(b_full + sb), phb, p.err_flag);
+                    tc_fence_after_sync();
+                    const uint32_t b_stage = b_base + sb * b_stage_bytes;
+                    const uint32_t a_tap   = a_stage + (uint32_t)(a * p.tap_step) * 16u;
+                    for (int kk = 0; kk < (kc >> 4); ++kk) {
+                        const uint64_t adesc = make_smem_desc(a_tap + (uint32_t)kk * 2u * lbo_a, lbo_a, 128u);
+                        const uint64_t bdesc = make_smem_desc(b_stage + (uint32_t)kk * 2u * lbo_b, lbo_b, 128u);
+                        umma_f16(tmem_base, adesc, bdesc, idesc, first ? 0u : 1u);
+                        first = 0;
+                    }
+                    umma_commit(smem_u32(b_empty + sb));
+                }
+                umma_commit(smem_u32(a_empty + sa));
+            }
+            umma_commit(smem_u32(acc_full));
+        }
+        __syncwarp();
+    } else {
+        // =================== weight (B operand) loader ===================
+        if (lane == 0) {
+            const __half *wbase = p.w_packed + (size_t)nchunk * ((size_t)Cin * ntaps * NC);
+            int it = 0;
+            for (int c = 0; c < nkc; ++c) {
+                const int kc = min(KCHUNK, Cin - c * KCHUNK);
+                const uint32_t bytes = (uint32_t)kc * NC * 2u;
+                for (int a = 0; a < ntaps; ++a, ++it) {
+                    const int sb = it % p.b_stages;
+                    const uint32_t phb = (uint32_t)(it / p.b_stages) & 1u;
+                    mbar_wait(smem_u32(b_empty + sb), phb ^ 1u, p.err_flag);
+                    const __half *src = wbase + ((size_t)c * KCHUNK * ntaps + (size_t)a * kc) * NC;
+                    mbar_arrive_expect_tx(smem_u32(b_full + sb), bytes);
+                    bulk_copy_g2s(b_base + sb * b_stage_bytes, src, bytes, smem_u32(b_full + sb));
+                }
+            }
+        }
+        __syncwarp();
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after_sync();
+        tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    }
+}
+
+// ------------------------------------------------------------------ host side
+static int round_a_rows(int need_rows, int kc_max)
+{
+    // rows per A stage, padded so that the 16-byte stores of one quarter-warp hit 32 distinct
+    // banks: with G = kc/8 groups, (rows*j + r) mod 8 must be distinct for j < G, r < 8/G.
+    const int G = kc_max >> 3;
+    const int want = (G >= 8) ? 1 : (G == 4) ? 2 : 4;
+    int r = need_rows;
+    while ((r & 7) != want) ++r;
+    return r;
+}
+
+size_t conv_umma_plan(ConvParams &p, size_t smem_budget)
+{
+    const int kc_max    = p.Cin < KCHUNK ? p.Cin : KCHUNK;
+    const int need_rows = TILE_M + (p.ntaps - 1) * p.tap_step;
+    p.a_rows            = round_a_rows(need_rows, kc_max);
+    const size_t a_stage = (size_t)(kc_max >> 3) * p.a_rows * 16;
+    const size_t b_stage = (size_t)kc_max * p.NC * 2;
+    const int nkc        = (p.Cin + KCHUNK - 1) / KCHUNK;
+    const int nb_total   = nkc * p.ntaps;
+    int as = nkc < 2 ? 1 : 2;
+    int bs = nb_total < 2 ? 1 : 2;
+    // grow B first (weights are the longer stream), then A, while it fits
+    while (true) {
+        bool grew = false;
+        if (bs < MAX_B_STAGES && bs < nb_total && SMEM_HEADER + as * a_stage + (bs + 1) * b_stage <= smem_budget) {
+            ++bs;
+            grew = true;
+        }
+        if (as < MAX_A_STAGES && as < nkc && as < 3 && SMEM_HEADER + (as + 1) * a_stage + bs * b_stage <= smem_budget) {
+            ++as;
+            grew = true;
+        }
+        if (!grew) break;
+    }
+    p.a_stages = as;
+    p.b_stages = bs;
+    int cols = 32;
+    while (cols < p.NC) cols <<= 1;
+    p.tmem_cols = cols;
+    return SMEM_HEADER + as * a_stage + bs * b_stage;
+}
+
+template <int MODE>
+static cudaError_t launch_mode(const ConvParams &p, int total_tiles, size_t smem, cudaStream_t st)
+{
+    dim3 grid(total_tiles, p.Cout / p.NC, 1);
+    conv_umma_kernel<MODE><<<grid, N_THREADS, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t conv_umma_init()
+{
+    cudaError_t e;
+    const int kMax = 227 * 1024;
+    if ((e = cudaFuncSetAttribute(conv_umma_kernel<PRO_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(conv_umma_kernel<PRO_CVT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(conv_umma_kernel<PRO_LRELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(conv_umma_kernel<PRO_NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(conv_umma_kernel<PRO_MEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax)) != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
+cudaError_t conv_umma_launch(const ConvParams &p, int total_tiles, size_t smem, cudaStream_t st)
+{
+    switch (p.pro_mode) {
+        case PRO_F16:   return launch_mode<PRO_F16>(p, total_tiles, smem, st);
+        case PRO_CVT:   return launch_mode<PRO_CVT>(p, total_tiles, smem, st);
+        case PRO_LRELU: return launch_mode<PRO_LRELU>(p, total_tiles, smem, st);
+        case PRO_NORM:  return launch_mode<PRO_NORM>(p, total_tiles, smem, st);
+        case PRO_MEL:   return launch_mode<PRO_MEL>(p, total_tiles, smem, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace zvx

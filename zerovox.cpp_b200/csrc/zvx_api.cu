@@ -1,0 +1,1007 @@
+// zvx_api.cu -- context, weight upload/repack, layer schedule and the C ABI (include/zvx.h).
+//
+// The schedule below is the B200 restatement of the two reference graphs:
+//   StyleTTSDecoder   /root/reference/src/stylettsdec.cpp:371-441
+//   HiFiGAN           /root/reference/src/hifigan.cpp:242-345
+// Every conv is one launch of the tcgen05 implicit-GEMM kernel (conv_umma.cu) with the
+// neighbouring elementwise ops fused into its prologue / epilogue.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/zvx.h"
+#include "zvx_internal.h"
+
+using namespace zvx;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevTensor {
+    void   *d = nullptr;
+    int     dtype = 0;
+    int     nd = 0;
+    int64_t ne[4] = {1, 1, 1, 1};
+    size_t  nbytes = 0;
+};
+
+struct ConvVariant {
+    __half *packed = nullptr;
+    int ntaps = 0, w_tap0 = 0, w_tap_stride = 1, tap_off0 = 0, tap_step = 1, out_add = 0;
+};
+
+struct ConvLayer {
+    int OC = 0, IC = 0, K = 0, NC = 0;
+    const __half *raw = nullptr;
+    const float  *bias = nullptr;
+    std::vector<ConvVariant> var;
+};
+
+struct ResBlkW  { ConvLayer conv1, conv2, conv1x1; bool learned_sc = false; const float *n1w, *n1b, *n2w, *n2b; int cin, cout; };
+struct AdaBlkW  { ConvLayer conv1, conv2, conv1x1; bool learned_sc = false; int ada1, ada2; int cin, cout; };
+
+}  // namespace
+
+struct zvx_ctx {
+    zvx_config cfg;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    int use_ref_kernels = 0;
+    int debug_stop = -1;
+
+    std::map<std::string, DevTensor> W;
+    std::vector<void *> owned;           // every cudaMalloc to free
+
+    // ---- decoder ----
+    ResBlkW enc[2];
+    ConvLayer asr0; const float *asr1w = nullptr, *asr1b = nullptr;
+    AdaBlkW dec[5];
+    ConvLayer to_out;
+    AdainTable adain;
+    // ---- vocoder ----
+    const float *mel_mean = nullptr, *mel_scale = nullptr;
+    ConvLayer input_conv;
+    std::vector<ConvLayer> up;                    // per stage, var = phases
+    std::vector<ConvLayer> mrf1, mrf2;            // [stage*nb*nd + j*nd + d]
+    ConvLayer output_conv;
+    std::vector<int> rates;                       // rows per frame after stage i (index 0 = 1)
+    std::vector<int> chans;                       // channels after stage i (index 0 = input conv out)
+
+    // ---- workspace ----
+    int64_t cap_frames = 0;
+    int cap_batch = 0;
+    float *enc_in = nullptr, *sc = nullptr, *h528 = nullptr, *e0 = nullptr, *h1056 = nullptr, *catA = nullptr,
+          *catB = nullptr, *asr = nullptr, *d1 = nullptr, *d2 = nullptr, *mel = nullptr, *style = nullptr;
+    float *mu = nullptr, *rstd = nullptr, *adain_gb = nullptr;
+    float *v0 = nullptr, *U = nullptr, *CS = nullptr, *Y1 = nullptr, *VA = nullptr, *VB = nullptr, *wav = nullptr;
+    __half *H16 = nullptr;
+    int *d_seg = nullptr;                         // [B+1] frames prefix
+    int *d_tiles = nullptr;                       // [nrates][B+1] tile prefixes
+    int *d_err = nullptr;
+    std::vector<int> h_seg, h_tiles;              // host mirrors
+    std::vector<int> total_tiles;                 // per rate
+    int *pin_tables = nullptr;                    // pinned staging for seg/tile tables
+    cudaEvent_t tables_event = nullptr;
+    bool tables_pending = false;
+    float *pin_in = nullptr, *pin_out = nullptr;  // pinned staging for host-pointer API
+    size_t pin_in_cap = 0, pin_out_cap = 0;
+    // conv test scratch
+    int last_B = 0;
+    int64_t last_frames = 0;
+};
+
+namespace {
+
+int fail(zvx_ctx *ctx, const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf; else g_create_error = buf;
+    return 1;
+}
+
+#define CK(ctx, call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+            return fail(ctx, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+template <typename T>
+int dev_alloc(zvx_ctx *ctx, T **p, size_t n)
+{
+    void *d = nullptr;
+    CK(ctx, cudaMalloc(&d, std::max<size_t>(n, 1) * sizeof(T)));
+    ctx->owned.push_back(d);
+    *p = reinterpret_cast<T *>(d);
+    return 0;
+}
+
+void dev_free(zvx_ctx *ctx, void *p)
+{
+    if (!p) return;
+    auto it = std::find(ctx->owned.begin(), ctx->owned.end(), p);
+    if (it != ctx->owned.end()) ctx->owned.erase(it);
+    cudaFree(p);
+}
+
+const DevTensor *find_w(zvx_ctx *ctx, const std::string &name)
+{
+    auto it = ctx->W.find(name);
+    return it == ctx->W.end() ? nullptr : &it->second;
+}
+
+// checked_get_tensor (utils.cpp:9-17): a missing tensor is an error
+int get_w(zvx_ctx *ctx, const std::string &name, int dtype, const DevTensor **out)
+{
+    const DevTensor *t = find_w(ctx, name);
+    if (!t) return fail(ctx, "tensor '%s' not found", name.c_str());
+    if (t->dtype != dtype)
+        return fail(ctx, "tensor '%s' has dtype %d, expected %d (conv kernels must be F16, everything else F32)",
+                    name.c_str(), t->dtype, dtype);
+    *out = t;
+    return 0;
+}
+
+int pick_nc(int oc)
+{
+    if (oc <= 256) return oc;
+    for (int nc = 256; nc >= 16; nc -= 16)
+        if (oc % nc == 0) return nc;
+    return 0;
+}
+
+// Pack raw (OC, IC, K) fp16 (K fastest) into UMMA-ready blocks, ordered
+// [n-chunk][k-chunk of 64 channels][tap] with each block laid out [kc/8][NC][8]:
+// the K-major no-swizzle canonical layout (8-row groups contiguous, LBO = NC*16 bytes).
+int pack_variant(zvx_ctx *ctx, const std::vector<__half> &raw, int OC, int IC, int K, int NC, ConvVariant &v)
+{
+    std::vector<__half> pk((size_t)OC * IC * v.ntaps);
+    size_t o = 0;
+    for (int n = 0; n < OC / NC; ++n)
+        for (int c0 = 0; c0 < IC; c0 += 64) {
+            const int kc = std::min(64, IC - c0);
+            for (int a = 0; a < v.ntaps; ++a) {
+                const int tap = v.w_tap0 + a * v.w_tap_stride;
+                for (int g = 0; g < kc / 8; ++g)
+                    for (int nn = 0; nn < NC; ++nn)
+                        for (int e = 0; e < 8; ++e)
+                            pk[o++] = raw[((size_t)(n * NC + nn) * IC + (c0 + g * 8 + e)) * K + tap];
+            }
+        }
+    if (dev_alloc(ctx, &v.packed, pk.size())) return 1;
+    CK(ctx, cudaMemcpy(v.packed, pk.data(), pk.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// host copies of raw conv weights are needed for packing
+struct HostW { std::map<std::string, std::vector<__half>> h; };
+
+int make_conv(zvx_ctx *ctx, HostW &hw, const std::string &prefix, bool with_bias, int dilation, ConvLayer &L,
+              int force_pad = -1)
+{
+    const DevTensor *w, *b = nullptr;
+    if (get_w(ctx, prefix + ".w", ZVX_F16, &w)) return 1;
+    if (with_bias && get_w(ctx, prefix + ".b", ZVX_F32, &b)) return 1;
+    L.K = (int)w->ne[0];
+    L.IC = (int)w->ne[1];
+    L.OC = (int)w->ne[2];
+    L.raw = reinterpret_cast<const __half *>(w->d);
+    L.bias = b ? reinterpret_cast<const float *>(b->d) : nullptr;
+    if (b && b->ne[0] != L.OC) return fail(ctx, "%s.b has %lld elements, expected %d", prefix.c_str(), (long long)b->ne[0], L.OC);
+    if (L.IC % 16 != 0) return fail(ctx, "%s: input channels %d not a multiple of 16", prefix.c_str(), L.IC);
+    if (L.OC == 1) return 0;   // single-channel output conv runs on CUDA cores, no packing
+    L.NC = pick_nc(L.OC);
+    if (L.NC == 0 || L.OC % 16 != 0) return fail(ctx, "%s: unsupported output channels %d", prefix.c_str(), L.OC);
+    ConvVariant v;
+    v.ntaps = L.K;
+    v.w_tap0 = 0;
+    v.w_tap_stride = 1;
+    v.tap_step = dilation;
+    v.tap_off0 = -(force_pad >= 0 ? force_pad : (L.K - 1) / 2 * dilation);
+    v.out_add = 0;
+    if (pack_variant(ctx, hw.h[prefix + ".w"], L.OC, L.IC, L.K, L.NC, v)) return 1;
+    L.var.push_back(v);
+    return 0;
+}
+
+// ConvTranspose1d(stride s, padding p = s/2 + s%2, output_padding s%2) emulated by the
+// reference as zero-stuffing + stride-1 conv with the pre-flipped kernel
+// (hifigan.cpp:44-65).  Polyphase form: output o = q*s + phi receives
+// exactly the taps k' = k0 + a*s with k0 = (off - phi) mod s, reading x[q + d0 + a].
+int make_upconv(zvx_ctx *ctx, HostW &hw, const std::string &prefix, int s, ConvLayer &L)
+{
+    const DevTensor *w, *b;
+    if (get_w(ctx, prefix + ".w", ZVX_F16, &w)) return 1;
+    if (get_w(ctx, prefix + ".b", ZVX_F32, &b)) return 1;
+    L.K = (int)w->ne[0];
+    L.IC = (int)w->ne[1];
+    L.OC = (int)w->ne[2];
+    L.raw = reinterpret_cast<const __half *>(w->d);
+    L.bias = reinterpret_cast<const float *>(b->d);
+    L.NC = pick_nc(L.OC);
+    if (L.NC == 0 || L.OC % 16 != 0 || L.IC % 16 != 0) return fail(ctx, "%s: unsupported shape", prefix.c_str());
+    const int p = s / 2 + s % 2, op = s % 2;
+    const int off = L.K - 1 - p;
+    if ((L.K - 2 * p + op) != s) return fail(ctx, "%s: kernel %d / stride %d does not give L_out = s*L_in", prefix.c_str(), L.K, s);
+    for (int phi = 0; phi < s; ++phi) {
+        ConvVariant v;
+        const int k0 = (((off - phi) % s) + s) % s;
+        v.w_tap0 = k0;
+        v.w_tap_stride = s;
+        v.ntaps = (L.K - k0 + s - 1) / s;
+        v.tap_off0 = (phi + k0 - off) / s;    // exact: phi + k0 - off is a multiple of s
+        if ((phi + k0 - off) % s != 0) return fail(ctx, "%s: polyphase derivation broken", prefix.c_str());
+        v.tap_step = 1;
+        v.out_add = phi;
+        if (pack_variant(ctx, hw.h[prefix + ".w"], L.OC, L.IC, L.K, L.NC, v)) return 1;
+        L.var.push_back(v);
+    }
+    return 0;
+}
+
+int f32_ptr(zvx_ctx *ctx, const std::string &name, int64_t n, const float **out)
+{
+    const DevTensor *t;
+    if (get_w(ctx, name, ZVX_F32, &t)) return 1;
+    if (n > 0 && t->ne[0] * t->ne[1] != n) return fail(ctx, "tensor '%s' has %lld elements, expected %lld", name.c_str(), (long long)(t->ne[0] * t->ne[1]), (long long)n);
+    *out = reinterpret_cast<const float *>(t->d);
+    return 0;
+}
+
+int build_decoder(zvx_ctx *ctx, HostW &hw)
+{
+    const int D = ctx->cfg.dim_in, BN = 2 * D, R = ctx->cfg.residual_dim, S = ctx->cfg.style_dim;
+    char nm[128];
+    const int enc_dims[2][2] = {{D, BN}, {BN, BN}};
+    for (int i = 0; i < 2; ++i) {
+        ResBlkW &b = ctx->enc[i];
+        b.cin = enc_dims[i][0];
+        b.cout = enc_dims[i][1];
+        b.learned_sc = b.cin != b.cout;
+        snprintf(nm, sizeof nm, "_mel_decoder.encode.%d", i);
+        const std::string p = nm;
+        if (make_conv(ctx, hw, p + ".conv1", true, 1, b.conv1)) return 1;
+        if (make_conv(ctx, hw, p + ".conv2", true, 1, b.conv2)) return 1;
+        if (b.learned_sc && make_conv(ctx, hw, p + ".conv1x1", false, 1, b.conv1x1)) return 1;
+        if (f32_ptr(ctx, p + ".norm1.w", b.cin, &b.n1w) || f32_ptr(ctx, p + ".norm1.b", b.cin, &b.n1b) ||
+            f32_ptr(ctx, p + ".norm2.w", b.cin, &b.n2w) || f32_ptr(ctx, p + ".norm2.b", b.cin, &b.n2b))
+            return 1;
+        if (b.conv1.IC != b.cin || b.conv1.OC != b.cin || b.conv2.IC != b.cin || b.conv2.OC != b.cout)
+            return fail(ctx, "%s: conv shapes do not match ResBlk1d(%d,%d)", nm, b.cin, b.cout);
+    }
+    if (make_conv(ctx, hw, "_mel_decoder.asr_res.0", true, 1, ctx->asr0)) return 1;
+    if (ctx->asr0.OC != R || ctx->asr0.IC != D) return fail(ctx, "asr_res.0 shape mismatch");
+    if (f32_ptr(ctx, "_mel_decoder.asr_res.1.w", R, &ctx->asr1w) || f32_ptr(ctx, "_mel_decoder.asr_res.1.b", R, &ctx->asr1b)) return 1;
+
+    const int dec_dims[5][2] = {{BN + R, BN}, {BN + R, BN}, {BN + R, D}, {D, D}, {D, D}};
+    ctx->adain.n = 0;
+    ctx->adain.total = 0;
+    ctx->adain.style_dim = S;
+    for (int i = 0; i < 5; ++i) {
+        AdaBlkW &b = ctx->dec[i];
+        b.cin = dec_dims[i][0];
+        b.cout = dec_dims[i][1];
+        b.learned_sc = b.cin != b.cout;
+        snprintf(nm, sizeof nm, "_mel_decoder.decode.%d", i);
+        const std::string p = nm;
+        if (make_conv(ctx, hw, p + ".conv1", true, 1, b.conv1)) return 1;
+        if (make_conv(ctx, hw, p + ".conv2", true, 1, b.conv2)) return 1;
+        if (b.learned_sc && make_conv(ctx, hw, p + ".conv1x1", false, 1, b.conv1x1)) return 1;
+        if (b.conv1.IC != b.cin || b.conv1.OC != b.cout || b.conv2.IC != b.cout || b.conv2.OC != b.cout)
+            return fail(ctx, "%s: conv shapes do not match AdainResBlk1d(%d,%d)", nm, b.cin, b.cout);
+        for (int k = 1; k <= 2; ++k) {
+            const int C = k == 1 ? b.cin : b.cout;
+            snprintf(nm, sizeof nm, "_mel_decoder.decode.%d.norm%d.fc", i, k);
+            const float *fw, *fb;
+            if (f32_ptr(ctx, std::string(nm) + ".w", (int64_t)2 * C * S, &fw) || f32_ptr(ctx, std::string(nm) + ".b", 2 * C, &fb)) return 1;
+            AdainDesc &d = ctx->adain.d[ctx->adain.n];
+            d.fc_w = fw;
+            d.fc_b = fb;
+            d.C = C;
+            d.out_off = ctx->adain.total;
+            (k == 1 ? b.ada1 : b.ada2) = ctx->adain.n;
+            ctx->adain.total += 2 * C;
+            ctx->adain.n++;
+        }
+    }
+    if (make_conv(ctx, hw, "_mel_decoder.to_out.0", true, 1, ctx->to_out)) return 1;
+    if (ctx->to_out.OC != ctx->cfg.num_mels) return fail(ctx, "to_out.0 has %d output channels, expected %d", ctx->to_out.OC, ctx->cfg.num_mels);
+    return 0;
+}
+
+int build_vocoder(zvx_ctx *ctx, HostW &hw)
+{
+    const zvx_config &c = ctx->cfg;
+    if (f32_ptr(ctx, "hifigan.mean", c.num_mels, &ctx->mel_mean) || f32_ptr(ctx, "hifigan.scale", c.num_mels, &ctx->mel_scale)) return 1;
+    if (make_conv(ctx, hw, "_meldec.input_conv", true, 1, ctx->input_conv, (c.kernel_size - 1) / 2)) return 1;
+    if (ctx->input_conv.IC != c.num_mels) return fail(ctx, "input_conv expects %d channels", ctx->input_conv.IC);
+    ctx->rates.assign(1, 1);
+    ctx->chans.assign(1, ctx->input_conv.OC);
+    char nm[128];
+    const int nb = c.num_resblocks, nd = c.num_resblock_dilations;
+    ctx->up.resize(c.num_upsamples);
+    ctx->mrf1.resize((size_t)c.num_upsamples * nb * nd);
+    ctx->mrf2.resize((size_t)c.num_upsamples * nb * nd);
+    for (int i = 0; i < c.num_upsamples; ++i) {
+        snprintf(nm, sizeof nm, "_meldec.upsamples.%d.1", i);
+        if (make_upconv(ctx, hw, nm, c.upsample_scales[i], ctx->up[i])) return 1;
+        if (ctx->up[i].IC != ctx->chans.back()) return fail(ctx, "%s: expects %d input channels, have %d", nm, ctx->up[i].IC, ctx->chans.back());
+        ctx->rates.push_back(ctx->rates.back() * c.upsample_scales[i]);
+        ctx->chans.push_back(ctx->up[i].OC);
+        for (int j = 0; j < nb; ++j)
+            for (int d = 0; d < nd; ++d) {
+                const size_t idx = ((size_t)i * nb + j) * nd + d;
+                const int dil = c.resblock_dilations[j * nd + d];
+                snprintf(nm, sizeof nm, "_meldec.blocks.%d.convs1.%d.1", i * nb + j, d);
+                if (make_conv(ctx, hw, nm, true, dil, ctx->mrf1[idx])) return 1;
+                snprintf(nm, sizeof nm, "_meldec.blocks.%d.convs2.%d.1", i * nb + j, d);
+                if (make_conv(ctx, hw, nm, true, 1, ctx->mrf2[idx])) return 1;
+                if (ctx->mrf1[idx].IC != ctx->chans.back() || ctx->mrf1[idx].OC != ctx->chans.back() ||
+                    ctx->mrf2[idx].IC != ctx->chans.back() || ctx->mrf2[idx].OC != ctx->chans.back())
+                    return fail(ctx, "%s: channel mismatch", nm);
+            }
+    }
+    if (ctx->rates.back() != c.hop_size) return fail(ctx, "product of upsample_scales (%d) != hop_size (%d)", ctx->rates.back(), c.hop_size);
+    if (make_conv(ctx, hw, "_meldec.output_conv.1", true, 1, ctx->output_conv, (c.kernel_size - 1) / 2)) return 1;
+    if (ctx->output_conv.OC != 1 || ctx->output_conv.IC != ctx->chans.back()) return fail(ctx, "output_conv shape mismatch");
+    return 0;
+}
+
+// ---------------------------------------------------------------- workspace
+int64_t max_stage_elems(const zvx_ctx *ctx)
+{
+    int64_t m = 0;
+    for (size_t i = 1; i < ctx->rates.size(); ++i) m = std::max<int64_t>(m, (int64_t)ctx->rates[i] * ctx->chans[i]);
+    return m;
+}
+
+int reserve(zvx_ctx *ctx, int64_t frames, int batch)
+{
+    const zvx_config &c = ctx->cfg;
+    if (batch > ctx->cap_batch) {
+        const int nb = std::max(batch, 64);
+        const int nr = (int)std::max<size_t>(ctx->rates.size(), 1);
+        dev_free(ctx, ctx->d_seg); dev_free(ctx, ctx->d_tiles); dev_free(ctx, ctx->mu); dev_free(ctx, ctx->rstd);
+        dev_free(ctx, ctx->adain_gb); dev_free(ctx, ctx->style);
+        if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+        if (ctx->pin_tables) cudaFreeHost(ctx->pin_tables);
+        ctx->pin_tables = nullptr;
+        ctx->tables_pending = false;
+        if (dev_alloc(ctx, &ctx->d_seg, nb + 1) || dev_alloc(ctx, &ctx->d_tiles, (size_t)nr * (nb + 1))) return 1;
+        const int maxc = 2 * c.dim_in + c.residual_dim;
+        if (dev_alloc(ctx, &ctx->mu, (size_t)nb * maxc) || dev_alloc(ctx, &ctx->rstd, (size_t)nb * maxc)) return 1;
+        if (dev_alloc(ctx, &ctx->adain_gb, (size_t)nb * std::max(ctx->adain.total, 1))) return 1;
+        if (dev_alloc(ctx, &ctx->style, (size_t)nb * c.style_dim)) return 1;
+        CK(ctx, cudaMallocHost(&ctx->pin_tables, sizeof(int) * (size_t)(nr + 1) * (nb + 1)));
+        ctx->cap_batch = nb;
+    }
+    if (frames > ctx->cap_frames) {
+        const int64_t F = std::max<int64_t>(frames, 256);
+        float **bufs[] = {&ctx->enc_in, &ctx->sc, &ctx->h528, &ctx->e0, &ctx->h1056, &ctx->catA, &ctx->catB, &ctx->asr,
+                          &ctx->d1, &ctx->d2, &ctx->mel, &ctx->v0, &ctx->U, &ctx->CS, &ctx->Y1, &ctx->VA, &ctx->VB, &ctx->wav};
+        for (float **b : bufs) { dev_free(ctx, *b); *b = nullptr; }
+        dev_free(ctx, ctx->H16); ctx->H16 = nullptr;
+        const int D = c.dim_in, BN = 2 * D, R = c.residual_dim;
+        if (c.with_decoder) {
+            if (dev_alloc(ctx, &ctx->enc_in, F * D) || dev_alloc(ctx, &ctx->sc, F * BN) || dev_alloc(ctx, &ctx->h528, F * D) ||
+                dev_alloc(ctx, &ctx->e0, F * BN) || dev_alloc(ctx, &ctx->h1056, F * BN) || dev_alloc(ctx, &ctx->catA, F * (BN + R)) ||
+                dev_alloc(ctx, &ctx->catB, F * (BN + R)) || dev_alloc(ctx, &ctx->asr, F * R) || dev_alloc(ctx, &ctx->d1, F * D) ||
+                dev_alloc(ctx, &ctx->d2, F * D))
+                return 1;
+        }
+        if (dev_alloc(ctx, &ctx->mel, F * c.num_mels)) return 1;
+        if (c.with_vocoder) {
+            const int64_t S = max_stage_elems(ctx);
+            if (dev_alloc(ctx, &ctx->v0, F * ctx->chans[0]) || dev_alloc(ctx, &ctx->U, F * S) || dev_alloc(ctx, &ctx->CS, F * S) ||
+                dev_alloc(ctx, &ctx->Y1, F * S) || dev_alloc(ctx, &ctx->VA, F * S) || dev_alloc(ctx, &ctx->VB, F * S) ||
+                dev_alloc(ctx, &ctx->H16, F * S) || dev_alloc(ctx, &ctx->wav, F * c.hop_size))
+                return 1;
+        }
+        ctx->cap_frames = F;
+    }
+    return 0;
+}
+
+// upload utterance segmentation: frames prefix + per-rate 128-row tile prefixes
+int set_batch(zvx_ctx *ctx, int B, const int32_t *L, bool reserve_workspace = true)
+{
+    if (B <= 0) return fail(ctx, "empty batch");
+    int64_t frames = 0;
+    for (int b = 0; b < B; ++b) {
+        if (L[b] <= 0) return fail(ctx, "utterance %d has non-positive length %d", b, L[b]);
+        frames += L[b];
+    }
+    if (frames * (int64_t)ctx->cfg.hop_size * 64 > (int64_t)1 << 40) return fail(ctx, "batch too large");
+    if (reserve(ctx, reserve_workspace ? frames : 0, B)) return 1;
+    // the pinned table buffer is reused: wait until the previous batch's table upload has been consumed
+    if (ctx->tables_pending) CK(ctx, cudaEventSynchronize(ctx->tables_event));
+    const int nr = (int)ctx->rates.size();
+    const int stride = ctx->cap_batch + 1;
+    int *tab = ctx->pin_tables;
+    ctx->h_seg.assign(B + 1, 0);
+    ctx->total_tiles.assign(std::max(nr, 1), 0);
+    tab[0] = 0;
+    for (int b = 0; b < B; ++b) tab[b + 1] = tab[b] + L[b];
+    for (int b = 0; b <= B; ++b) ctx->h_seg[b] = tab[b];
+    for (int r = 0; r < std::max(nr, 1); ++r) {
+        int *t = tab + (size_t)(r + 1) * stride;
+        const int rate = nr ? ctx->rates[r] : 1;
+        t[0] = 0;
+        for (int b = 0; b < B; ++b) t[b + 1] = t[b] + (int)(((int64_t)L[b] * rate + 127) / 128);
+        ctx->total_tiles[r] = t[B];
+    }
+    CK(ctx, cudaMemcpyAsync(ctx->d_seg, tab, sizeof(int) * (B + 1), cudaMemcpyHostToDevice, ctx->stream));
+    for (int r = 0; r < std::max(nr, 1); ++r)
+        CK(ctx, cudaMemcpyAsync(ctx->d_tiles + (size_t)r * stride, tab + (size_t)(r + 1) * stride, sizeof(int) * (B + 1),
+                                cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaEventRecord(ctx->tables_event, ctx->stream));
+    ctx->tables_pending = true;
+    ctx->last_B = B;
+    ctx->last_frames = frames;
+    return 0;
+}
+
+// ---------------------------------------------------------------- conv launch helper
+struct ConvCall {
+    const ConvLayer *L = nullptr;
+    int variant = 0;
+    const void *x = nullptr; int ldx = 0, x_ch_off = 0;
+    int rate_idx = 0;          // index into ctx->rates of the INPUT rate
+    int pro_mode = PRO_CVT; float pro_slope = 0.f;
+    const float *mu = nullptr, *rstd = nullptr; int stat_stride = 0;
+    const float *g = nullptr, *b = nullptr; int gb_stride = 0;
+    bool use_bias = true;
+    const float *res = nullptr; int ldres = 0, res_ch_off = 0;
+    const float *acc_in = nullptr;
+    float scale = 0.f;
+    float *out32 = nullptr; int ldo32 = 0, o32_ch_off = 0;
+    __half *out16 = nullptr; int ldo16 = 0, o16_ch_off = 0; float out16_slope = 0.f;
+    int out_mul = 1;
+};
+
+int run_conv(zvx_ctx *ctx, const ConvCall &cc)
+{
+    const ConvLayer &L = *cc.L;
+    const ConvVariant &v = L.var[cc.variant];
+    ConvParams p;
+    memset(&p, 0, sizeof p);
+    p.x = cc.x; p.ldx = cc.ldx; p.x_ch_off = cc.x_ch_off; p.Cin = L.IC;
+    p.seg_start = ctx->d_seg;
+    p.tile_start = ctx->d_tiles + (size_t)cc.rate_idx * (ctx->cap_batch + 1);
+    p.B = ctx->last_B;
+    p.rate_in = ctx->rates.empty() ? 1 : ctx->rates[cc.rate_idx];
+    p.ntaps = v.ntaps; p.tap_off0 = v.tap_off0; p.tap_step = v.tap_step;
+    p.w_packed = v.packed; p.w_raw = L.raw; p.w_taps_total = L.K; p.w_tap0 = v.w_tap0; p.w_tap_stride = v.w_tap_stride;
+    p.Cout = L.OC; p.NC = L.NC;
+    p.pro_mode = cc.pro_mode; p.pro_slope = cc.pro_slope;
+    p.p_mu = cc.mu; p.p_rstd = cc.rstd; p.p_stat_stride = cc.stat_stride;
+    p.p_g = cc.g; p.p_b = cc.b; p.p_gb_stride = cc.gb_stride;
+    p.bias = cc.use_bias ? L.bias : nullptr;
+    p.res = cc.res; p.ldres = cc.ldres; p.res_ch_off = cc.res_ch_off;
+    p.acc_in = cc.acc_in;
+    p.has_scale = cc.scale != 0.f; p.scale = cc.scale;
+    p.out32 = cc.out32; p.ldo32 = cc.ldo32; p.o32_ch_off = cc.o32_ch_off;
+    p.out16 = cc.out16; p.ldo16 = cc.ldo16; p.o16_ch_off = cc.o16_ch_off; p.out16_slope = cc.out16_slope;
+    p.out_mul = cc.out_mul; p.out_add = v.out_add;
+    p.err_flag = ctx->d_err;
+    const int tiles = ctx->total_tiles[cc.rate_idx];
+    ctx->launches++;
+    if (ctx->use_ref_kernels) {
+        CK(ctx, conv_ref_launch(p, tiles, ctx->stream));
+    } else {
+        const size_t smem = conv_umma_plan(p, 100 * 1024);
+        if (smem > 227 * 1024) return fail(ctx, "conv needs %zu bytes of shared memory", smem);
+        CK(ctx, conv_umma_launch(p, tiles, smem, ctx->stream));
+    }
+    return 0;
+}
+
+int run_stats(zvx_ctx *ctx, const float *x, int ld, int ch_off, int C)
+{
+    ctx->launches++;
+    CK(ctx, stats_launch(x, ld, ch_off, C, ctx->d_seg, ctx->last_B, 1, ctx->mu, ctx->rstd, ctx->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------- decoder schedule
+// enc_in [F][D] and style [B][S] are already on the device.
+int run_decoder(zvx_ctx *ctx, float *mel_out)
+{
+    const zvx_config &c = ctx->cfg;
+    const int D = c.dim_in, BN = 2 * D, R = c.residual_dim, CAT = BN + R;
+    const float inv_sqrt2 = (float)(1.0 / std::sqrt(2.0));
+
+    ctx->launches++;
+    CK(ctx, adain_fc_launch(ctx->adain, ctx->style, ctx->last_B, ctx->adain_gb, ctx->stream));
+
+    // ---- encode.0 / encode.1 : ResBlk1d (stylettsdec.cpp:69-149) ----
+    const float *x = ctx->enc_in; int ldx = D;
+    float *enc_out[2] = {ctx->e0, ctx->catA};
+    int enc_ld[2] = {BN, CAT};
+    float *enc_h[2] = {ctx->h528, ctx->h1056};
+    for (int i = 0; i < 2; ++i) {
+        ResBlkW &b = ctx->enc[i];
+        const float *sc = x; int ldsc = ldx;
+        if (b.learned_sc) {
+            ConvCall s; s.L = &b.conv1x1; s.x = x; s.ldx = ldx; s.pro_mode = PRO_CVT; s.use_bias = false;
+            s.out32 = ctx->sc; s.ldo32 = b.cout;
+            if (run_conv(ctx, s)) return 1;
+            sc = ctx->sc; ldsc = b.cout;
+        }
+        if (run_stats(ctx, x, ldx, 0, b.cin)) return 1;
+        ConvCall c1; c1.L = &b.conv1; c1.x = x; c1.ldx = ldx; c1.pro_mode = PRO_NORM; c1.pro_slope = 0.2f;
+        c1.mu = ctx->mu; c1.rstd = ctx->rstd; c1.stat_stride = b.cin; c1.g = b.n1w; c1.b = b.n1b; c1.gb_stride = 0;
+        c1.out32 = enc_h[i]; c1.ldo32 = b.cin;
+        if (run_conv(ctx, c1)) return 1;
+        if (run_stats(ctx, enc_h[i], b.cin, 0, b.cin)) return 1;
+        ConvCall c2; c2.L = &b.conv2; c2.x = enc_h[i]; c2.ldx = b.cin; c2.pro_mode = PRO_NORM; c2.pro_slope = 0.2f;
+        c2.mu = ctx->mu; c2.rstd = ctx->rstd; c2.stat_stride = b.cin; c2.g = b.n2w; c2.b = b.n2b; c2.gb_stride = 0;
+        c2.res = sc; c2.ldres = ldsc; c2.scale = inv_sqrt2;
+        c2.out32 = enc_out[i]; c2.ldo32 = enc_ld[i];
+        if (run_conv(ctx, c2)) return 1;
+        x = enc_out[i]; ldx = enc_ld[i];
+    }
+    // ---- asr_res = IN_affine(conv1x1(enc_seq) + b)  (stylettsdec.cpp:382-396), into both concat buffers ----
+    {
+        ConvCall a; a.L = &ctx->asr0; a.x = ctx->enc_in; a.ldx = D; a.pro_mode = PRO_CVT; a.out32 = ctx->asr; a.ldo32 = R;
+        if (run_conv(ctx, a)) return 1;
+        if (run_stats(ctx, ctx->asr, R, 0, R)) return 1;
+        ctx->launches++;
+        CK(ctx, norm_affine_launch(ctx->asr, R, R, ctx->d_seg, ctx->last_B, ctx->mu, ctx->rstd, ctx->asr1w, ctx->asr1b,
+                                   ctx->catA, ctx->catB, CAT, BN, ctx->stream));
+    }
+    // ---- decode.0-4 : AdainResBlk1d (stylettsdec.cpp:242-304) ----
+    const float *din[5]  = {ctx->catA, ctx->catB, ctx->catA, ctx->d1, ctx->d2};
+    const int    dinl[5] = {CAT, CAT, CAT, D, D};
+    float       *dout[5] = {ctx->catB, ctx->catA, ctx->d1, ctx->d2, ctx->d1};
+    const int    doutl[5] = {CAT, CAT, D, D, D};
+    for (int i = 0; i < 5; ++i) {
+        AdaBlkW &b = ctx->dec[i];
+        const AdainDesc &a1 = ctx->adain.d[b.ada1], &a2 = ctx->adain.d[b.ada2];
+        float *h = b.cout == BN ? ctx->h1056 : ctx->h528;
+        if (run_stats(ctx, din[i], dinl[i], 0, b.cin)) return 1;
+        ConvCall c1; c1.L = &b.conv1; c1.x = din[i]; c1.ldx = dinl[i]; c1.pro_mode = PRO_NORM; c1.pro_slope = 0.2f;
+        c1.mu = ctx->mu; c1.rstd = ctx->rstd; c1.stat_stride = b.cin;
+        c1.g = ctx->adain_gb + a1.out_off; c1.b = ctx->adain_gb + a1.out_off + a1.C; c1.gb_stride = ctx->adain.total;
+        c1.out32 = h; c1.ldo32 = b.cout;
+        if (run_conv(ctx, c1)) return 1;
+        const float *sc = din[i]; int ldsc = dinl[i];
+        if (b.learned_sc) {
+            ConvCall s; s.L = &b.conv1x1; s.x = din[i]; s.ldx = dinl[i]; s.pro_mode = PRO_CVT; s.use_bias = false;
+            s.out32 = ctx->sc; s.ldo32 = b.cout;
+            if (run_conv(ctx, s)) return 1;
+            sc = ctx->sc; ldsc = b.cout;
+        }
+        if (run_stats(ctx, h, b.cout, 0, b.cout)) return 1;
+        ConvCall c2; c2.L = &b.conv2; c2.x = h; c2.ldx = b.cout; c2.pro_mode = PRO_NORM; c2.pro_slope = 0.2f;
+        c2.mu = ctx->mu; c2.rstd = ctx->rstd; c2.stat_stride = b.cout;
+        c2.g = ctx->adain_gb + a2.out_off; c2.b = ctx->adain_gb + a2.out_off + a2.C; c2.gb_stride = ctx->adain.total;
+        c2.res = sc; c2.ldres = ldsc; c2.scale = inv_sqrt2;
+        c2.out32 = dout[i]; c2.ldo32 = doutl[i];
+        if (run_conv(ctx, c2)) return 1;
+    }
+    // ---- to_out (stylettsdec.cpp:432-441) ----
+    ConvCall o; o.L = &ctx->to_out; o.x = dout[4]; o.ldx = D; o.pro_mode = PRO_CVT; o.out32 = mel_out; o.ldo32 = c.num_mels;
+    return run_conv(ctx, o);
+}
+
+// ---------------------------------------------------------------- vocoder schedule
+int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out)
+{
+    const zvx_config &c = ctx->cfg;
+    const int nb = c.num_resblocks, nd = c.num_resblock_dilations;
+    // (mel - mean) / scale -> input_conv (hifigan.cpp:242-265)
+    {
+        ConvCall ic; ic.L = &ctx->input_conv; ic.x = mel_in; ic.ldx = c.num_mels; ic.pro_mode = PRO_MEL;
+        ic.mu = ctx->mel_mean; ic.rstd = ctx->mel_scale; ic.stat_stride = 0;
+        ic.out32 = ctx->v0; ic.ldo32 = ctx->chans[0];
+        if (run_conv(ctx, ic)) return 1;
+    }
+    const float *vin = ctx->v0;
+    float *vout[2] = {ctx->VA, ctx->VB};
+    const float third = (float)(1.0 / (float)nb);
+    for (int i = 0; i < c.num_upsamples; ++i) {
+        if (ctx->debug_stop >= 0 && i >= ctx->debug_stop) return 0;
+        const int cin = ctx->chans[i], ch = ctx->chans[i + 1];
+        const int s = c.upsample_scales[i];
+        // leaky_relu(0.1) -> ConvTranspose1d, one launch per output phase (hifigan.cpp:281-297, :22-71)
+        for (int phi = 0; phi < s; ++phi) {
+            ConvCall u; u.L = &ctx->up[i]; u.variant = phi; u.x = vin; u.ldx = cin; u.rate_idx = i;
+            u.pro_mode = PRO_LRELU; u.pro_slope = 0.1f; u.out32 = ctx->U; u.ldo32 = ch; u.out_mul = s;
+            if (run_conv(ctx, u)) return 1;
+        }
+        // MRF: three residual blocks on U, averaged (hifigan.cpp:300-315, :97-183)
+        for (int j = 0; j < nb; ++j) {
+            float *Y = (j == 0) ? ctx->CS : ctx->Y1;
+            for (int d = 0; d < nd; ++d) {
+                const size_t idx = ((size_t)i * nb + j) * nd + d;
+                const float *yin = d == 0 ? ctx->U : Y;
+                ConvCall c1; c1.L = &ctx->mrf1[idx]; c1.x = yin; c1.ldx = ch; c1.rate_idx = i + 1;
+                c1.pro_mode = PRO_LRELU; c1.pro_slope = 0.1f;
+                c1.out16 = ctx->H16; c1.ldo16 = ch; c1.out16_slope = 0.1f;
+                if (run_conv(ctx, c1)) return 1;
+                ConvCall c2; c2.L = &ctx->mrf2[idx]; c2.x = ctx->H16; c2.ldx = ch; c2.rate_idx = i + 1; c2.pro_mode = PRO_F16;
+                c2.res = yin; c2.ldres = ch;
+                const bool last = d == nd - 1;
+                if (last && j > 0) {
+                    c2.acc_in = ctx->CS;                       // cs = cs + y_j
+                    if (j == nb - 1) { c2.scale = third; c2.out32 = vout[i & 1]; }   // c = cs / num_blocks
+                    else c2.out32 = ctx->CS;
+                } else {
+                    c2.out32 = Y;
+                }
+                c2.ldo32 = ch;
+                if (run_conv(ctx, c2)) return 1;
+            }
+        }
+        vin = vout[i & 1];
+    }
+    if (ctx->debug_stop >= 0) return 0;
+    // leaky_relu(0.01) -> output_conv -> tanh (hifigan.cpp:324-345)
+    const int last = c.num_upsamples;
+    ctx->launches++;
+    CK(ctx, out_conv_launch(vin, ctx->chans[last], ctx->output_conv.K, ctx->output_conv.raw, ctx->output_conv.bias, 0.01f,
+                            ctx->d_seg, ctx->d_tiles + (size_t)last * (ctx->cap_batch + 1), ctx->last_B, ctx->rates[last],
+                            ctx->total_tiles[last], wav_out, ctx->stream));
+    return 0;
+}
+
+int check_device_error(zvx_ctx *ctx)
+{
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    int flag = 0;
+    CK(ctx, cudaMemcpy(&flag, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (flag) return fail(ctx, "device pipeline timeout flag set");
+    return 0;
+}
+
+int ensure_pinned(zvx_ctx *ctx, float **buf, size_t *cap, size_t n)
+{
+    if (n <= *cap) return 0;
+    if (*buf) cudaFreeHost(*buf);
+    *buf = nullptr;
+    *cap = 0;
+    CK(ctx, cudaMallocHost(buf, n * sizeof(float)));
+    *cap = n;
+    return 0;
+}
+
+}  // namespace
+
+// ====================================================================== C ABI
+extern "C" {
+
+void zvx_default_config(zvx_config *cfg)
+{
+    memset(cfg, 0, sizeof *cfg);
+    cfg->device = 0;
+    cfg->dim_in = 528;
+    cfg->style_dim = 528;
+    cfg->residual_dim = 64;
+    cfg->num_mels = 80;
+    cfg->hop_size = 300;
+    cfg->kernel_size = 7;
+    cfg->num_upsamples = 4;
+    const int s[4] = {5, 5, 4, 3};
+    for (int i = 0; i < 4; ++i) cfg->upsample_scales[i] = s[i];
+    cfg->num_resblocks = 3;
+    cfg->num_resblock_dilations = 3;
+    const int d[9] = {1, 3, 5, 1, 3, 5, 1, 3, 5};
+    for (int i = 0; i < 9; ++i) cfg->resblock_dilations[i] = d[i];
+    cfg->with_decoder = 1;
+    cfg->with_vocoder = 1;
+}
+
+const char *zvx_last_error(const zvx_ctx *ctx)
+{
+    return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+void zvx_destroy(zvx_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (void *p : ctx->owned) cudaFree(p);
+    if (ctx->pin_tables) cudaFreeHost(ctx->pin_tables);
+    if (ctx->pin_in) cudaFreeHost(ctx->pin_in);
+    if (ctx->pin_out) cudaFreeHost(ctx->pin_out);
+    if (ctx->tables_event) cudaEventDestroy(ctx->tables_event);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int zvx_create(zvx_ctx **out, const zvx_config *cfg, const zvx_tensor_desc *weights, int32_t n_weights)
+{
+    if (!out || !cfg) return fail(nullptr, "zvx_create: null argument");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(nullptr, "zvx_create: no CUDA device (this library has no CPU fallback)");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, "zvx_create: device %d out of range", cfg->device);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return fail(nullptr, "cudaGetDeviceProperties failed");
+    if (prop.major != 10)
+        return fail(nullptr, "zvx_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", cfg->device,
+                    prop.major, prop.minor);
+    if (cfg->num_upsamples < 0 || cfg->num_upsamples > 8 || cfg->num_resblocks * cfg->num_resblock_dilations > 32)
+        return fail(nullptr, "zvx_create: unsupported topology");
+
+    zvx_ctx *ctx = new zvx_ctx();
+    ctx->cfg = *cfg;
+    ctx->device = cfg->device;
+    auto bail = [&](void) { g_create_error = ctx->err; zvx_destroy(ctx); return 1; };
+#define CKC(call)                                                                              \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            fail(ctx, "%s failed: %s", #call, cudaGetErrorString(e__));                        \
+            return bail();                                                                     \
+        }                                                                                      \
+    } while (0)
+    CKC(cudaSetDevice(ctx->device));
+    CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CKC(cudaEventCreateWithFlags(&ctx->tables_event, cudaEventDisableTiming));
+    CKC(conv_umma_init());
+    if (dev_alloc(ctx, &ctx->d_err, 1)) return bail();
+    CKC(cudaMemset(ctx->d_err, 0, sizeof(int)));
+
+    HostW hw;
+    for (int i = 0; i < n_weights; ++i) {
+        const zvx_tensor_desc &t = weights[i];
+        if (!t.name || !t.data) { fail(ctx, "weight %d has null name/data", i); return bail(); }
+        if (t.dtype != ZVX_F32 && t.dtype != ZVX_F16) { fail(ctx, "tensor '%s': unsupported dtype %d", t.name, t.dtype); return bail(); }
+        DevTensor d;
+        d.dtype = t.dtype;
+        d.nd = t.n_dims;
+        size_t n = 1;
+        for (int k = 0; k < 4; ++k) { d.ne[k] = k < t.n_dims ? t.ne[k] : 1; n *= (size_t)d.ne[k]; }
+        d.nbytes = n * (t.dtype == ZVX_F16 ? 2 : 4);
+        void *p = nullptr;
+        CKC(cudaMalloc(&p, d.nbytes));
+        ctx->owned.push_back(p);
+        CKC(cudaMemcpy(p, t.data, d.nbytes, cudaMemcpyHostToDevice));
+        d.d = p;
+        ctx->W[t.name] = d;
+        if (t.dtype == ZVX_F16) {
+            const __half *h = reinterpret_cast<const __half *>(t.data);
+            hw.h[t.name].assign(h, h + n);
+        }
+    }
+    if (cfg->with_decoder && build_decoder(ctx, hw)) return bail();
+    if (cfg->with_vocoder && build_vocoder(ctx, hw)) return bail();
+    if (!cfg->with_vocoder) { ctx->rates.assign(1, 1); ctx->chans.assign(1, 0); }
+    if (reserve(ctx, 512, 8)) return bail();
+    CKC(cudaStreamSynchronize(ctx->stream));
+#undef CKC
+    *out = ctx;
+    return 0;
+}
+
+void *zvx_stream(zvx_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int zvx_synchronize(zvx_ctx *ctx)
+{
+    if (!ctx) return 1;
+    CK(ctx, cudaSetDevice(ctx->device));
+    return check_device_error(ctx);
+}
+
+int64_t zvx_kernel_launches(const zvx_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int zvx_reserve(zvx_ctx *ctx, int64_t total_frames, int32_t max_batch)
+{
+    if (!ctx) return 1;
+    CK(ctx, cudaSetDevice(ctx->device));
+    return reserve(ctx, total_frames, max_batch);
+}
+
+void zvx_set_debug_kernels(zvx_ctx *ctx, int32_t v) { if (ctx) ctx->use_ref_kernels = v; }
+void zvx_set_debug_stop(zvx_ctx *ctx, int32_t s) { if (ctx) ctx->debug_stop = s; }
+
+int zvx_synth_batch_device(zvx_ctx *ctx, int32_t B, const float *d_enc, const float *d_style, const int32_t *L,
+                           float *d_mel, float *d_wav, int32_t sync)
+{
+    if (!ctx) return 1;
+    if (!ctx->cfg.with_decoder || !ctx->cfg.with_vocoder) return fail(ctx, "context was built without decoder or vocoder");
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (set_batch(ctx, B, L)) return 1;
+    const int64_t F = ctx->last_frames;
+    // the schedule reads its inputs from the workspace: D2D copies keep the public pointers const
+    CK(ctx, cudaMemcpyAsync(ctx->enc_in, d_enc, sizeof(float) * F * ctx->cfg.dim_in, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(ctx, cudaMemcpyAsync(ctx->style, d_style, sizeof(float) * (size_t)B * ctx->cfg.style_dim, cudaMemcpyDeviceToDevice, ctx->stream));
+    float *mel = d_mel ? d_mel : ctx->mel;
+    if (run_decoder(ctx, mel)) return 1;
+    if (run_vocoder(ctx, mel, d_wav)) return 1;
+    return sync ? check_device_error(ctx) : 0;
+}
+
+int zvx_vocode_batch_device(zvx_ctx *ctx, int32_t B, const float *d_mel, const int32_t *L, float *d_wav, int32_t sync)
+{
+    if (!ctx) return 1;
+    if (!ctx->cfg.with_vocoder) return fail(ctx, "context was built without vocoder");
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (set_batch(ctx, B, L)) return 1;
+    if (run_vocoder(ctx, d_mel, d_wav)) return 1;
+    return sync ? check_device_error(ctx) : 0;
+}
+
+int zvx_synth_batch(zvx_ctx *ctx, int32_t B, const float *const *enc_seq, const float *const *style, const int32_t *L,
+                    float *const *mel, float *const *wav)
+{
+    if (!ctx) return 1;
+    if (!ctx->cfg.with_decoder || !ctx->cfg.with_vocoder) return fail(ctx, "context was built without decoder or vocoder");
+    if (!enc_seq || !style || !L || !wav) return fail(ctx, "zvx_synth_batch: null argument");
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (set_batch(ctx, B, L)) return 1;
+    const zvx_config &c = ctx->cfg;
+    const int64_t F = ctx->last_frames;
+    for (int b = 0; b < B; ++b) {
+        CK(ctx, cudaMemcpyAsync(ctx->enc_in + (size_t)ctx->h_seg[b] * c.dim_in, enc_seq[b], sizeof(float) * (size_t)L[b] * c.dim_in,
+                                cudaMemcpyHostToDevice, ctx->stream));
+        CK(ctx, cudaMemcpyAsync(ctx->style + (size_t)b * c.style_dim, style[b], sizeof(float) * c.style_dim, cudaMemcpyHostToDevice,
+                                ctx->stream));
+    }
+    if (run_decoder(ctx, ctx->mel)) return 1;
+    if (run_vocoder(ctx, ctx->mel, ctx->wav)) return 1;
+    for (int b = 0; b < B; ++b) {
+        if (mel && mel[b])
+            CK(ctx, cudaMemcpyAsync(mel[b], ctx->mel + (size_t)ctx->h_seg[b] * c.num_mels, sizeof(float) * (size_t)L[b] * c.num_mels,
+                                    cudaMemcpyDeviceToHost, ctx->stream));
+        CK(ctx, cudaMemcpyAsync(wav[b], ctx->wav + (size_t)ctx->h_seg[b] * c.hop_size, sizeof(float) * (size_t)L[b] * c.hop_size,
+                                cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    (void)F;
+    return check_device_error(ctx);
+}
+
+int zvx_decode(zvx_ctx *ctx, const float *enc_seq, const float *style, int32_t L, float *mel)
+{
+    if (!ctx) return 1;
+    if (!ctx->cfg.with_decoder) return fail(ctx, "context was built without decoder");
+    if (!enc_seq || !style || !mel) return fail(ctx, "zvx_decode: null argument");
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (set_batch(ctx, 1, &L)) return 1;
+    const zvx_config &c = ctx->cfg;
+    CK(ctx, cudaMemcpyAsync(ctx->enc_in, enc_seq, sizeof(float) * (size_t)L * c.dim_in, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaMemcpyAsync(ctx->style, style, sizeof(float) * c.style_dim, cudaMemcpyHostToDevice, ctx->stream));
+    if (run_decoder(ctx, ctx->mel)) return 1;
+    CK(ctx, cudaMemcpyAsync(mel, ctx->mel, sizeof(float) * (size_t)L * c.num_mels, cudaMemcpyDeviceToHost, ctx->stream));
+    return check_device_error(ctx);
+}
+
+int zvx_vocode(zvx_ctx *ctx, const float *mel, int32_t L, float *wav)
+{
+    if (!ctx) return 1;
+    if (!ctx->cfg.with_vocoder) return fail(ctx, "context was built without vocoder");
+    if (!mel || !wav) return fail(ctx, "zvx_vocode: null argument");
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (set_batch(ctx, 1, &L)) return 1;
+    const zvx_config &c = ctx->cfg;
+    CK(ctx, cudaMemcpyAsync(ctx->mel, mel, sizeof(float) * (size_t)L * c.num_mels, cudaMemcpyHostToDevice, ctx->stream));
+    if (run_vocoder(ctx, ctx->mel, ctx->wav)) return 1;
+    if (ctx->debug_stop < 0)
+        CK(ctx, cudaMemcpyAsync(wav, ctx->wav, sizeof(float) * (size_t)L * c.hop_size, cudaMemcpyDeviceToHost, ctx->stream));
+    return check_device_error(ctx);
+}
+
+int zvx_debug_fetch(zvx_ctx *ctx, const char *what, float *dst, int64_t n)
+{
+    if (!ctx || !what || !dst) return 1;
+    CK(ctx, cudaSetDevice(ctx->device));
+    const std::string w = what;
+    const float *src = nullptr;
+    int64_t have = 0;
+    const int64_t F = ctx->last_frames;
+    if (w == "mel") { src = ctx->mel; have = F * ctx->cfg.num_mels; }
+    else if (w == "v0") { src = ctx->v0; have = F * ctx->chans[0]; }
+    else if (w == "u") { src = ctx->U; have = F * max_stage_elems(ctx); }
+    else if (w.rfind("stage", 0) == 0 && w.size() == 6) {
+        const int i = w[5] - '0';
+        if (i < 0 || i >= ctx->cfg.num_upsamples) return fail(ctx, "bad stage");
+        src = (i & 1) ? ctx->VB : ctx->VA;
+        have = F * ctx->rates[i + 1] * ctx->chans[i + 1];
+    } else return fail(ctx, "unknown debug tensor '%s'", what);
+    if (n > have) return fail(ctx, "debug tensor '%s' has %lld floats, asked for %lld", what, (long long)have, (long long)n);
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    CK(ctx, cudaMemcpy(dst, src, sizeof(float) * n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int zvx_test_conv(zvx_ctx *ctx, const zvx_conv_test *t)
+{
+    if (!ctx || !t) return 1;
+    CK(ctx, cudaSetDevice(ctx->device));
+    // rows play the role of frames at rate index 0 (rate 1)
+    int rc = 1;
+    std::vector<void *> tmp;
+    auto talloc = [&](size_t bytes) -> void * {
+        void *p = nullptr;
+        if (cudaMalloc(&p, std::max<size_t>(bytes, 16)) != cudaSuccess) return nullptr;
+        tmp.push_back(p);
+        return p;
+    };
+    do {
+        if (set_batch(ctx, t->B, t->rows, false)) break;
+        const int64_t R = ctx->last_frames;
+        ConvLayer L;
+        L.OC = t->Cout; L.IC = t->Cin; L.K = t->K; L.NC = pick_nc(t->Cout);
+        if (L.NC == 0 || t->Cout % 16 || t->Cin % 16) { fail(ctx, "zvx_test_conv: unsupported channels"); break; }
+        const size_t wn = (size_t)t->Cout * t->Cin * t->K;
+        __half *d_raw = (__half *)talloc(wn * 2);
+        if (!d_raw || cudaMemcpy(d_raw, t->w, wn * 2, cudaMemcpyHostToDevice) != cudaSuccess) { fail(ctx, "alloc/copy w"); break; }
+        L.raw = d_raw;
+        float *d_bias = nullptr;
+        if (t->bias) {
+            d_bias = (float *)talloc(sizeof(float) * t->Cout);
+            if (!d_bias || cudaMemcpy(d_bias, t->bias, sizeof(float) * t->Cout, cudaMemcpyHostToDevice) != cudaSuccess) { fail(ctx, "alloc/copy bias"); break; }
+        }
+        L.bias = d_bias;
+        ConvVariant v;
+        v.ntaps = t->K; v.w_tap0 = 0; v.w_tap_stride = 1; v.tap_step = t->dilation; v.tap_off0 = -t->pad; v.out_add = 0;
+        std::vector<__half> hraw((const __half *)t->w, (const __half *)t->w + wn);
+        if (pack_variant(ctx, hraw, L.OC, L.IC, L.K, L.NC, v)) break;
+        L.var.push_back(v);
+        ConvCall cc;
+        cc.L = &L;
+        cc.pro_mode = t->pro_mode; cc.pro_slope = t->pro_slope;
+        void *d_x;
+        if (t->pro_mode == PRO_F16) {
+            d_x = talloc((size_t)R * t->Cin * 2);
+            if (!d_x || cudaMemcpy(d_x, t->x16, (size_t)R * t->Cin * 2, cudaMemcpyHostToDevice) != cudaSuccess) { fail(ctx, "alloc/copy x16"); break; }
+        } else {
+            d_x = talloc((size_t)R * t->Cin * 4);
+            if (!d_x || cudaMemcpy(d_x, t->x, (size_t)R * t->Cin * 4, cudaMemcpyHostToDevice) != cudaSuccess) { fail(ctx, "alloc/copy x"); break; }
+        }
+        cc.x = d_x; cc.ldx = t->Cin;
+        auto up = [&](const float *h, size_t n) -> float * {
+            if (!h) return nullptr;
+            float *d = (float *)talloc(n * 4);
+            if (d && cudaMemcpy(d, h, n * 4, cudaMemcpyHostToDevice) != cudaSuccess) d = nullptr;
+            return d;
+        };
+        if (t->pro_mode == PRO_NORM) {
+            cc.mu = up(t->mu, (size_t)t->B * t->Cin); cc.rstd = up(t->rstd, (size_t)t->B * t->Cin); cc.stat_stride = t->Cin;
+            cc.g = up(t->g, (size_t)t->B * t->Cin); cc.b = up(t->b, (size_t)t->B * t->Cin); cc.gb_stride = t->Cin;
+            if (!cc.mu || !cc.rstd || !cc.g || !cc.b) { fail(ctx, "norm params missing"); break; }
+        } else if (t->pro_mode == PRO_MEL) {
+            cc.mu = up(t->mu, t->Cin); cc.rstd = up(t->rstd, t->Cin); cc.stat_stride = 0;
+            if (!cc.mu || !cc.rstd) { fail(ctx, "mel params missing"); break; }
+        }
+        cc.use_bias = t->bias != nullptr;
+        if (t->res) { cc.res = up(t->res, (size_t)R * t->Cout); cc.ldres = t->Cout; if (!cc.res) { fail(ctx, "res"); break; } }
+        cc.scale = t->scale;
+        float *d_out = (float *)talloc((size_t)R * t->Cout * 4);
+        __half *d_out16 = t->out16 ? (__half *)talloc((size_t)R * t->Cout * 2) : nullptr;
+        if (!d_out) { fail(ctx, "alloc out"); break; }
+        cudaMemsetAsync(d_out, 0xff, (size_t)R * t->Cout * 4, ctx->stream);
+        cc.out32 = d_out; cc.ldo32 = t->Cout;
+        cc.out16 = d_out16; cc.ldo16 = t->Cout; cc.out16_slope = t->out16_slope;
+        const int saved = ctx->use_ref_kernels;
+        ctx->use_ref_kernels = t->use_validation_kernel;
+        const int r = run_conv(ctx, cc);
+        ctx->use_ref_kernels = saved;
+        if (r) break;
+        if (check_device_error(ctx)) break;
+        if (cudaMemcpy(t->out, d_out, (size_t)R * t->Cout * 4, cudaMemcpyDeviceToHost) != cudaSuccess) { fail(ctx, "copy out"); break; }
+        if (t->out16 && cudaMemcpy(t->out16, d_out16, (size_t)R * t->Cout * 2, cudaMemcpyDeviceToHost) != cudaSuccess) { fail(ctx, "copy out16"); break; }
+        if (v.packed) dev_free(ctx, v.packed);
+        rc = 0;
+    } while (0);
+    for (void *p : tmp) cudaFree(p);
+    return rc;
+}
+
+}  // extern "C"

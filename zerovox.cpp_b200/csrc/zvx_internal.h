@@ -1,0 +1,51 @@
+// zvx_internal.h -- host-side declarations shared by the .cu translation units.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stddef.h>
+
+#include "zvx_common.cuh"
+
+namespace zvx {
+
+// conv_umma.cu -----------------------------------------------------------------------
+// Fill p.a_rows / a_stages / b_stages / tmem_cols; returns the dynamic smem bytes.
+size_t      conv_umma_plan(ConvParams &p, size_t smem_budget);
+cudaError_t conv_umma_init();   // once per device: opt in to > 48 KB dynamic smem
+cudaError_t conv_umma_launch(const ConvParams &p, int total_tiles, size_t smem, cudaStream_t st);
+
+// conv_ref.cu (validation kernel: plain CUDA cores, same prologue/epilogue arithmetic) ---
+cudaError_t conv_ref_launch(const ConvParams &p, int total_tiles, cudaStream_t st);
+
+// aux_kernels.cu ---------------------------------------------------------------------
+// per-(utterance, channel) InstanceNorm statistics over the utterance's rows
+cudaError_t stats_launch(const float *x, int ld, int ch_off, int C, const int *seg_start, int B, int rate,
+                         float *mu, float *rstd, cudaStream_t st);
+
+struct AdainDesc {
+    const float *fc_w;    // (2C, style_dim) row-major
+    const float *fc_b;    // (2C)
+    int C;
+    int out_off;          // gamma1 at out_off, beta at out_off + C inside one utterance's row
+};
+constexpr int MAX_ADAIN = 16;
+struct AdainTable {
+    AdainDesc d[MAX_ADAIN];
+    int n;
+    int total;            // sum of 2C
+    int style_dim;
+};
+cudaError_t adain_fc_launch(const AdainTable &tab, const float *style, int B, float *out, cudaStream_t st);
+
+// y = ((x-mu)*rstd)*w + b for an [rows][C] fp32 tensor, written to up to two destinations
+cudaError_t norm_affine_launch(const float *x, int ldx, int C, const int *seg_start, int B, const float *mu,
+                               const float *rstd, const float *w, const float *b, float *dst0, float *dst1, int ld_dst,
+                               int dst_ch_off, cudaStream_t st);
+
+// wav = tanh(conv_k(leaky_relu(x, slope)) + b), single output channel
+cudaError_t out_conv_launch(const float *x, int C, int K, const __half *w_raw, const float *bias, float slope,
+                            const int *seg_start, const int *tile_start, int B, int rate, int total_tiles, float *wav,
+                            cudaStream_t st);
+
+}  // namespace zvx
