@@ -100,6 +100,23 @@ int   zvx_synchronize(zvx_ctx *ctx);
 int64_t zvx_kernel_launches(const zvx_ctx *ctx); /* kernels launched by this ctx so far */
 int   zvx_reserve(zvx_ctx *ctx, int64_t total_frames, int32_t max_batch);
 
+/* Per-launch timing with CUDA events recorded on the ctx stream around every kernel this
+ * library launches between zvx_profile_begin and zvx_profile_end (bench.py's roofline).
+ * flops / bytes are the ALGORITHMIC work of that launch. */
+enum {
+    ZVX_K_DEC_CONV = 0, ZVX_K_VOC_INPUT_CONV = 1, ZVX_K_UPCONV = 2, ZVX_K_MRF_CONV = 3, ZVX_K_OUT_CONV = 4,
+    ZVX_K_STATS = 5, ZVX_K_ADAIN_FC = 6, ZVX_K_NORM_AFFINE = 7
+};
+typedef struct zvx_launch_record {
+    int32_t kind;     /* ZVX_K_* */
+    int32_t stage;    /* vocoder stage for UPCONV / MRF_CONV / OUT_CONV, else 0 */
+    double  flops;
+    double  bytes;
+    float   ms;
+} zvx_launch_record;
+int     zvx_profile_begin(zvx_ctx *ctx);
+int64_t zvx_profile_end(zvx_ctx *ctx, zvx_launch_record *recs, int64_t max_recs); /* returns #records or -1 */
+
 /* ---- test / debug surface (used by tests/ only) ---------------------------------- */
 /* 0: tcgen05 implicit-GEMM kernels (the product path); 1: plain-CUDA validation kernels */
 void zvx_set_debug_kernels(zvx_ctx *ctx, int32_t use_validation_kernels);

@@ -141,6 +141,7 @@ int main(int argc, char **argv)
     }
 
     double t_dec_best = 1e30, t_voc_best = 1e30, t_tot_best = 1e30, t_tot_sum = 0;
+    std::string rep_list;
     for (int r = 0; r < reps; r++) {
         double t0 = now_s();
         if (do_dec) decoder->eval(enc.data(), sty.data(), mel.data());
@@ -151,6 +152,9 @@ int main(int argc, char **argv)
         if (t2 - t1 < t_voc_best) t_voc_best = t2 - t1;
         if (t2 - t0 < t_tot_best) t_tot_best = t2 - t0;
         if (r > 0 || reps == 1) t_tot_sum += t2 - t0;
+        char tmp[64];
+        snprintf(tmp, sizeof tmp, "%s%.6f", r ? ", " : "", t2 - t0);
+        rep_list += tmp;
     }
     const int timed = reps > 1 ? reps - 1 : 1;
 
@@ -161,8 +165,8 @@ int main(int argc, char **argv)
 
     fprintf(stderr,
             "{\"L\": %u, \"threads\": %d, \"reps\": %d, \"stage\": \"%s\", \"dec_s\": %.6f, \"voc_s\": %.6f, "
-            "\"total_best_s\": %.6f, \"total_mean_s\": %.6f, \"audio_s\": %.6f}\n",
+            "\"total_best_s\": %.6f, \"total_mean_s\": %.6f, \"audio_s\": %.6f, \"rep_s\": [%s]}\n",
             L, threads, reps, stage.c_str(), do_dec ? t_dec_best : 0.0, do_voc ? t_voc_best : 0.0,
-            t_tot_best, t_tot_sum / timed, (double)L * hop / 24000.0);
+            t_tot_best, t_tot_sum / timed, (double)L * hop / 24000.0, rep_list.c_str());
     return 0;
 }

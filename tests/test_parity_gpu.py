@@ -1,0 +1,128 @@
+"""GPU parity of the whole hot path through the C ABI against the UNMODIFIED reference.
+
+Tolerances (north_star): waveform max-abs error <= 1e-3 and SNR >= 60 dB vs the fp32 ggml CPU path.
+The reference rounds every conv input to fp16 (ggml.c:3776), which makes the network chaotic at the
+fp16-ulp level: the SAME reference compiled for AVX2 instead of AVX-512 differs from itself by
+mel ~60.4-61 dB, end-to-end wav ~61.9 dB, vocoder-only ~65.7 dB on this model (tests/golden/*_v3).
+So: vocoder-only and end-to-end are gated at the north-star 60 dB / 1e-3; the mel at 55 dB.
+"""
+import numpy as np
+import pytest
+
+import zv_oracle
+from conftest import golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("L", [48, 160, 400])
+def test_decoder_vocoder_match_reference(ctx, zvx, L):
+    g = golden(L)
+    enc, sty = zvx.synth.make_inputs(L)
+    mel = ctx.decode(enc, sty)                       # StyleTTSDecoder::eval
+    assert mel.shape == (L, 80)
+    assert zv_oracle.snr_db(g["mel"], mel) >= 55.0
+    voc = ctx.vocode(g["mel"])                       # HiFiGAN::eval fed the reference mel
+    assert voc.shape == (L * 300,)
+    assert zv_oracle.snr_db(g["wav"], voc) >= 60.0
+    assert np.abs(voc - g["wav"]).max() <= 1e-3
+    wav = ctx.vocode(mel)                            # free-running end to end
+    assert np.abs(wav - g["wav"]).max() <= 1e-3
+    assert zv_oracle.snr_db(g["wav"], wav) >= 60.0
+    assert np.all(np.isfinite(wav)) and np.abs(wav).max() < 1.0
+
+
+def test_validation_kernels_agree_with_tensor_core_path(ctx, zvx):
+    """Plain-CUDA validation kernels (fp32 FMA order) vs tcgen05 path: both sit at the reference floor."""
+    L = 48
+    g = golden(L)
+    enc, sty = zvx.synth.make_inputs(L)
+    ctx.set_debug_kernels(True)
+    try:
+        mel_v = ctx.decode(enc, sty)
+        voc_v = ctx.vocode(g["mel"])
+    finally:
+        ctx.set_debug_kernels(False)
+    assert zv_oracle.snr_db(g["mel"], mel_v) >= 55.0
+    assert zv_oracle.snr_db(g["wav"], voc_v) >= 60.0
+    assert zv_oracle.snr_db(voc_v, ctx.vocode(g["mel"])) >= 60.0
+
+
+def test_vocoder_stages_match_oracle(ctx, weights):
+    """Per-stage activations (up-conv + MRF average) against the numpy restatement's taps."""
+    L = 24
+    g = golden(48)
+    mel = g["mel"][:L]
+    o = zv_oracle.Oracle(weights)
+    o.keep_taps = True
+    o.vocoder(mel)
+    rates, chans = (5, 25, 100, 300), (256, 128, 64, 32)
+    try:
+        for i in range(4):
+            ctx.set_debug_stop(i + 1)
+            ctx.vocode(mel)
+            got = ctx.debug_fetch(f"stage{i}", L * rates[i] * chans[i]).reshape(L * rates[i], chans[i])
+            assert zv_oracle.snr_db(o.taps[f"stage{i}"], got) >= 60.0, i
+            if i == 0:
+                v0 = ctx.debug_fetch("v0", L * 512).reshape(L, 512)
+                assert np.abs(v0 - o.taps["input_conv"]).max() <= 1e-4
+    finally:
+        ctx.set_debug_stop(-1)
+
+
+def test_batched_varlen_equals_single_utterance_bit_exact(ctx, zvx):
+    """Utterances are independent: batching, order and neighbours must not change a bit."""
+    Ls = [48, 160, 33, 129]
+    ins = [zvx.synth.make_inputs(L, seed=20 + i) for i, L in enumerate(Ls)]
+    mels, wavs = ctx.synth_batch([e for e, _ in ins], [s for _, s in ins])
+    for i, (e, s) in enumerate(ins):
+        m1, w1 = ctx.synth_batch([e], [s])
+        assert np.array_equal(m1[0], mels[i]) and np.array_equal(w1[0], wavs[i])
+    perm = [2, 0, 3, 1]
+    mp, wp = ctx.synth_batch([ins[p][0] for p in perm], [ins[p][1] for p in perm])
+    for k, p in enumerate(perm):
+        assert np.array_equal(wp[k], wavs[p])
+    # reference semantics for one of them: decode + vocode == synth_batch
+    m = ctx.decode(*ins[0])
+    assert np.array_equal(m, mels[0]) and np.array_equal(ctx.vocode(m), wavs[0])
+
+
+def test_live_reference_on_unseen_length(ctx, zvx, gguf_path):
+    """Run the compiled reference on the GPU box's host for a length without a committed fixture."""
+    import refrun
+    if not refrun.available():
+        pytest.skip("oracle/_ref not present")
+    L = 77
+    enc, sty = zvx.synth.make_inputs(L, seed=99)
+    r = refrun.run(gguf_path, L, enc, sty)
+    mel = ctx.decode(enc, sty)
+    assert zv_oracle.snr_db(r["mel"], mel) >= 55.0
+    voc = ctx.vocode(r["mel"])
+    assert zv_oracle.snr_db(r["wav"], voc) >= 60.0 and np.abs(voc - r["wav"]).max() <= 1e-3
+
+
+def test_full_size_batch_properties(ctx, zvx):
+    """BASELINE.json configs[1] size (64 utterances, 2-10 s): size-independent properties --
+    determinism, range, batch-independence of a probe utterance, silence of nothing (all finite)."""
+    lengths = zvx.synth.batch_lengths(64, seed=11)
+    rng = np.random.default_rng(1)
+    encs = [rng.standard_normal((int(L), 528)).astype(np.float32) for L in lengths]
+    stys = [(0.05 * rng.standard_normal(528)).astype(np.float32) for _ in lengths]
+    _, w1 = ctx.synth_batch(encs, stys, want_mel=False)
+    _, w2 = ctx.synth_batch(encs, stys, want_mel=False)
+    for a, b, L in zip(w1, w2, lengths):
+        assert a.shape == (int(L) * 300,) and np.array_equal(a, b)
+        assert np.all(np.isfinite(a)) and np.abs(a).max() < 1.0
+    probe = int(np.argmin(lengths))
+    _, ws = ctx.synth_batch([encs[probe]], [stys[probe]], want_mel=False)
+    assert np.array_equal(ws[0], w1[probe])
+    assert ctx.kernel_launches() > 0
+
+
+def test_error_behaviour(ctx):
+    """Errors surface as exceptions carrying zvx_last_error (reference: std::runtime_error)."""
+    from zerovox_cpp_b200 import capi
+    with pytest.raises(capi.ZvxError):
+        ctx.synth_batch([np.zeros((0, 528), np.float32)], [np.zeros(528, np.float32)])
+    with pytest.raises(capi.ZvxError, match="not found"):
+        capi.Context({"hifigan.mean": np.zeros(80, np.float32)})

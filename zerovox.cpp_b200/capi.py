@@ -42,11 +42,18 @@ class ConvTest(C.Structure):
                 ("out", C.c_void_p), ("out16", C.c_void_p), ("use_validation_kernel", C.c_int32)]
 
 
+class LaunchRecord(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("stage", C.c_int32), ("flops", C.c_double), ("bytes", C.c_double),
+                ("ms", C.c_float)]
+
+
+KIND_NAMES = ["dec_conv", "voc_input_conv", "upconv", "mrf_conv", "out_conv", "stats", "adain_fc", "norm_affine"]
+
 EXPORTS = [
     "zvx_default_config", "zvx_create", "zvx_destroy", "zvx_last_error", "zvx_decode", "zvx_vocode",
     "zvx_synth_batch", "zvx_synth_batch_device", "zvx_vocode_batch_device", "zvx_stream", "zvx_synchronize",
     "zvx_kernel_launches", "zvx_reserve", "zvx_set_debug_kernels", "zvx_test_conv", "zvx_debug_fetch",
-    "zvx_set_debug_stop",
+    "zvx_set_debug_stop", "zvx_profile_begin", "zvx_profile_end",
 ]
 
 _lib = None
@@ -96,6 +103,10 @@ def load_library() -> C.CDLL:
     lib.zvx_test_conv.restype = i32
     lib.zvx_debug_fetch.argtypes = [vp, C.c_char_p, vp, i64]
     lib.zvx_debug_fetch.restype = i32
+    lib.zvx_profile_begin.argtypes = [vp]
+    lib.zvx_profile_begin.restype = i32
+    lib.zvx_profile_end.argtypes = [vp, C.POINTER(LaunchRecord), i64]
+    lib.zvx_profile_end.restype = i64
     _lib = lib
     return lib
 
@@ -217,6 +228,17 @@ class Context:
 
     def reserve(self, total_frames: int, max_batch: int):
         self._check(self.lib.zvx_reserve(self.h, total_frames, max_batch))
+
+    def profile_begin(self):
+        self._check(self.lib.zvx_profile_begin(self.h))
+
+    def profile_end(self, max_recs: int = 1 << 16):
+        """-> list of (kind_name, stage, flops, bytes, ms), one per kernel launched since profile_begin."""
+        recs = (LaunchRecord * max_recs)()
+        n = self.lib.zvx_profile_end(self.h, recs, max_recs)
+        if n < 0:
+            self._check(1)
+        return [(KIND_NAMES[r.kind], r.stage, r.flops, r.bytes, r.ms) for r in recs[:min(n, max_recs)]]
 
     # ---- test / debug surface -------------------------------------------------------
     def set_debug_kernels(self, on: bool):

@@ -93,9 +93,14 @@ struct zvx_ctx {
     bool tables_pending = false;
     float *pin_in = nullptr, *pin_out = nullptr;  // pinned staging for host-pointer API
     size_t pin_in_cap = 0, pin_out_cap = 0;
-    // conv test scratch
     int last_B = 0;
     int64_t last_frames = 0;
+    // ---- per-launch profiling (CUDA events on the launch stream) ----
+    bool prof = false;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    struct ProfEntry { int kind, stage; double flops, bytes; size_t ev; };
+    std::vector<ProfEntry> prof_entries;
 };
 
 namespace {
@@ -453,8 +458,31 @@ int set_batch(zvx_ctx *ctx, int B, const int32_t *L, bool reserve_workspace = tr
     return 0;
 }
 
+// ---------------------------------------------------------------- per-launch profiling
+int prof_begin(zvx_ctx *ctx, int kind, int stage, double flops, double bytes)
+{
+    if (!ctx->prof) return 0;
+    while (ctx->ev_pool.size() < ctx->ev_used + 2) {
+        cudaEvent_t e;
+        CK(ctx, cudaEventCreate(&e));
+        ctx->ev_pool.push_back(e);
+    }
+    zvx_ctx::ProfEntry pe = {kind, stage, flops, bytes, ctx->ev_used};
+    ctx->prof_entries.push_back(pe);
+    CK(ctx, cudaEventRecord(ctx->ev_pool[ctx->ev_used], ctx->stream));
+    ctx->ev_used += 2;
+    return 0;
+}
+int prof_end(zvx_ctx *ctx)
+{
+    if (!ctx->prof) return 0;
+    CK(ctx, cudaEventRecord(ctx->ev_pool[ctx->prof_entries.back().ev + 1], ctx->stream));
+    return 0;
+}
+
 // ---------------------------------------------------------------- conv launch helper
 struct ConvCall {
+    int kind = ZVX_K_DEC_CONV, stage = 0;
     const ConvLayer *L = nullptr;
     int variant = 0;
     const void *x = nullptr; int ldx = 0, x_ch_off = 0;
@@ -498,6 +526,8 @@ int run_conv(zvx_ctx *ctx, const ConvCall &cc)
     p.err_flag = ctx->d_err;
     const int tiles = ctx->total_tiles[cc.rate_idx];
     ctx->launches++;
+    const double rows = (double)ctx->last_frames * p.rate_in;
+    if (prof_begin(ctx, cc.kind, cc.stage, 2.0 * rows * L.OC * L.IC * v.ntaps, 0.0)) return 1;
     if (ctx->use_ref_kernels) {
         CK(ctx, conv_ref_launch(p, tiles, ctx->stream));
     } else {
@@ -505,14 +535,15 @@ int run_conv(zvx_ctx *ctx, const ConvCall &cc)
         if (smem > 227 * 1024) return fail(ctx, "conv needs %zu bytes of shared memory", smem);
         CK(ctx, conv_umma_launch(p, tiles, smem, ctx->stream));
     }
-    return 0;
+    return prof_end(ctx);
 }
 
 int run_stats(zvx_ctx *ctx, const float *x, int ld, int ch_off, int C)
 {
     ctx->launches++;
+    if (prof_begin(ctx, ZVX_K_STATS, 0, 0.0, 2.0 * (double)ctx->last_frames * C * sizeof(float))) return 1;
     CK(ctx, stats_launch(x, ld, ch_off, C, ctx->d_seg, ctx->last_B, 1, ctx->mu, ctx->rstd, ctx->stream));
-    return 0;
+    return prof_end(ctx);
 }
 
 // ---------------------------------------------------------------- decoder schedule
@@ -524,7 +555,11 @@ int run_decoder(zvx_ctx *ctx, float *mel_out)
     const float inv_sqrt2 = (float)(1.0 / std::sqrt(2.0));
 
     ctx->launches++;
+    if (prof_begin(ctx, ZVX_K_ADAIN_FC, 0, 2.0 * ctx->last_B * (double)ctx->adain.total * c.style_dim,
+                   (double)ctx->adain.total * c.style_dim * sizeof(float)))
+        return 1;
     CK(ctx, adain_fc_launch(ctx->adain, ctx->style, ctx->last_B, ctx->adain_gb, ctx->stream));
+    if (prof_end(ctx)) return 1;
 
     // ---- encode.0 / encode.1 : ResBlk1d (stylettsdec.cpp:69-149) ----
     const float *x = ctx->enc_in; int ldx = D;
@@ -559,8 +594,10 @@ int run_decoder(zvx_ctx *ctx, float *mel_out)
         if (run_conv(ctx, a)) return 1;
         if (run_stats(ctx, ctx->asr, R, 0, R)) return 1;
         ctx->launches++;
+        if (prof_begin(ctx, ZVX_K_NORM_AFFINE, 0, 0.0, 3.0 * (double)ctx->last_frames * R * sizeof(float))) return 1;
         CK(ctx, norm_affine_launch(ctx->asr, R, R, ctx->d_seg, ctx->last_B, ctx->mu, ctx->rstd, ctx->asr1w, ctx->asr1b,
                                    ctx->catA, ctx->catB, CAT, BN, ctx->stream));
+        if (prof_end(ctx)) return 1;
     }
     // ---- decode.0-4 : AdainResBlk1d (stylettsdec.cpp:242-304) ----
     const float *din[5]  = {ctx->catA, ctx->catB, ctx->catA, ctx->d1, ctx->d2};
@@ -604,7 +641,7 @@ int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out)
     const int nb = c.num_resblocks, nd = c.num_resblock_dilations;
     // (mel - mean) / scale -> input_conv (hifigan.cpp:242-265)
     {
-        ConvCall ic; ic.L = &ctx->input_conv; ic.x = mel_in; ic.ldx = c.num_mels; ic.pro_mode = PRO_MEL;
+        ConvCall ic; ic.kind = ZVX_K_VOC_INPUT_CONV; ic.L = &ctx->input_conv; ic.x = mel_in; ic.ldx = c.num_mels; ic.pro_mode = PRO_MEL;
         ic.mu = ctx->mel_mean; ic.rstd = ctx->mel_scale; ic.stat_stride = 0;
         ic.out32 = ctx->v0; ic.ldo32 = ctx->chans[0];
         if (run_conv(ctx, ic)) return 1;
@@ -618,7 +655,7 @@ int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out)
         const int s = c.upsample_scales[i];
         // leaky_relu(0.1) -> ConvTranspose1d, one launch per output phase (hifigan.cpp:281-297, :22-71)
         for (int phi = 0; phi < s; ++phi) {
-            ConvCall u; u.L = &ctx->up[i]; u.variant = phi; u.x = vin; u.ldx = cin; u.rate_idx = i;
+            ConvCall u; u.kind = ZVX_K_UPCONV; u.stage = i; u.L = &ctx->up[i]; u.variant = phi; u.x = vin; u.ldx = cin; u.rate_idx = i;
             u.pro_mode = PRO_LRELU; u.pro_slope = 0.1f; u.out32 = ctx->U; u.ldo32 = ch; u.out_mul = s;
             if (run_conv(ctx, u)) return 1;
         }
@@ -628,11 +665,11 @@ int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out)
             for (int d = 0; d < nd; ++d) {
                 const size_t idx = ((size_t)i * nb + j) * nd + d;
                 const float *yin = d == 0 ? ctx->U : Y;
-                ConvCall c1; c1.L = &ctx->mrf1[idx]; c1.x = yin; c1.ldx = ch; c1.rate_idx = i + 1;
+                ConvCall c1; c1.kind = ZVX_K_MRF_CONV; c1.stage = i; c1.L = &ctx->mrf1[idx]; c1.x = yin; c1.ldx = ch; c1.rate_idx = i + 1;
                 c1.pro_mode = PRO_LRELU; c1.pro_slope = 0.1f;
                 c1.out16 = ctx->H16; c1.ldo16 = ch; c1.out16_slope = 0.1f;
                 if (run_conv(ctx, c1)) return 1;
-                ConvCall c2; c2.L = &ctx->mrf2[idx]; c2.x = ctx->H16; c2.ldx = ch; c2.rate_idx = i + 1; c2.pro_mode = PRO_F16;
+                ConvCall c2; c2.kind = ZVX_K_MRF_CONV; c2.stage = i; c2.L = &ctx->mrf2[idx]; c2.x = ctx->H16; c2.ldx = ch; c2.rate_idx = i + 1; c2.pro_mode = PRO_F16;
                 c2.res = yin; c2.ldres = ch;
                 const bool last = d == nd - 1;
                 if (last && j > 0) {
@@ -652,10 +689,16 @@ int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out)
     // leaky_relu(0.01) -> output_conv -> tanh (hifigan.cpp:324-345)
     const int last = c.num_upsamples;
     ctx->launches++;
+    {
+        const double rows = (double)ctx->last_frames * ctx->rates[last];
+        if (prof_begin(ctx, ZVX_K_OUT_CONV, last, 2.0 * rows * ctx->chans[last] * ctx->output_conv.K,
+                       rows * (ctx->chans[last] + 1) * sizeof(float)))
+            return 1;
+    }
     CK(ctx, out_conv_launch(vin, ctx->chans[last], ctx->output_conv.K, ctx->output_conv.raw, ctx->output_conv.bias, 0.01f,
                             ctx->d_seg, ctx->d_tiles + (size_t)last * (ctx->cap_batch + 1), ctx->last_B, ctx->rates[last],
                             ctx->total_tiles[last], wav_out, ctx->stream));
-    return 0;
+    return prof_end(ctx);
 }
 
 int check_device_error(zvx_ctx *ctx)
@@ -806,6 +849,42 @@ int zvx_reserve(zvx_ctx *ctx, int64_t total_frames, int32_t max_batch)
     if (!ctx) return 1;
     CK(ctx, cudaSetDevice(ctx->device));
     return reserve(ctx, total_frames, max_batch);
+}
+
+int zvx_profile_begin(zvx_ctx *ctx)
+{
+    if (!ctx) return 1;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->prof = true;
+    ctx->ev_used = 0;
+    ctx->prof_entries.clear();
+    return 0;
+}
+
+int64_t zvx_profile_end(zvx_ctx *ctx, zvx_launch_record *recs, int64_t max_recs)
+{
+    if (!ctx) return -1;
+    ctx->prof = false;
+    if (cudaSetDevice(ctx->device) != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        fail(ctx, "zvx_profile_end: synchronize failed");
+        return -1;
+    }
+    const int64_t n = (int64_t)ctx->prof_entries.size();
+    for (int64_t i = 0; i < n && i < max_recs; ++i) {
+        const zvx_ctx::ProfEntry &e = ctx->prof_entries[i];
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->ev_pool[e.ev], ctx->ev_pool[e.ev + 1]) != cudaSuccess) {
+            fail(ctx, "cudaEventElapsedTime failed");
+            return -1;
+        }
+        recs[i].kind = e.kind;
+        recs[i].stage = e.stage;
+        recs[i].flops = e.flops;
+        recs[i].bytes = e.bytes;
+        recs[i].ms = ms;
+    }
+    return n;
 }
 
 void zvx_set_debug_kernels(zvx_ctx *ctx, int32_t v) { if (ctx) ctx->use_ref_kernels = v; }
