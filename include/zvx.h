@@ -85,6 +85,9 @@ int zvx_vocode(zvx_ctx *ctx, const float *mel, int32_t L, float *wav);
 int zvx_synth_batch(zvx_ctx *ctx, int32_t B, const float *const *enc_seq, const float *const *style,
                     const int32_t *L, float *const *mel, float *const *wav);
 
+/* Batched HiFiGAN::eval (hifigan.cpp:358-377) for B independent mels; HOST pointers. */
+int zvx_vocode_batch(zvx_ctx *ctx, int32_t B, const float *const *mel, const int32_t *L, float *const *wav);
+
 /* Same computation with inputs/outputs already resident in device memory, packed back to
  * back: d_enc [sum L][dim_in], d_style [B][style_dim], d_mel [sum L][num_mels] (may be
  * NULL), d_wav [sum L * hop].  L is a HOST array.  Asynchronous on the ctx stream unless
@@ -120,6 +123,9 @@ int64_t zvx_profile_end(zvx_ctx *ctx, zvx_launch_record *recs, int64_t max_recs)
 /* ---- test / debug surface (used by tests/ only) ---------------------------------- */
 /* 0: tcgen05 implicit-GEMM kernels (the product path); 1: plain-CUDA validation kernels */
 void zvx_set_debug_kernels(zvx_ctx *ctx, int32_t use_validation_kernels);
+/* 1 (default): MRF residual blocks run as fused on-chip chains (mrf_fused.cu); 0: one
+ * implicit-GEMM launch per convolution (conv_umma.cu).  Both are tcgen05 paths. */
+void zvx_set_fused_mrf(zvx_ctx *ctx, int32_t on);
 
 /* Run ONE convolution through the selected kernel on packed utterances.
  * x [sum rows][Cin] fp32 host, w (OC, IC, K) fp16 host (K fastest), bias [OC] or NULL,

@@ -1,0 +1,235 @@
+// mrf_fused_emul.cpp -- CPU emulation of the fused MRF residual-block kernel's DATA MOVEMENT.
+//
+// Test infrastructure (not product code).  It runs the real host-side packing / table / plan
+// code of zerovox.cpp_b200/csrc/mrf_fused_host.h and re-enacts, byte for byte, what
+// mrf_fused.cu does with shared memory and tensor memory: the prologue scatter, every
+// tcgen05.mma as "D[m][n] (+)= sum_k A[m][k] * B[n][k]" with A / B fetched through the same
+// no-swizzle K-major descriptor arithmetic (start, LBO, SBO = 128), and the epilogue scatter
+// through the tables.  The result is compared with a direct evaluation of
+// HiFiGANResidualBlock (/root/reference/src/hifigan.cpp:97-183) on the same fp16-rounded
+// operands.  This pins the window trick, the polyphase / phase-major layouts, halo handling
+// and the per-layer zero masking at utterance edges without a GPU.
+//
+// usage: mrf_fused_emul CH k T [npairs_min_eff]   -> prints max abs error, exits 1 on mismatch
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <vector>
+
+#include "../../zerovox.cpp_b200/csrc/mrf_fused_host.h"
+
+using namespace zvx::mrf;
+
+static uint16_t f2h(float f)
+{
+    uint32_t x;
+    memcpy(&x, &f, 4);
+    const uint32_t sign = (x >> 16) & 0x8000u;
+    int32_t e = (int32_t)((x >> 23) & 0xFF) - 127 + 15;
+    uint32_t m = x & 0x7FFFFFu;
+    if (((x >> 23) & 0xFF) == 0xFF) return (uint16_t)(sign | 0x7C00u | (m ? 0x200u : 0));
+    if (e >= 31) return (uint16_t)(sign | 0x7C00u);
+    if (e <= 0) {
+        if (e < -10) return (uint16_t)sign;
+        m |= 0x800000u;
+        const int shift = 14 - e;
+        uint32_t h = m >> shift;
+        const uint32_t rem = m & ((1u << shift) - 1), halfway = 1u << (shift - 1);
+        if (rem > halfway || (rem == halfway && (h & 1))) ++h;
+        return (uint16_t)(sign | h);
+    }
+    uint32_t h = ((uint32_t)e << 10) | (m >> 13);
+    const uint32_t rem = m & 0x1FFFu;
+    if (rem > 0x1000u || (rem == 0x1000u && (h & 1))) ++h;
+    return (uint16_t)(sign | h);
+}
+static float h2f(uint16_t h)
+{
+    const uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
+    uint32_t e = (h >> 10) & 0x1F, m = h & 0x3FFu, x;
+    if (e == 0) {
+        if (m == 0) x = sign;
+        else {
+            e = 1;
+            while (!(m & 0x400u)) { m <<= 1; --e; }
+            m &= 0x3FFu;
+            x = sign | ((e + 127 - 15) << 23) | (m << 13);
+        }
+    } else if (e == 31) x = sign | 0x7F800000u | (m << 13);
+    else x = sign | ((e + 127 - 15) << 23) | (m << 13);
+    float f;
+    memcpy(&f, &x, 4);
+    return f;
+}
+static float lrelu(float x, float a) { return x > 0.f ? x : a * x; }
+
+struct Conv { int k, d; std::vector<uint16_t> raw; std::vector<float> bias; };
+
+// direct reference: y [T][CH] fp32
+static void direct_block(std::vector<float> &y, int T, int CH, const std::vector<Conv> &convs)
+{
+    const int P = (int)convs.size() / 2;
+    std::vector<float> xt((size_t)T * CH), h((size_t)T * CH);
+    for (int p = 0; p < P; ++p) {
+        for (size_t i = 0; i < y.size(); ++i) xt[i] = h2f(f2h(lrelu(y[i], 0.1f)));
+        for (int c = 0; c < 2; ++c) {
+            const Conv &cv = convs[2 * p + c];
+            const std::vector<float> &in = c == 0 ? xt : h;
+            const int pad = (cv.k - 1) / 2 * cv.d;
+            std::vector<float> out((size_t)T * CH);
+            for (int t = 0; t < T; ++t)
+                for (int oc = 0; oc < CH; ++oc) {
+                    double acc = 0.0;
+                    for (int a = 0; a < cv.k; ++a) {
+                        const int ti = t + a * cv.d - pad;
+                        if (ti < 0 || ti >= T) continue;
+                        for (int ic = 0; ic < CH; ++ic)
+                            acc += (double)in[(size_t)ti * CH + ic] * (double)h2f(cv.raw[((size_t)oc * CH + ic) * cv.k + a]);
+                    }
+                    out[(size_t)t * CH + oc] = (float)acc + cv.bias[oc];
+                }
+            if (c == 0) for (size_t i = 0; i < out.size(); ++i) h[i] = h2f(f2h(lrelu(out[i], 0.1f)));
+            else for (size_t i = 0; i < out.size(); ++i) y[i] = y[i] + out[i];
+        }
+    }
+}
+
+template <int CH>
+static int run(int k, int T, double min_eff)
+{
+    using G = Geo<CH>;
+    const int S = G::S, Wp = G::WP, P = 3;
+    const int dil[3] = {1, 3, 5};
+    std::mt19937 rng(1234 + CH * 100 + k);
+    std::normal_distribution<float> nd(0.f, 1.f);
+    std::vector<Conv> convs(2 * P);
+    for (int p = 0; p < P; ++p)
+        for (int c = 0; c < 2; ++c) {
+            Conv &cv = convs[2 * p + c];
+            cv.k = k;
+            cv.d = c == 0 ? dil[p] : 1;
+            cv.raw.resize((size_t)CH * CH * k);
+            for (auto &w : cv.raw) w = f2h(nd(rng) * 0.5f / std::sqrt((float)CH * k));
+            cv.bias.resize(CH);
+            for (auto &b : cv.bias) b = 0.02f * nd(rng);
+        }
+    std::vector<float> y0((size_t)T * CH);
+    for (auto &v : y0) v = nd(rng);
+    std::vector<float> ref = y0;
+    direct_block(ref, T, CH, convs);
+
+    // ---- emulate the launches ----
+    std::vector<float> cur = y0;
+    const std::vector<ChainPlan> plan = plan_chains(CH, k, dil, P, min_eff);
+    for (const ChainPlan &cp : plan) {
+        const int nl = 2 * (cp.p1 - cp.p0);
+        // per-layer host data, exactly as the library prepares it
+        std::vector<std::vector<uint16_t>> wpk(nl);
+        std::vector<std::vector<float>> bias(nl);
+        std::vector<std::vector<uint32_t>> tbl(nl);
+        std::vector<float> cum(CH, 0.f);
+        for (int l = 0; l < nl; ++l) {
+            const Conv &cv = convs[2 * cp.p0 + l];
+            wpk[l] = pack_weights(cv.raw.data(), CH, cv.k);
+            if (l & 1) { for (int i = 0; i < CH; ++i) cum[i] += cv.bias[i]; bias[l] = cum; }
+            else bias[l] = cv.bias;
+            if (l + 1 < nl) tbl[l] = make_table(CH, cv.d, convs[2 * cp.p0 + l + 1].d);
+        }
+        const std::vector<uint32_t> tbl0 = make_table(CH, 1, convs[2 * cp.p0].d);
+        std::vector<float> out = cur;
+        const int nwin = (T + cp.valid - 1) / cp.valid;
+        for (int wi = 0; wi < nwin; ++wi) {
+            const int tw = wi * cp.valid - cp.halo;
+            std::vector<uint8_t> buf[2] = {std::vector<uint8_t>(G::BUF, 0), std::vector<uint8_t>(G::BUF, 0)};
+            std::vector<float> Hacc((size_t)128 * NCOL, 0.f), Yacc((size_t)128 * NCOL, 0.f);
+            auto sts16 = [&](std::vector<uint8_t> &b, int unit, int oc, float v) {
+                const size_t a = (size_t)unit * 16 + (size_t)(oc >> 3) * LBO_B + (oc & 7) * 2;
+                const uint16_t hv = f2h(v);
+                memcpy(&b[a], &hv, 2);
+            };
+            // prologue
+            for (int m = 0; m < 128; ++m) {
+                const int s = m / CH, oc = m % CH;
+                for (int n = 0; n < NCOL; ++n) {
+                    const int tau = S * n + s, t = tw + tau;
+                    const bool ok = tau < Wp && t >= 0 && t < T;
+                    const float yv = ok ? cur[(size_t)t * CH + oc] : 0.f;
+                    Yacc[(size_t)m * NCOL + n] = yv;
+                    const uint32_t e = tbl0[(size_t)s * NCOL + n];
+                    if (e & TBL_VALID) sts16(buf[0], tbl_unit(e), oc, lrelu(yv, 0.1f));
+                }
+            }
+            for (int l = 0; l < nl; ++l) {
+                const Conv &cv = convs[2 * cp.p0 + l];
+                const int TB = tap_blocks(cv.k, S);
+                std::vector<uint8_t> &in = buf[l & 1], &ob = buf[(l & 1) ^ 1];
+                std::vector<float> &D = (l & 1) ? Yacc : Hacc;
+                const bool accum = (l & 1) != 0;
+                const uint32_t cb = chunk_bytes(cv.k, S, CH);
+                bool first = true;
+                for (int c = 0; c < G::KSTEPS; ++c) {
+                    const uint8_t *slot = reinterpret_cast<const uint8_t *>(wpk[l].data()) + (size_t)c * cb;
+                    for (int j = 0; j < cv.k + S - 1; ++j) {
+                        int q, ro;
+                        b_step(cv.k, S, j, q, ro);
+                        const long a_start = (long)a_block(cv.k, S, j) * CH * 16;
+                        const long lbo_a = (long)TB * CH * 16;
+                        const long b_start = (long)q * G::SUB + (long)2 * c * LBO_B + (long)(GUARD + ro) * 16;
+                        if (a_start < 0 || a_start + lbo_a + 15 * 128 + 7 * 16 + 16 > (long)cb) { printf("A window out of chunk\n"); return 1; }
+                        if (b_start < 0 || b_start + LBO_B + 255 * 16 + 16 > (long)G::BUF) { printf("B tile out of buffer\n"); return 1; }
+                        for (int m = 0; m < 128; ++m)
+                            for (int n = 0; n < NCOL; ++n) {
+                                float acc = (accum || !first) ? D[(size_t)m * NCOL + n] : 0.f;
+                                for (int kk = 0; kk < 16; ++kk) {
+                                    uint16_t av, bv;
+                                    memcpy(&av, slot + a_start + (kk / 8) * lbo_a + (m / 8) * 128 + (m % 8) * 16 + (kk % 8) * 2, 2);
+                                    memcpy(&bv, &in[b_start + (kk / 8) * LBO_B + (n / 8) * 128 + (n % 8) * 16 + (kk % 8) * 2], 2);
+                                    acc += h2f(av) * h2f(bv);
+                                }
+                                D[(size_t)m * NCOL + n] = acc;
+                            }
+                        first = false;
+                    }
+                }
+                // epilogue
+                const bool last = l == nl - 1;
+                for (int m = 0; m < 128; ++m) {
+                    const int s = m / CH, oc = m % CH;
+                    for (int n = 0; n < NCOL; ++n) {
+                        const float v = D[(size_t)m * NCOL + n] + bias[l][oc];
+                        if (!last) {
+                            const uint32_t e = tbl[l][(size_t)s * NCOL + n];
+                            if (!(e & TBL_VALID)) continue;
+                            const int t = tw + tbl_tau(e);
+                            sts16(ob, tbl_unit(e), oc, (t >= 0 && t < T) ? lrelu(v, 0.1f) : 0.f);
+                        } else {
+                            const int tau = S * n + s, t = tw + tau;
+                            if (tau >= cp.halo && tau < cp.halo + cp.valid && t >= 0 && t < T) out[(size_t)t * CH + oc] = v;
+                        }
+                    }
+                }
+            }
+        }
+        cur = out;
+    }
+    double maxerr = 0.0, maxref = 0.0;
+    for (size_t i = 0; i < ref.size(); ++i) {
+        maxerr = std::max(maxerr, (double)std::fabs(ref[i] - cur[i]));
+        maxref = std::max(maxref, (double)std::fabs(ref[i]));
+    }
+    printf("CH=%d k=%d T=%d launches=%zu max|ref|=%.3f max_abs_err=%.3e\n", CH, k, T, plan.size(), maxref, maxerr);
+    return maxerr < 2e-3 ? 0 : 1;   // fp16 re-rounding of intermediates can flip an ulp; see DESIGN.md
+}
+
+int main(int argc, char **argv)
+{
+    if (argc < 4) { fprintf(stderr, "usage: %s CH k T [min_eff]\n", argv[0]); return 2; }
+    const int CH = atoi(argv[1]), k = atoi(argv[2]), T = atoi(argv[3]);
+    const double me = argc > 4 ? atof(argv[4]) : 0.0;
+    if (CH == 32) return run<32>(k, T, me);
+    if (CH == 64) return run<64>(k, T, me);
+    if (CH == 128) return run<128>(k, T, me);
+    return 2;
+}

@@ -53,7 +53,7 @@ EXPORTS = [
     "zvx_default_config", "zvx_create", "zvx_destroy", "zvx_last_error", "zvx_decode", "zvx_vocode",
     "zvx_synth_batch", "zvx_synth_batch_device", "zvx_vocode_batch_device", "zvx_stream", "zvx_synchronize",
     "zvx_kernel_launches", "zvx_reserve", "zvx_set_debug_kernels", "zvx_test_conv", "zvx_debug_fetch",
-    "zvx_set_debug_stop", "zvx_profile_begin", "zvx_profile_end",
+    "zvx_set_debug_stop", "zvx_profile_begin", "zvx_profile_end", "zvx_set_fused_mrf", "zvx_vocode_batch",
 ]
 
 _lib = None
@@ -83,6 +83,8 @@ def load_library() -> C.CDLL:
     lib.zvx_vocode.restype = i32
     lib.zvx_synth_batch.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(i32), C.POINTER(vp), C.POINTER(vp)]
     lib.zvx_synth_batch.restype = i32
+    lib.zvx_vocode_batch.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(i32), C.POINTER(vp)]
+    lib.zvx_vocode_batch.restype = i32
     lib.zvx_synth_batch_device.argtypes = [vp, i32, vp, vp, C.POINTER(i32), vp, vp, i32]
     lib.zvx_synth_batch_device.restype = i32
     lib.zvx_vocode_batch_device.argtypes = [vp, i32, vp, C.POINTER(i32), vp, i32]
@@ -99,6 +101,8 @@ def load_library() -> C.CDLL:
     lib.zvx_set_debug_kernels.restype = None
     lib.zvx_set_debug_stop.argtypes = [vp, i32]
     lib.zvx_set_debug_stop.restype = None
+    lib.zvx_set_fused_mrf.argtypes = [vp, i32]
+    lib.zvx_set_fused_mrf.restype = None
     lib.zvx_test_conv.argtypes = [vp, C.POINTER(ConvTest)]
     lib.zvx_test_conv.restype = i32
     lib.zvx_debug_fetch.argtypes = [vp, C.c_char_p, vp, i64]
@@ -195,6 +199,17 @@ class Context:
         self._check(self.lib.zvx_vocode(self.h, _ptr(mel), L, _ptr(wav)))
         return wav
 
+    def vocode_batch(self, mel_list: Sequence[np.ndarray]):
+        B = len(mel_list)
+        mels = [np.ascontiguousarray(m, np.float32) for m in mel_list]
+        Ls = (C.c_int32 * B)(*[m.shape[0] for m in mels])
+        wavs = [np.empty(m.shape[0] * self.hop, np.float32) for m in mels]
+        vp = C.c_void_p
+        pm = (vp * B)(*[m.ctypes.data for m in mels])
+        pw = (vp * B)(*[w.ctypes.data for w in wavs])
+        self._check(self.lib.zvx_vocode_batch(self.h, B, pm, Ls, pw))
+        return wavs
+
     def synth_batch(self, enc_list: Sequence[np.ndarray], style_list: Sequence[np.ndarray], want_mel: bool = True):
         B = len(enc_list)
         encs = [np.ascontiguousarray(e, np.float32) for e in enc_list]
@@ -243,6 +258,10 @@ class Context:
     # ---- test / debug surface -------------------------------------------------------
     def set_debug_kernels(self, on: bool):
         self.lib.zvx_set_debug_kernels(self.h, int(on))
+
+    def set_fused_mrf(self, on: bool):
+        """True (default): fused residual-block kernel; False: one launch per convolution."""
+        self.lib.zvx_set_fused_mrf(self.h, int(on))
 
     def set_debug_stop(self, stages: int):
         self.lib.zvx_set_debug_stop(self.h, int(stages))

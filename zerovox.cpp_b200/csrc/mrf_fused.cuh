@@ -1,0 +1,135 @@
+// mrf_fused.cuh -- geometry of the fused MRF residual-block kernel (mrf_fused.cu).
+//
+// What it replaces: HiFiGANResidualBlock, /root/reference/src/hifigan.cpp:74-185 -- for one
+// residual block (kernel size k, dilations d_0..d_{P-1}):
+//     y = x;  for p:  y = y + conv2_p(lrelu(conv1_p(lrelu(y, .1)) , .1))
+// The reference executes 6 ggml_conv_1d (im2col + mul_mat) with fp32 tensors in between;
+// this kernel keeps the whole chain of one time window on chip.
+//
+// Orientation ("swapped" implicit GEMM).  Measured on B200 (tools/ubench/umma_issue.cu):
+// tcgen05.mma reads its shared-memory operands at 128 B/clk, so a M=128 x N x K=16 MMA
+// costs max(N/2, (4096 + 32 N)/128) cycles: N = 32 / 64 output channels would run at 40 % /
+// 67 % of the tensor rate.  Therefore the WEIGHTS are the A operand (M = 128 rows) and the
+// time axis is N = 256:
+//     D[(s, oc), n'] = sum_{j, ic}  A_j[(s, oc), ic] * X[pos = S n' + j - c, ic]
+// with S = 128 / CH output shifts stacked along M (output position S n' + s), taps
+// j = s + tap in [0, k + S - 2] and c = (k - 1) / 2.  A_j[(s, oc), :] = W[oc, :, j - s]
+// (zero when j - s is not a tap), which is a WINDOW of 128 consecutive rows of the tap-
+// reversed weight array -- no stacked copy is materialised.
+//
+// Positions.  A dilated conv (dilation d) over a window of Wp time steps is a dilation-1
+// conv over "positions" when the window is stored phase-major: time tau = m d + r
+// (r < d, m < Wp / d) sits at position p = r (Wp / d) + m.  Positions are split into S
+// polyphase sub-buffers (q = p mod S, row = p div S) so that a tap shift is a row offset.
+// Everything here is shared by the device kernel, the host-side packing code and the CPU
+// emulator in tests/cpu/ (which checks exactly this index arithmetic against a direct conv).
+#pragma once
+
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define ZVX_HD __host__ __device__ __forceinline__
+#else
+#define ZVX_HD inline
+#endif
+
+namespace zvx {
+namespace mrf {
+
+constexpr int NCOL       = 256;   // GEMM N: columns n' per window
+constexpr int GUARD      = 8;     // zero rows before / after the 256 data rows of a sub-buffer
+constexpr int NROWS      = 273;   // rows per (sub-buffer, channel group): 8 + 256 + 8, +1 so that the
+                                  // four 16-byte group segments of one warp store hit distinct banks
+constexpr int ROW_BYTES  = 16;    // 8 channels x fp16
+constexpr int LBO_B      = NROWS * ROW_BYTES;      // byte distance between channel groups
+constexpr int MAX_LAYERS = 6;
+constexpr int MAX_K      = 11;
+
+template <int CH>
+struct Geo {
+    static constexpr int S       = 128 / CH;                 // output shifts stacked along M
+    static constexpr int NPOS    = S * NCOL;                 // positions per window
+    static constexpr int WP      = (NPOS / (15 * S)) * 15 * S;   // window length in time steps:
+                                                                 // multiple of S*d for d in {1,3,5}
+    static constexpr int GROUPS  = CH / 8;                   // 8-channel groups
+    static constexpr int SUB     = GROUPS * LBO_B;           // bytes per polyphase sub-buffer
+    static constexpr int BUF     = S * SUB;                  // bytes per activation buffer
+    static constexpr int KSTEPS  = CH / 16;                  // MMA K-steps per tap
+};
+
+// tap blocks of the reversed, zero-padded weight array of a conv with k taps
+ZVX_HD int tap_blocks(int k, int S) { return k + 2 * S - 2; }
+// first tap block of the A window for step j (row s of the window uses tap j - s)
+ZVX_HD int a_block(int k, int S, int j) { return k + S - 2 - j; }
+// bytes of one weight chunk = (layer, 16-channel K-step): two channel groups
+ZVX_HD uint32_t chunk_bytes(int k, int S, int CH) { return 2u * (uint32_t)tap_blocks(k, S) * CH * 16u; }
+
+ZVX_HD int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+// B operand of step j: sub-buffer and row offset (relative to data row 0)
+ZVX_HD void b_step(int k, int S, int j, int &q, int &row_off)
+{
+    const int u = j - (k - 1) / 2;
+    row_off = floor_div(u, S);
+    q = u - row_off * S;
+}
+
+// time (relative to the window start) of position p in the phase-major layout of dilation d
+ZVX_HD int pos_to_tau(int p, int d, int Wp)
+{
+    const int wd = Wp / d;
+    return (p % wd) * d + p / wd;
+}
+ZVX_HD int tau_to_pos(int tau, int d, int Wp)
+{
+    const int wd = Wp / d;
+    return (tau % d) * wd + tau / d;
+}
+
+// Scatter-table entry: where the element (shift s, column n') of a layer's output goes in the
+// NEXT layer's input buffer.  unit = 16-byte row index inside the buffer (group 0), tau = its
+// time inside the window.
+constexpr uint32_t TBL_VALID = 0x80000000u;
+ZVX_HD uint32_t tbl_pack(int unit, int tau) { return TBL_VALID | ((uint32_t)tau << 16) | (uint32_t)unit; }
+ZVX_HD int tbl_unit(uint32_t e) { return (int)(e & 0xFFFFu); }
+ZVX_HD int tbl_tau(uint32_t e) { return (int)((e >> 16) & 0x7FFFu); }
+
+// unit index of time tau in a buffer laid out for dilation d
+ZVX_HD int dest_unit(int tau, int d, int Wp, int S, int groups)
+{
+    const int p = tau_to_pos(tau, d, Wp);
+    const int q = p % S, row = p / S;
+    return q * groups * NROWS + GUARD + row;
+}
+
+struct Layer {
+    int             k;          // taps
+    int             d;          // dilation (layout of this layer's input and output positions)
+    int             accumulate; // 0: conv1 -> H accumulator (fresh); 1: conv2 -> accumulates onto y
+    float           out_slope;  // leaky-relu slope applied to (acc + bias) before the fp16 store
+    const uint16_t *w;          // packed fp16: [K-step][2 groups][tap block][oc][8]
+    const float    *bias;       // [CH]: conv1: its bias; conv2: cumulative sum of conv2 biases so far
+    const uint32_t *tbl;        // [S][NCOL] scatter into the next layer's buffer (unused for the last)
+};
+
+struct Params {
+    const float    *y_in;       // [rows][CH] fp32 block input (up-conv output)
+    const float    *acc_in;     // running sum over residual blocks or null, indexed like out
+    float          *out;        // [rows][CH] fp32
+    float           scale;      // out = (acc_in + y) * scale when has_scale
+    int             has_scale;
+    float           in_slope;   // leaky-relu slope of the first conv input (0.1)
+    const uint32_t *tbl0;       // [S][NCOL] scatter of the block input into layer 0's buffer
+    int             nlayers;
+    Layer           L[MAX_LAYERS];
+    const int      *seg_start;  // [B+1] utterance prefix in frames
+    const int      *win_start;  // [B+1] prefix of windows per utterance
+    int             B;
+    int             rate;       // rows per frame at this stage
+    int             halo;       // sum of pads of all layers
+    int             valid;      // output time steps per window = WP - 2 halo
+    int            *err_flag;
+};
+
+}  // namespace mrf
+}  // namespace zvx

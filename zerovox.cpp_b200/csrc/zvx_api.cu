@@ -16,6 +16,7 @@
 
 #include "../../include/zvx.h"
 #include "zvx_internal.h"
+#include "mrf_fused_host.h"
 
 using namespace zvx;
 
@@ -42,6 +43,16 @@ struct ConvLayer {
     const float  *bias = nullptr;
     std::vector<ConvVariant> var;
 };
+
+// one launch of the fused MRF kernel: conv pairs [p0, p1) of a residual block
+struct FusedChain {
+    int p0 = 0, p1 = 0, halo = 0, valid = 0, wincfg = 0, nlayers = 0;
+    mrf::Layer layers[mrf::MAX_LAYERS];
+    const uint32_t *tbl0 = nullptr;
+    double flops_per_row = 0.0;
+};
+struct FusedBlock { int CH = 0, k = 0; std::vector<FusedChain> chains; };
+struct WinCfg { int rate_idx, valid; };
 
 struct ResBlkW  { ConvLayer conv1, conv2, conv1x1; bool learned_sc = false; const float *n1w, *n1b, *n2w, *n2b; int cin, cout; };
 struct AdaBlkW  { ConvLayer conv1, conv2, conv1x1; bool learned_sc = false; int ada1, ada2; int cin, cout; };
@@ -72,6 +83,13 @@ struct zvx_ctx {
     std::vector<ConvLayer> up;                    // per stage, var = phases
     std::vector<ConvLayer> mrf1, mrf2;            // [stage*nb*nd + j*nd + d]
     ConvLayer output_conv;
+    std::vector<FusedBlock> fused;                // [stage*nb + j]; CH == 0: not fused
+    std::vector<WinCfg> wincfg;                   // window tilings used by the fused chains
+    std::map<std::vector<int>, const uint32_t *> tbl_cache;
+    int use_fused = 1;
+    double fused_min_eff = 0.8;
+    int *d_wins = nullptr;                        // [nwincfg][B+1] window prefixes
+    std::vector<int> total_wins;
     std::vector<int> rates;                       // rows per frame after stage i (index 0 = 1)
     std::vector<int> chans;                       // channels after stage i (index 0 = input conv out)
 
@@ -191,7 +209,7 @@ int pack_variant(zvx_ctx *ctx, const std::vector<__half> &raw, int OC, int IC, i
 }
 
 // host copies of raw conv weights are needed for packing
-struct HostW { std::map<std::string, std::vector<__half>> h; };
+struct HostW { std::map<std::string, std::vector<__half>> h; std::map<std::string, std::vector<float>> f; };
 
 int make_conv(zvx_ctx *ctx, HostW &hw, const std::string &prefix, bool with_bias, int dilation, ConvLayer &L,
               int force_pad = -1)
@@ -326,6 +344,100 @@ int build_decoder(zvx_ctx *ctx, HostW &hw)
     return 0;
 }
 
+template <typename T>
+int upload_vec(zvx_ctx *ctx, const std::vector<T> &v, const T **out)
+{
+    T *d = nullptr;
+    if (dev_alloc(ctx, &d, v.size())) return 1;
+    CK(ctx, cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = d;
+    return 0;
+}
+
+int get_table(zvx_ctx *ctx, int CH, int d_cur, int d_next, const uint32_t **out)
+{
+    const std::vector<int> key = {CH, d_cur, d_next};
+    auto it = ctx->tbl_cache.find(key);
+    if (it != ctx->tbl_cache.end()) { *out = it->second; return 0; }
+    if (upload_vec(ctx, mrf::make_table(CH, d_cur, d_next), out)) return 1;
+    ctx->tbl_cache[key] = *out;
+    return 0;
+}
+
+// Prepare the fused residual-block launches (mrf_fused.cu) for every stage whose channel count
+// divides 128: packed weights, cumulative conv2 biases, scatter tables, window tilings.
+int build_fused(zvx_ctx *ctx, HostW &hw)
+{
+    const zvx_config &c = ctx->cfg;
+    const int nb = c.num_resblocks, nd = c.num_resblock_dilations;
+    ctx->fused.assign((size_t)c.num_upsamples * nb, FusedBlock());
+    char nm[128];
+    for (int i = 0; i < c.num_upsamples; ++i) {
+        const int CH = ctx->chans[i + 1];
+        if (CH != 32 && CH != 64 && CH != 128) continue;
+        if (2 * nd > mrf::MAX_LAYERS) continue;
+        for (int j = 0; j < nb; ++j) {
+            const size_t idx0 = ((size_t)i * nb + j) * nd;
+            const int k = ctx->mrf1[idx0].K;
+            bool ok = k <= mrf::MAX_K && (k & 1);
+            for (int d = 0; d < nd; ++d) ok = ok && ctx->mrf1[idx0 + d].K == k && ctx->mrf2[idx0 + d].K == k;
+            int dil[8];
+            for (int d = 0; d < nd; ++d) {
+                dil[d] = c.resblock_dilations[j * nd + d];
+                ok = ok && (dil[d] == 1 || dil[d] == 3 || dil[d] == 5);
+            }
+            if (!ok) continue;
+            FusedBlock &fb = ctx->fused[(size_t)i * nb + j];
+            fb.k = k;
+            std::vector<float> cum(CH, 0.f);
+            for (const mrf::ChainPlan &cp : mrf::plan_chains(CH, k, dil, nd, ctx->fused_min_eff)) {
+                if (cp.valid <= 0) return fail(ctx, "fused MRF: window too small for kernel %d", k);
+                FusedChain fc;
+                fc.p0 = cp.p0; fc.p1 = cp.p1; fc.halo = cp.halo; fc.valid = cp.valid;
+                fc.nlayers = 2 * (cp.p1 - cp.p0);
+                fc.wincfg = -1;
+                for (size_t w = 0; w < ctx->wincfg.size(); ++w)
+                    if (ctx->wincfg[w].rate_idx == i + 1 && ctx->wincfg[w].valid == cp.valid) fc.wincfg = (int)w;
+                if (fc.wincfg < 0) { ctx->wincfg.push_back({i + 1, cp.valid}); fc.wincfg = (int)ctx->wincfg.size() - 1; }
+                if (get_table(ctx, CH, 1, dil[cp.p0], &fc.tbl0)) return 1;
+                for (int l = 0; l < fc.nlayers; ++l) {
+                    const int p = cp.p0 + l / 2;
+                    const bool second = l & 1;
+                    snprintf(nm, sizeof nm, "_meldec.blocks.%d.convs%d.%d.1", i * nb + j, second ? 2 : 1, p);
+                    const std::string name = nm;
+                    mrf::Layer &L = fc.layers[l];
+                    L.k = k;
+                    L.d = second ? 1 : dil[p];
+                    L.accumulate = second ? 1 : 0;
+                    L.out_slope = 0.1f;
+                    const std::vector<__half> &raw = hw.h[name + ".w"];
+                    const std::vector<float> &bias = hw.f[name + ".b"];
+                    if ((int)raw.size() != CH * CH * k || (int)bias.size() != CH) return fail(ctx, "%s: unexpected size for the fused path", nm);
+                    if (upload_vec(ctx, mrf::pack_weights(reinterpret_cast<const uint16_t *>(raw.data()), CH, k), &L.w)) return 1;
+                    if (second) {
+                        for (int q = 0; q < CH; ++q) cum[q] += bias[q];   // y_true = accumulator + sum of conv2 biases so far
+                        if (upload_vec(ctx, cum, &L.bias)) return 1;
+                    } else {
+                        L.bias = ctx->mrf1[idx0 + p].bias;
+                    }
+                    L.tbl = nullptr;
+                    if (l + 1 < fc.nlayers) {
+                        const int d_next = (l & 1) ? dil[p + 1] : 1;
+                        if (get_table(ctx, CH, L.d, d_next, &L.tbl)) return 1;
+                    }
+                    fc.flops_per_row += 2.0 * CH * CH * k;
+                }
+                // the cumulative bias restarts with every launch: y is re-read in fp32 with the
+                // previous launches' biases already folded in
+                std::fill(cum.begin(), cum.end(), 0.f);
+                fb.chains.push_back(fc);
+            }
+            fb.CH = CH;
+        }
+    }
+    return 0;
+}
+
 int build_vocoder(zvx_ctx *ctx, HostW &hw)
 {
     const zvx_config &c = ctx->cfg;
@@ -358,6 +470,7 @@ int build_vocoder(zvx_ctx *ctx, HostW &hw)
                     return fail(ctx, "%s: channel mismatch", nm);
             }
     }
+    if (build_fused(ctx, hw)) return 1;
     if (ctx->rates.back() != c.hop_size) return fail(ctx, "product of upsample_scales (%d) != hop_size (%d)", ctx->rates.back(), c.hop_size);
     if (make_conv(ctx, hw, "_meldec.output_conv.1", true, 1, ctx->output_conv, (c.kernel_size - 1) / 2)) return 1;
     if (ctx->output_conv.OC != 1 || ctx->output_conv.IC != ctx->chans.back()) return fail(ctx, "output_conv shape mismatch");
@@ -378,18 +491,21 @@ int reserve(zvx_ctx *ctx, int64_t frames, int batch)
     if (batch > ctx->cap_batch) {
         const int nb = std::max(batch, 64);
         const int nr = (int)std::max<size_t>(ctx->rates.size(), 1);
-        dev_free(ctx, ctx->d_seg); dev_free(ctx, ctx->d_tiles); dev_free(ctx, ctx->mu); dev_free(ctx, ctx->rstd);
+        const int nw = (int)std::max<size_t>(ctx->wincfg.size(), 1);
+        dev_free(ctx, ctx->d_seg); dev_free(ctx, ctx->d_tiles); dev_free(ctx, ctx->d_wins); dev_free(ctx, ctx->mu); dev_free(ctx, ctx->rstd);
         dev_free(ctx, ctx->adain_gb); dev_free(ctx, ctx->style);
         if (ctx->stream) cudaStreamSynchronize(ctx->stream);
         if (ctx->pin_tables) cudaFreeHost(ctx->pin_tables);
         ctx->pin_tables = nullptr;
         ctx->tables_pending = false;
-        if (dev_alloc(ctx, &ctx->d_seg, nb + 1) || dev_alloc(ctx, &ctx->d_tiles, (size_t)nr * (nb + 1))) return 1;
+        if (dev_alloc(ctx, &ctx->d_seg, nb + 1) || dev_alloc(ctx, &ctx->d_tiles, (size_t)nr * (nb + 1)) ||
+            dev_alloc(ctx, &ctx->d_wins, (size_t)nw * (nb + 1)))
+            return 1;
         const int maxc = 2 * c.dim_in + c.residual_dim;
         if (dev_alloc(ctx, &ctx->mu, (size_t)nb * maxc) || dev_alloc(ctx, &ctx->rstd, (size_t)nb * maxc)) return 1;
         if (dev_alloc(ctx, &ctx->adain_gb, (size_t)nb * std::max(ctx->adain.total, 1))) return 1;
         if (dev_alloc(ctx, &ctx->style, (size_t)nb * c.style_dim)) return 1;
-        CK(ctx, cudaMallocHost(&ctx->pin_tables, sizeof(int) * (size_t)(nr + 1) * (nb + 1)));
+        CK(ctx, cudaMallocHost(&ctx->pin_tables, sizeof(int) * (size_t)(nr + 1 + nw) * (nb + 1)));
         ctx->cap_batch = nb;
     }
     if (frames > ctx->cap_frames) {
@@ -451,6 +567,16 @@ int set_batch(zvx_ctx *ctx, int B, const int32_t *L, bool reserve_workspace = tr
     for (int r = 0; r < std::max(nr, 1); ++r)
         CK(ctx, cudaMemcpyAsync(ctx->d_tiles + (size_t)r * stride, tab + (size_t)(r + 1) * stride, sizeof(int) * (B + 1),
                                 cudaMemcpyHostToDevice, ctx->stream));
+    // window prefixes of the fused MRF chains: ceil(rows / valid) windows per utterance
+    ctx->total_wins.assign(ctx->wincfg.size(), 0);
+    for (size_t w = 0; w < ctx->wincfg.size(); ++w) {
+        int *t = tab + (size_t)(std::max(nr, 1) + 1 + w) * stride;
+        const int rate = ctx->rates[ctx->wincfg[w].rate_idx], valid = ctx->wincfg[w].valid;
+        t[0] = 0;
+        for (int b = 0; b < B; ++b) t[b + 1] = t[b] + (int)(((int64_t)L[b] * rate + valid - 1) / valid);
+        ctx->total_wins[w] = t[B];
+        CK(ctx, cudaMemcpyAsync(ctx->d_wins + w * stride, t, sizeof(int) * (B + 1), cudaMemcpyHostToDevice, ctx->stream));
+    }
     CK(ctx, cudaEventRecord(ctx->tables_event, ctx->stream));
     ctx->tables_pending = true;
     ctx->last_B = B;
@@ -661,6 +787,46 @@ int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out)
         }
         // MRF: three residual blocks on U, averaged (hifigan.cpp:300-315, :97-183)
         for (int j = 0; j < nb; ++j) {
+            const FusedBlock &fb = ctx->fused[(size_t)i * nb + j];
+            if (ctx->use_fused && !ctx->use_ref_kernels && fb.CH) {
+                // whole residual block (or chains of its conv pairs) on chip: mrf_fused.cu
+                float *tmp[2] = {ctx->Y1, vout[(i + 1) & 1]};     // the stage-input buffer is free after the up-conv
+                const float *yin = ctx->U;
+                for (size_t q = 0; q < fb.chains.size(); ++q) {
+                    const FusedChain &fc = fb.chains[q];
+                    const bool lastc = q + 1 == fb.chains.size();
+                    mrf::Params fp;
+                    memset(&fp, 0, sizeof fp);
+                    fp.y_in = yin;
+                    fp.in_slope = 0.1f;
+                    fp.tbl0 = fc.tbl0;
+                    fp.nlayers = fc.nlayers;
+                    for (int l = 0; l < fc.nlayers; ++l) fp.L[l] = fc.layers[l];
+                    fp.seg_start = ctx->d_seg;
+                    fp.win_start = ctx->d_wins + (size_t)fc.wincfg * (ctx->cap_batch + 1);
+                    fp.B = ctx->last_B;
+                    fp.rate = ctx->rates[i + 1];
+                    fp.halo = fc.halo;
+                    fp.valid = fc.valid;
+                    fp.err_flag = ctx->d_err;
+                    if (!lastc) {
+                        fp.out = tmp[q & 1];
+                    } else if (j == 0 && nb > 1) {
+                        fp.out = ctx->CS;                              // cs = y_0
+                    } else {
+                        fp.acc_in = j > 0 ? ctx->CS : nullptr;         // cs = cs + y_j
+                        if (j == nb - 1) { fp.out = vout[i & 1]; if (nb > 1) { fp.has_scale = 1; fp.scale = third; } }
+                        else fp.out = ctx->CS;
+                    }
+                    ctx->launches++;
+                    const double rows = (double)ctx->last_frames * fp.rate;
+                    if (prof_begin(ctx, ZVX_K_MRF_CONV, i, rows * fc.flops_per_row, 0.0)) return 1;
+                    CK(ctx, mrf_fused_launch(fb.CH, fp, ctx->total_wins[fc.wincfg], ctx->stream));
+                    if (prof_end(ctx)) return 1;
+                    yin = fp.out;
+                }
+                continue;
+            }
             float *Y = (j == 0) ? ctx->CS : ctx->Y1;
             for (int d = 0; d < nd; ++d) {
                 const size_t idx = ((size_t)i * nb + j) * nd + d;
@@ -798,6 +964,7 @@ int zvx_create(zvx_ctx **out, const zvx_config *cfg, const zvx_tensor_desc *weig
     CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CKC(cudaEventCreateWithFlags(&ctx->tables_event, cudaEventDisableTiming));
     CKC(conv_umma_init());
+    CKC(mrf_fused_init());
     if (dev_alloc(ctx, &ctx->d_err, 1)) return bail();
     CKC(cudaMemset(ctx->d_err, 0, sizeof(int)));
 
@@ -821,6 +988,9 @@ int zvx_create(zvx_ctx **out, const zvx_config *cfg, const zvx_tensor_desc *weig
         if (t.dtype == ZVX_F16) {
             const __half *h = reinterpret_cast<const __half *>(t.data);
             hw.h[t.name].assign(h, h + n);
+        } else if (n <= 4096) {
+            const float *f = reinterpret_cast<const float *>(t.data);
+            hw.f[t.name].assign(f, f + n);
         }
     }
     if (cfg->with_decoder && build_decoder(ctx, hw)) return bail();
@@ -889,6 +1059,7 @@ int64_t zvx_profile_end(zvx_ctx *ctx, zvx_launch_record *recs, int64_t max_recs)
 
 void zvx_set_debug_kernels(zvx_ctx *ctx, int32_t v) { if (ctx) ctx->use_ref_kernels = v; }
 void zvx_set_debug_stop(zvx_ctx *ctx, int32_t s) { if (ctx) ctx->debug_stop = s; }
+void zvx_set_fused_mrf(zvx_ctx *ctx, int32_t on) { if (ctx) ctx->use_fused = on; }
 
 int zvx_synth_batch_device(zvx_ctx *ctx, int32_t B, const float *d_enc, const float *d_style, const int32_t *L,
                            float *d_mel, float *d_wav, int32_t sync)
@@ -973,6 +1144,24 @@ int zvx_vocode(zvx_ctx *ctx, const float *mel, int32_t L, float *wav)
     if (run_vocoder(ctx, ctx->mel, ctx->wav)) return 1;
     if (ctx->debug_stop < 0)
         CK(ctx, cudaMemcpyAsync(wav, ctx->wav, sizeof(float) * (size_t)L * c.hop_size, cudaMemcpyDeviceToHost, ctx->stream));
+    return check_device_error(ctx);
+}
+
+int zvx_vocode_batch(zvx_ctx *ctx, int32_t B, const float *const *mel, const int32_t *L, float *const *wav)
+{
+    if (!ctx) return 1;
+    if (!ctx->cfg.with_vocoder) return fail(ctx, "context was built without vocoder");
+    if (!mel || !L || !wav) return fail(ctx, "zvx_vocode_batch: null argument");
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (set_batch(ctx, B, L)) return 1;
+    const zvx_config &c = ctx->cfg;
+    for (int b = 0; b < B; ++b)
+        CK(ctx, cudaMemcpyAsync(ctx->mel + (size_t)ctx->h_seg[b] * c.num_mels, mel[b], sizeof(float) * (size_t)L[b] * c.num_mels,
+                                cudaMemcpyHostToDevice, ctx->stream));
+    if (run_vocoder(ctx, ctx->mel, ctx->wav)) return 1;
+    for (int b = 0; b < B; ++b)
+        CK(ctx, cudaMemcpyAsync(wav[b], ctx->wav + (size_t)ctx->h_seg[b] * c.hop_size, sizeof(float) * (size_t)L[b] * c.hop_size,
+                                cudaMemcpyDeviceToHost, ctx->stream));
     return check_device_error(ctx);
 }
 

@@ -6,6 +6,7 @@
 #include <stddef.h>
 
 #include "zvx_common.cuh"
+#include "mrf_fused.cuh"
 
 namespace zvx {
 
@@ -17,6 +18,10 @@ cudaError_t conv_umma_launch(const ConvParams &p, int total_tiles, size_t smem, 
 
 // conv_ref.cu (validation kernel: plain CUDA cores, same prologue/epilogue arithmetic) ---
 cudaError_t conv_ref_launch(const ConvParams &p, int total_tiles, cudaStream_t st);
+
+// mrf_fused.cu (fused MRF residual block, swapped-orientation implicit GEMM) -------------------
+cudaError_t mrf_fused_init();   // once per device: opt in to > 48 KB dynamic smem
+cudaError_t mrf_fused_launch(int CH, const mrf::Params &p, int total_windows, cudaStream_t st);
 
 // aux_kernels.cu ---------------------------------------------------------------------
 // per-(utterance, channel) InstanceNorm statistics over the utterance's rows
