@@ -28,12 +28,20 @@ namespace {
 
 constexpr int F_THREADS   = 320;
 constexpr int F_EPI       = 256;
-constexpr int F_HEADER    = 1024;
+constexpr int F_HEADER    = 512;
 constexpr int F_MAX_SLOTS = 8;
 
-__device__ __forceinline__ void sts_u16(uint32_t addr, uint16_t v)
+template <int CH>
+__host__ __device__ constexpr int f_tables_bytes() { return 2 * mrf::Geo<CH>::S * mrf::NCOL * 4; }
+
+__device__ __forceinline__ float lrelu_max(float x, float a)
 {
-    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+    // max(x, a x) == ggml's max(x,0) + a min(x,0) for 0 < a < 1 (up to the sign of zero)
+    return fmaxf(x, __fmul_rn(a, x));
+}
+__device__ __forceinline__ void epi_bar_sync()
+{
+    asm volatile("bar.sync 1, 256;" ::: "memory");
 }
 
 template <int CH>
@@ -41,22 +49,27 @@ __global__ void __launch_bounds__(F_THREADS, 1) mrf_fused_kernel(const mrf::Para
 {
     using G = mrf::Geo<CH>;
     constexpr int S = G::S;
+    constexpr int TBL_WORDS = S * mrf::NCOL;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t *bars      = reinterpret_cast<uint64_t *>(smem);
     uint64_t *w_full    = bars;                        // [F_MAX_SLOTS]
     uint64_t *w_empty   = bars + F_MAX_SLOTS;          // [F_MAX_SLOTS]
     uint64_t *acc_full  = bars + 2 * F_MAX_SLOTS;
     uint64_t *act_ready = bars + 2 * F_MAX_SLOTS + 1;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 512);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 256);
+    uint32_t *tbl_s     = reinterpret_cast<uint32_t *>(smem + F_HEADER);     // [2][S][NCOL]
+    constexpr uint32_t OFF_BUF0 = F_HEADER + f_tables_bytes<CH>();
+    constexpr uint32_t OFF_BUF1 = OFF_BUF0 + G::BUF;
+    constexpr uint32_t OFF_RING = OFF_BUF1 + G::BUF;
 
     const int tid  = threadIdx.x;
     const int warp = tid >> 5;
     const int lane = tid & 31;
 
     const uint32_t smem_base = smem_u32(smem);
-    const uint32_t buf0      = smem_base + F_HEADER;
-    const uint32_t buf1      = buf0 + G::BUF;
-    const uint32_t ring      = buf1 + G::BUF;
+    const uint32_t buf0      = smem_base + OFF_BUF0;
+    const uint32_t buf1      = smem_base + OFF_BUF1;
+    const uint32_t ring      = smem_base + OFF_RING;
 
     // ---- which window of which utterance ----
     const int win = blockIdx.x;
@@ -71,7 +84,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) mrf_fused_kernel(const mrf::Para
     // ---- one-time setup: zero both activation buffers (guard rows and never-written rows must
     //      read as finite zeros), barriers, tensor memory ----
     {
-        uint4 *z = reinterpret_cast<uint4 *>(smem + F_HEADER);
+        uint4 *z = reinterpret_cast<uint4 *>(smem + OFF_BUF0);
         for (int i = tid; i < 2 * G::BUF / 16; i += F_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     if (tid == 0) {
@@ -102,8 +115,11 @@ __global__ void __launch_bounds__(F_THREADS, 1) mrf_fused_kernel(const mrf::Para
 
         // ---- prologue: y window -> tensor memory (fp32), lrelu(y) -> buffer 0 (fp16) ----
         {
+            for (int i = tid; i < TBL_WORDS; i += F_EPI) tbl_s[TBL_WORDS + i] = __ldg(p.tbl0 + i);
+            epi_bar_sync();
             const float *yin = p.y_in + row0 * CH + oc;
-            const uint32_t *tb0 = p.tbl0 + s * mrf::NCOL;
+            const uint32_t *tb = tbl_s + TBL_WORDS + s * mrf::NCOL;
+            uint8_t *dst = smem + OFF_BUF0 + toff;
 #pragma unroll 1
             for (int b = 0; b < 4; ++b) {
                 const int col0 = half * 128 + b * 32;
@@ -118,11 +134,13 @@ __global__ void __launch_bounds__(F_THREADS, 1) mrf_fused_kernel(const mrf::Para
                 }
                 tmem_st32(tlane + 256u + (uint32_t)col0, v);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const uint32_t e = __ldg(tb0 + col0 + i);
-                    if (e & mrf::TBL_VALID) {
-                        const float x = lrelu_f(__uint_as_float(v[i]), p.in_slope);
-                        sts_u16(buf0 + (uint32_t)mrf::tbl_unit(e) * 16u + toff, __half_as_ushort(__float2half_rn(x)));
+                for (int i4 = 0; i4 < 8; ++i4) {
+                    const uint4 e4 = *reinterpret_cast<const uint4 *>(tb + col0 + 4 * i4);
+                    const uint32_t e[4] = {e4.x, e4.y, e4.z, e4.w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const __half h = __float2half_rn(lrelu_max(__uint_as_float(v[4 * i4 + q]), p.in_slope));
+                        if (e[q] & mrf::TBL_VALID) *reinterpret_cast<__half *>(dst + mrf::tbl_byte(e[q])) = h;
                     }
                 }
             }
@@ -139,11 +157,18 @@ __global__ void __launch_bounds__(F_THREADS, 1) mrf_fused_kernel(const mrf::Para
             const bool last = l == p.nlayers - 1;
             const float bias = __ldg(L.bias + oc);
             const uint32_t acc = tlane + (L.accumulate ? 256u : 0u);
-            const uint32_t obuf = (l & 1) ? buf0 : buf1;
+            if (!last) {
+                // stage this layer's scatter table while the MMAs run (double-buffered: a warp can only
+                // be one layer ahead of the slowest one, which reads the other copy)
+                uint32_t *tdst = tbl_s + (l & 1) * TBL_WORDS;
+                for (int i = tid; i < TBL_WORDS; i += F_EPI) tdst[i] = __ldg(L.tbl + i);
+                epi_bar_sync();
+            }
             mbar_wait(smem_u32(acc_full), (uint32_t)l & 1u, p.err_flag);
             tc_fence_after_sync();
             if (!last) {
-                const uint32_t *tb = L.tbl + s * mrf::NCOL;
+                const uint32_t *tb = tbl_s + (l & 1) * TBL_WORDS + s * mrf::NCOL;
+                uint8_t *dst = smem + ((l & 1) ? OFF_BUF0 : OFF_BUF1) + toff;
                 const float slope = L.out_slope;
 #pragma unroll 1
                 for (int b = 0; b < 4; ++b) {
@@ -151,15 +176,17 @@ __global__ void __launch_bounds__(F_THREADS, 1) mrf_fused_kernel(const mrf::Para
                     uint32_t r[32];
                     tmem_ld32(acc + (uint32_t)col0, r);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const uint32_t e = __ldg(tb + col0 + i);
-                        if (e & mrf::TBL_VALID) {
-                            float v = lrelu_f(__fadd_rn(__uint_as_float(r[i]), bias), slope);
+                    for (int i4 = 0; i4 < 8; ++i4) {
+                        const uint4 e4 = *reinterpret_cast<const uint4 *>(tb + col0 + 4 * i4);
+                        const uint32_t e[4] = {e4.x, e4.y, e4.z, e4.w};
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            float v = lrelu_max(__fadd_rn(__uint_as_float(r[4 * i4 + q]), bias), slope);
                             if (!interior) {
-                                const int t = tw + mrf::tbl_tau(e);
+                                const int t = tw + mrf::tbl_tau(e[q]);
                                 if (t < 0 || t >= T) v = 0.f;
                             }
-                            sts_u16(obuf + (uint32_t)mrf::tbl_unit(e) * 16u + toff, __half_as_ushort(__float2half_rn(v)));
+                            if (e[q] & mrf::TBL_VALID) *reinterpret_cast<__half *>(dst + mrf::tbl_byte(e[q])) = __float2half_rn(v);
                         }
                     }
                 }
@@ -175,13 +202,22 @@ __global__ void __launch_bounds__(F_THREADS, 1) mrf_fused_kernel(const mrf::Para
                     const int col0 = half * 128 + b * 32;
                     uint32_t r[32];
                     tmem_ld32(acc + (uint32_t)col0, r);
+                    float a[32];
+                    if (ain) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const int tau = S * (col0 + i) + s;
+                            const int t   = tw + tau;
+                            a[i] = (tau >= p.halo && tau < p.halo + p.valid && t < T) ? ain[(size_t)t * CH] : 0.f;
+                        }
+                    }
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         const int tau = S * (col0 + i) + s;
                         const int t   = tw + tau;
                         if (tau >= p.halo && tau < p.halo + p.valid && t < T) {
                             float v = __fadd_rn(__uint_as_float(r[i]), bias);
-                            if (ain) v = __fadd_rn(ain[(size_t)t * CH], v);
+                            if (ain) v = __fadd_rn(a[i], v);
                             if (p.has_scale) v = __fmul_rn(v, p.scale);
                             out[(size_t)t * CH] = v;
                         }
@@ -262,7 +298,7 @@ cudaError_t launch_ch(const mrf::Params &p, int total_windows, cudaStream_t st)
     using G = mrf::Geo<CH>;
     uint32_t slot = 0;
     for (int l = 0; l < p.nlayers; ++l) slot = max(slot, mrf::chunk_bytes(p.L[l].k, G::S, CH));
-    const size_t fixed = F_HEADER + 2 * (size_t)G::BUF;
+    const size_t fixed = F_HEADER + f_tables_bytes<CH>() + 2 * (size_t)G::BUF;
     const size_t budget = 227 * 1024;
     int nslots = (int)((budget - fixed) / slot);
     if (nslots < 1) return cudaErrorInvalidConfiguration;

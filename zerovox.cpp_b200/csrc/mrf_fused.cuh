@@ -89,10 +89,12 @@ ZVX_HD int tau_to_pos(int tau, int d, int Wp)
 // Scatter-table entry: where the element (shift s, column n') of a layer's output goes in the
 // NEXT layer's input buffer.  unit = 16-byte row index inside the buffer (group 0), tau = its
 // time inside the window.
+// Packed as: bit 31 valid, bits 17-30 tau, bits 0-16 byte offset of the row (unit * 16).
 constexpr uint32_t TBL_VALID = 0x80000000u;
-ZVX_HD uint32_t tbl_pack(int unit, int tau) { return TBL_VALID | ((uint32_t)tau << 16) | (uint32_t)unit; }
-ZVX_HD int tbl_unit(uint32_t e) { return (int)(e & 0xFFFFu); }
-ZVX_HD int tbl_tau(uint32_t e) { return (int)((e >> 16) & 0x7FFFu); }
+ZVX_HD uint32_t tbl_pack(int unit, int tau) { return TBL_VALID | ((uint32_t)tau << 17) | ((uint32_t)unit * 16u); }
+ZVX_HD int tbl_unit(uint32_t e) { return (int)((e & 0x1FFFFu) >> 4); }
+ZVX_HD uint32_t tbl_byte(uint32_t e) { return e & 0x1FFFFu; }
+ZVX_HD int tbl_tau(uint32_t e) { return (int)((e >> 17) & 0x3FFFu); }
 
 // unit index of time tau in a buffer laid out for dilation d
 ZVX_HD int dest_unit(int tau, int d, int Wp, int S, int groups)
