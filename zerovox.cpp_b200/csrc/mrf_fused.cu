@@ -26,8 +26,11 @@ namespace zvx {
 
 namespace {
 
-constexpr int F_THREADS   = 320;
-constexpr int F_EPI       = 256;
+constexpr int F_EPI_WARPS = 16;                 // 4 per lane quarter, 64 columns each
+constexpr int F_EPI       = F_EPI_WARPS * 32;
+constexpr int F_THREADS   = F_EPI + 64;
+constexpr int F_COLS_PER_WARP = mrf::NCOL / (F_EPI_WARPS / 4);
+constexpr int F_BATCHES   = F_COLS_PER_WARP / 32;
 constexpr int F_HEADER    = 512;
 constexpr int F_MAX_SLOTS = 8;
 
@@ -41,7 +44,7 @@ __device__ __forceinline__ float lrelu_max(float x, float a)
 }
 __device__ __forceinline__ void epi_bar_sync()
 {
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(F_EPI) : "memory");
 }
 
 template <int CH>
@@ -96,17 +99,17 @@ __global__ void __launch_bounds__(F_THREADS, 1) mrf_fused_kernel(const mrf::Para
         mbar_init(smem_u32(act_ready), F_EPI);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 8) tmem_alloc(smem_u32(tmem_slot), 512u);
+    if (warp == F_EPI_WARPS) tmem_alloc(smem_u32(tmem_slot), 512u);
     fence_proxy_async_smem();
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 8) {
+    if (warp < F_EPI_WARPS) {
         // =================== prologue + epilogues ===================
         const int quarter = warp & 3;
-        const int half    = warp >> 2;
+        const int part    = warp >> 2;
         const int m       = quarter * 32 + lane;
         const int s       = m / CH;
         const int oc      = m % CH;
@@ -121,8 +124,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) mrf_fused_kernel(const mrf::Para
             const uint32_t *tb = tbl_s + TBL_WORDS + s * mrf::NCOL;
             uint8_t *dst = smem + OFF_BUF0 + toff;
 #pragma unroll 1
-            for (int b = 0; b < 4; ++b) {
-                const int col0 = half * 128 + b * 32;
+            for (int b = 0; b < F_BATCHES; ++b) {
+                const int col0 = part * F_COLS_PER_WARP + b * 32;
                 uint32_t v[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
@@ -171,8 +174,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) mrf_fused_kernel(const mrf::Para
                 uint8_t *dst = smem + ((l & 1) ? OFF_BUF0 : OFF_BUF1) + toff;
                 const float slope = L.out_slope;
 #pragma unroll 1
-                for (int b = 0; b < 4; ++b) {
-                    const int col0 = half * 128 + b * 32;
+                for (int b = 0; b < F_BATCHES; ++b) {
+                    const int col0 = part * F_COLS_PER_WARP + b * 32;
                     uint32_t r[32];
                     tmem_ld32(acc + (uint32_t)col0, r);
 #pragma unroll
@@ -198,8 +201,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) mrf_fused_kernel(const mrf::Para
                 float *out = p.out + row0 * CH + oc;
                 const float *ain = p.acc_in ? p.acc_in + row0 * CH + oc : nullptr;
 #pragma unroll 1
-                for (int b = 0; b < 4; ++b) {
-                    const int col0 = half * 128 + b * 32;
+                for (int b = 0; b < F_BATCHES; ++b) {
+                    const int col0 = part * F_COLS_PER_WARP + b * 32;
                     uint32_t r[32];
                     tmem_ld32(acc + (uint32_t)col0, r);
                     float a[32];
@@ -225,7 +228,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) mrf_fused_kernel(const mrf::Para
                 }
             }
         }
-    } else if (warp == 8) {
+    } else if (warp == F_EPI_WARPS) {
         // =================== MMA issuer ===================
         const uint32_t leader = elect_one();
         const uint32_t idesc  = make_idesc_mn(128, mrf::NCOL);
@@ -286,7 +289,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) mrf_fused_kernel(const mrf::Para
 
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == F_EPI_WARPS) {
         tc_fence_after_sync();
         tmem_dealloc(tmem_base, 512u);
     }
