@@ -10,7 +10,7 @@
 // operands.  This pins the window trick, the polyphase / phase-major layouts, halo handling
 // and the per-layer zero masking at utterance edges without a GPU.
 //
-// usage: mrf_fused_emul CH k T [npairs_min_eff]   -> prints max abs error, exits 1 on mismatch
+// usage: mrf_fused_emul CH k T [min_eff] [ncol]   -> prints max abs error, exits 1 on mismatch
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -96,10 +96,11 @@ static void direct_block(std::vector<float> &y, int T, int CH, const std::vector
     }
 }
 
-template <int CH>
+template <int CH, int NCOL>
 static int run(int k, int T, double min_eff)
 {
-    using G = Geo<CH>;
+    using G = Geo<CH, NCOL>;
+    constexpr int LBO_B = G::LBO_B;
     const int S = G::S, Wp = G::WP, P = 3;
     const int dil[3] = {1, 3, 5};
     std::mt19937 rng(1234 + CH * 100 + k);
@@ -122,7 +123,7 @@ static int run(int k, int T, double min_eff)
 
     // ---- emulate the launches ----
     std::vector<float> cur = y0;
-    const std::vector<ChainPlan> plan = plan_chains(CH, k, dil, P, min_eff);
+    const std::vector<ChainPlan> plan = plan_chains(CH, NCOL, k, dil, P, min_eff);
     for (const ChainPlan &cp : plan) {
         const int nl = 2 * (cp.p1 - cp.p0);
         // per-layer host data, exactly as the library prepares it
@@ -135,9 +136,9 @@ static int run(int k, int T, double min_eff)
             wpk[l] = pack_weights(cv.raw.data(), CH, cv.k);
             if (l & 1) { for (int i = 0; i < CH; ++i) cum[i] += cv.bias[i]; bias[l] = cum; }
             else bias[l] = cv.bias;
-            if (l + 1 < nl) tbl[l] = make_table(CH, cv.d, convs[2 * cp.p0 + l + 1].d);
+            if (l + 1 < nl) tbl[l] = make_table(CH, NCOL, cv.d, convs[2 * cp.p0 + l + 1].d);
         }
-        const std::vector<uint32_t> tbl0 = make_table(CH, 1, convs[2 * cp.p0].d);
+        const std::vector<uint32_t> tbl0 = make_table(CH, NCOL, 1, convs[2 * cp.p0].d);
         std::vector<float> out = cur;
         const int nwin = (T + cp.valid - 1) / cp.valid;
         for (int wi = 0; wi < nwin; ++wi) {
@@ -158,7 +159,9 @@ static int run(int k, int T, double min_eff)
                     const float yv = ok ? cur[(size_t)t * CH + oc] : 0.f;
                     Yacc[(size_t)m * NCOL + n] = yv;
                     const uint32_t e = tbl0[(size_t)s * NCOL + n];
-                    if (e & TBL_VALID) sts16(buf[0], tbl_unit(e), oc, lrelu(yv, 0.1f));
+                    // the stmatrix fast path of the kernel dumps beyond-window elements on the trash row:
+                    // poison it to prove that no valid output ever reads it
+                    sts16(buf[0], tbl_unit(e), oc, (e & TBL_VALID) ? lrelu(yv, 0.1f) : 777.f);
                 }
             }
             for (int l = 0; l < nl; ++l) {
@@ -178,7 +181,7 @@ static int run(int k, int T, double min_eff)
                         const long lbo_a = (long)TB * CH * 16;
                         const long b_start = (long)q * G::SUB + (long)2 * c * LBO_B + (long)(GUARD + ro) * 16;
                         if (a_start < 0 || a_start + lbo_a + 15 * 128 + 7 * 16 + 16 > (long)cb) { printf("A window out of chunk\n"); return 1; }
-                        if (b_start < 0 || b_start + LBO_B + 255 * 16 + 16 > (long)G::BUF) { printf("B tile out of buffer\n"); return 1; }
+                        if (b_start < 0 || b_start + LBO_B + (NCOL - 1) * 16 + 16 > (long)G::BUF) { printf("B tile out of buffer\n"); return 1; }
                         for (int m = 0; m < 128; ++m)
                             for (int n = 0; n < NCOL; ++n) {
                                 float acc = (accum || !first) ? D[(size_t)m * NCOL + n] : 0.f;
@@ -201,7 +204,7 @@ static int run(int k, int T, double min_eff)
                         const float v = D[(size_t)m * NCOL + n] + bias[l][oc];
                         if (!last) {
                             const uint32_t e = tbl[l][(size_t)s * NCOL + n];
-                            if (!(e & TBL_VALID)) continue;
+                            if (!(e & TBL_VALID)) { sts16(ob, tbl_unit(e), oc, 777.f); continue; }
                             const int t = tw + tbl_tau(e);
                             sts16(ob, tbl_unit(e), oc, (t >= 0 && t < T) ? lrelu(v, 0.1f) : 0.f);
                         } else {
@@ -219,17 +222,24 @@ static int run(int k, int T, double min_eff)
         maxerr = std::max(maxerr, (double)std::fabs(ref[i] - cur[i]));
         maxref = std::max(maxref, (double)std::fabs(ref[i]));
     }
-    printf("CH=%d k=%d T=%d launches=%zu max|ref|=%.3f max_abs_err=%.3e\n", CH, k, T, plan.size(), maxref, maxerr);
+    printf("CH=%d NCOL=%d k=%d T=%d launches=%zu max|ref|=%.3f max_abs_err=%.3e\n", CH, NCOL, k, T, plan.size(), maxref, maxerr);
     return maxerr < 2e-3 ? 0 : 1;   // fp16 re-rounding of intermediates can flip an ulp; see DESIGN.md
 }
 
 int main(int argc, char **argv)
 {
-    if (argc < 4) { fprintf(stderr, "usage: %s CH k T [min_eff]\n", argv[0]); return 2; }
+    if (argc < 4) { fprintf(stderr, "usage: %s CH k T [min_eff] [ncol]\n", argv[0]); return 2; }
     const int CH = atoi(argv[1]), k = atoi(argv[2]), T = atoi(argv[3]);
     const double me = argc > 4 ? atof(argv[4]) : 0.0;
-    if (CH == 32) return run<32>(k, T, me);
-    if (CH == 64) return run<64>(k, T, me);
-    if (CH == 128) return run<128>(k, T, me);
+    const int ncol = argc > 5 ? atoi(argv[5]) : 256;
+    if (ncol == 256) {
+        if (CH == 32) return run<32, 256>(k, T, me);
+        if (CH == 64) return run<64, 256>(k, T, me);
+        if (CH == 128) return run<128, 256>(k, T, me);
+    } else if (ncol == 128) {
+        if (CH == 32) return run<32, 128>(k, T, me);
+        if (CH == 64) return run<64, 128>(k, T, me);
+        if (CH == 128) return run<128, 128>(k, T, me);
+    }
     return 2;
 }

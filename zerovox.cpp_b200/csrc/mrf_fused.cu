@@ -5,18 +5,27 @@
 // final epilogue.  Geometry and the reasons for the swapped (weights = A operand) orientation
 // are in mrf_fused.cuh.
 //
-// One CTA (320 threads, 1 per SM) owns one window of WP time steps of one utterance:
-//   warps 0-7  prologue + epilogues.  Thread (quarter q = warp & 3, lane) owns accumulator row
-//              m = 32 q + lane = (shift s, output channel oc); warps 0-3 take columns 0-127,
-//              warps 4-7 columns 128-255.
-//   warp  8    MMA issuer (one elected lane): per layer (k + S - 1) * CH/16 tcgen05.mma of
-//              shape M=128 (weights window) x N=256 (positions) x K=16.
-//   warp  9    weight loader: cp.async.bulk of per-(layer, K-step) chunks into a ring.
-// Tensor memory: columns [0,256) = H accumulator (conv1 output), [256,512) = y.  The residual
-// stream y stays in tensor memory in fp32 for the whole chain: conv2's MMAs accumulate
+// One CTA owns one window of WP time steps of one utterance (NCOL = 256 columns: one CTA per SM,
+// 16 epilogue warps; NCOL = 128: two CTAs per SM, 8 epilogue warps each, so that one CTA's
+// epilogue overlaps the other's MMAs):
+//   epilogue warps  prologue + epilogues.  Warp w works on TMEM lane quarter w & 3 and on the 64
+//              columns [64 (w >> 2), +64).
+//   MMA warp   one elected lane issues, per layer, (k + S - 1) * CH/16 tcgen05.mma of shape
+//              M=128 (weights window) x N=NCOL (positions) x K=16.
+//   loader warp  cp.async.bulk of per-(layer, K-step) weight chunks into a ring.
+// Tensor memory: columns [0,NCOL) = H accumulator (conv1 output), [NCOL,2 NCOL) = y.  The
+// residual stream y stays in tensor memory in fp32 for the whole chain: conv2's MMAs accumulate
 // directly on top of it, its bias is added when y is read (cumulative bias, host-prepared).
 // Shared memory: two activation buffers (fp16, layouts per mrf_fused.cuh) that alternate as
-// MMA B operand / epilogue destination, and the weight ring.
+// MMA B operand / epilogue destination, the staged scatter tables and the weight ring.
+//
+// Epilogue data path.  Interior windows (no utterance edge inside): tcgen05.ld.16x256b hands
+// every thread the accumulator in the mma-fragment layout (row = lane/4 (+8), two adjacent
+// columns per register pair), so after bias + leaky-ReLU + cvt.f16x2 a stmatrix.x4.trans stores
+// four 8(channels) x 8(positions) blocks as 16-byte rows [position][8 channels] -- exactly the
+// K-major operand rows the next MMA reads; row addresses come from the scatter table.  Windows
+// that touch an utterance edge use a scalar path (tcgen05.ld.32x32b, one 2-byte store per
+// element) that also applies the per-layer zero masking (SURVEY.md H-d).
 #include "mrf_fused.cuh"
 #include "ptx_sm100.cuh"
 #include "zvx_common.cuh"
@@ -26,33 +35,78 @@ namespace zvx {
 
 namespace {
 
-constexpr int F_EPI_WARPS = 16;                 // 4 per lane quarter, 64 columns each
-constexpr int F_EPI       = F_EPI_WARPS * 32;
-constexpr int F_THREADS   = F_EPI + 64;
-constexpr int F_COLS_PER_WARP = mrf::NCOL / (F_EPI_WARPS / 4);
-constexpr int F_BATCHES   = F_COLS_PER_WARP / 32;
 constexpr int F_HEADER    = 512;
 constexpr int F_MAX_SLOTS = 8;
-
-template <int CH>
-__host__ __device__ constexpr int f_tables_bytes() { return 2 * mrf::Geo<CH>::S * mrf::NCOL * 4; }
 
 __device__ __forceinline__ float lrelu_max(float x, float a)
 {
     // max(x, a x) == ggml's max(x,0) + a min(x,0) for 0 < a < 1 (up to the sign of zero)
     return fmaxf(x, __fmul_rn(a, x));
 }
-__device__ __forceinline__ void epi_bar_sync()
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi)
 {
-    asm volatile("bar.sync 1, %0;" ::"n"(F_EPI) : "memory");
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ void stmatrix_x4_trans(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d)
+                 : "memory");
+}
+// 16 lanes x 64 columns; thread T gets for column group cg (8 columns): r[4cg+0/1] = (lane T/4,
+// columns 8cg + 2(T%4), +1), r[4cg+2/3] = (lane T/4 + 8, same columns)
+__device__ __forceinline__ void tmem_ld_16x256b_x8(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st_16x256b_x8(uint32_t taddr, const uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.16x256b.x8.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+        "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+        "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
 }
 
-template <int CH>
-__global__ void __launch_bounds__(F_THREADS, 1) mrf_fused_kernel(const mrf::Params p, const int nslots, const uint32_t slot_bytes)
+template <int CH, int NCOL>
+struct FCfg {
+    using G = mrf::Geo<CH, NCOL>;
+    static constexpr int EPI_WARPS = NCOL / 16;            // 64 columns per warp, 4 lane quarters
+    static constexpr int EPI       = EPI_WARPS * 32;
+    static constexpr int THREADS   = EPI + 64;
+    static constexpr int CTAS      = NCOL == 128 ? 2 : 1;
+    static constexpr int TBL_WORDS = G::S * NCOL;
+    static constexpr uint32_t OFF_TBL  = F_HEADER;
+    static constexpr uint32_t OFF_BUF0 = OFF_TBL + 2 * TBL_WORDS * 4;
+    static constexpr uint32_t OFF_BUF1 = OFF_BUF0 + G::BUF;
+    static constexpr uint32_t OFF_RING = OFF_BUF1 + G::BUF;
+    static constexpr size_t   SMEM_BUDGET = NCOL == 128 ? 112 * 1024 : 227 * 1024;
+};
+
+template <int CH, int NCOL>
+__global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
+    mrf_fused_kernel(const mrf::Params p, const int nslots, const uint32_t slot_bytes)
 {
-    using G = mrf::Geo<CH>;
+    using C = FCfg<CH, NCOL>;
+    using G = typename C::G;
     constexpr int S = G::S;
-    constexpr int TBL_WORDS = S * mrf::NCOL;
+    constexpr int TBL_WORDS = C::TBL_WORDS;
+    constexpr int EPI_WARPS = C::EPI_WARPS;
+    constexpr uint32_t LBO_B = G::LBO_B;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t *bars      = reinterpret_cast<uint64_t *>(smem);
     uint64_t *w_full    = bars;                        // [F_MAX_SLOTS]
@@ -60,19 +114,16 @@ __global__ void __launch_bounds__(F_THREADS, 1) mrf_fused_kernel(const mrf::Para
     uint64_t *acc_full  = bars + 2 * F_MAX_SLOTS;
     uint64_t *act_ready = bars + 2 * F_MAX_SLOTS + 1;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 256);
-    uint32_t *tbl_s     = reinterpret_cast<uint32_t *>(smem + F_HEADER);     // [2][S][NCOL]
-    constexpr uint32_t OFF_BUF0 = F_HEADER + f_tables_bytes<CH>();
-    constexpr uint32_t OFF_BUF1 = OFF_BUF0 + G::BUF;
-    constexpr uint32_t OFF_RING = OFF_BUF1 + G::BUF;
+    uint32_t *tbl_s     = reinterpret_cast<uint32_t *>(smem + C::OFF_TBL);     // [2][S][NCOL]
 
     const int tid  = threadIdx.x;
     const int warp = tid >> 5;
     const int lane = tid & 31;
 
     const uint32_t smem_base = smem_u32(smem);
-    const uint32_t buf0      = smem_base + OFF_BUF0;
-    const uint32_t buf1      = smem_base + OFF_BUF1;
-    const uint32_t ring      = smem_base + OFF_RING;
+    const uint32_t buf0      = smem_base + C::OFF_BUF0;
+    const uint32_t buf1      = smem_base + C::OFF_BUF1;
+    const uint32_t ring      = smem_base + C::OFF_RING;
 
     // ---- which window of which utterance ----
     const int win = blockIdx.x;
@@ -87,8 +138,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) mrf_fused_kernel(const mrf::Para
     // ---- one-time setup: zero both activation buffers (guard rows and never-written rows must
     //      read as finite zeros), barriers, tensor memory ----
     {
-        uint4 *z = reinterpret_cast<uint4 *>(smem + OFF_BUF0);
-        for (int i = tid; i < 2 * G::BUF / 16; i += F_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        uint4 *z = reinterpret_cast<uint4 *>(smem + C::OFF_BUF0);
+        for (int i = tid; i < 2 * G::BUF / 16; i += C::THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     if (tid == 0) {
         for (int s = 0; s < nslots; ++s) {
@@ -96,54 +147,89 @@ __global__ void __launch_bounds__(F_THREADS, 1) mrf_fused_kernel(const mrf::Para
             mbar_init(smem_u32(w_empty + s), 1);
         }
         mbar_init(smem_u32(acc_full), 1);
-        mbar_init(smem_u32(act_ready), F_EPI);
+        mbar_init(smem_u32(act_ready), C::EPI);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == F_EPI_WARPS) tmem_alloc(smem_u32(tmem_slot), 512u);
+    if (warp == EPI_WARPS) tmem_alloc(smem_u32(tmem_slot), 2u * NCOL);
     fence_proxy_async_smem();
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < F_EPI_WARPS) {
+    if (warp < EPI_WARPS) {
         // =================== prologue + epilogues ===================
         const int quarter = warp & 3;
-        const int part    = warp >> 2;
+        const int colw    = (warp >> 2) * 64;          // this warp's 64 columns
+        // ---- scalar-path coordinates: thread = accumulator row m ----
         const int m       = quarter * 32 + lane;
         const int s       = m / CH;
         const int oc      = m % CH;
-        const uint32_t toff = (uint32_t)(oc >> 3) * mrf::LBO_B + (uint32_t)(oc & 7) * 2u;
+        const uint32_t toff = (uint32_t)(oc >> 3) * LBO_B + (uint32_t)(oc & 7) * 2u;
         const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        // ---- fragment-path coordinates: per 16-lane half lh, rows rb + lane/4 and rb + lane/4 + 8 ----
+        const int mi = lane >> 3, r8 = lane & 7;       // stmatrix: this thread addresses row r8 of matrix mi
+
+        auto epi_sync = []() { asm volatile("bar.sync 1, %0;" ::"n"(C::EPI) : "memory"); };
 
         // ---- prologue: y window -> tensor memory (fp32), lrelu(y) -> buffer 0 (fp16) ----
         {
-            for (int i = tid; i < TBL_WORDS; i += F_EPI) tbl_s[TBL_WORDS + i] = __ldg(p.tbl0 + i);
-            epi_bar_sync();
-            const float *yin = p.y_in + row0 * CH + oc;
-            const uint32_t *tb = tbl_s + TBL_WORDS + s * mrf::NCOL;
-            uint8_t *dst = smem + OFF_BUF0 + toff;
+            for (int i = tid; i < TBL_WORDS; i += C::EPI) tbl_s[TBL_WORDS + i] = __ldg(p.tbl0 + i);
+            epi_sync();
+            if (interior) {
 #pragma unroll 1
-            for (int b = 0; b < F_BATCHES; ++b) {
-                const int col0 = part * F_COLS_PER_WARP + b * 32;
-                uint32_t v[32];
+                for (int lh = 0; lh < 2; ++lh) {
+                    const int rb  = quarter * 32 + lh * 16;
+                    const int sA  = rb / CH;
+                    const int ocA = rb % CH + (lane >> 2);
+                    const float *yA = p.y_in + (row0 + (size_t)tw) * CH + ocA;
+                    const uint32_t *tb = tbl_s + TBL_WORDS + sA * NCOL + colw;
+                    uint32_t v[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int tau = S * (col0 + i) + s;
-                    const int t   = tw + tau;
-                    float y = 0.f;
-                    if (tau < G::WP && t >= 0 && t < T) y = __ldg(yin + (size_t)t * CH);
-                    v[i] = __float_as_uint(y);
+                    for (int cg = 0; cg < 8; ++cg) {
+                        const int n0 = colw + 8 * cg + 2 * (lane & 3);
+                        const int tau0 = S * n0 + sA, tau1 = tau0 + S;
+                        v[4 * cg + 0] = tau0 < G::WP ? __float_as_uint(__ldg(yA + (size_t)tau0 * CH)) : 0u;
+                        v[4 * cg + 1] = tau1 < G::WP ? __float_as_uint(__ldg(yA + (size_t)tau1 * CH)) : 0u;
+                        v[4 * cg + 2] = tau0 < G::WP ? __float_as_uint(__ldg(yA + (size_t)tau0 * CH + 8)) : 0u;
+                        v[4 * cg + 3] = tau1 < G::WP ? __float_as_uint(__ldg(yA + (size_t)tau1 * CH + 8)) : 0u;
+                    }
+                    tmem_st_16x256b_x8(tmem_base + ((uint32_t)rb << 16) + (uint32_t)(NCOL + colw), v);
+                    const uint32_t gbase = buf0 + (uint32_t)((rb % CH) >> 3) * LBO_B + (uint32_t)(mi & 1) * LBO_B;
+#pragma unroll
+                    for (int pr = 0; pr < 4; ++pr) {
+                        uint32_t f[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int i0 = 8 * pr + 2 * q;   // (cg = 2pr + q/2, row A/B = q & 1)
+                            f[q] = pack_h2(lrelu_max(__uint_as_float(v[i0]), p.in_slope), lrelu_max(__uint_as_float(v[i0 + 1]), p.in_slope));
+                        }
+                        const uint32_t e = tb[8 * (2 * pr + (mi >> 1)) + r8];
+                        stmatrix_x4_trans(gbase + mrf::tbl_byte(e), f[0], f[1], f[2], f[3]);
+                    }
                 }
-                tmem_st32(tlane + 256u + (uint32_t)col0, v);
+            } else {
+                const float *yin = p.y_in + row0 * CH + oc;
+                const uint32_t *tb = tbl_s + TBL_WORDS + s * NCOL;
+                uint8_t *dst = smem + C::OFF_BUF0 + toff;
+#pragma unroll 1
+                for (int b = 0; b < 2; ++b) {
+                    const int col0 = colw + b * 32;
+                    uint32_t v[32];
 #pragma unroll
-                for (int i4 = 0; i4 < 8; ++i4) {
-                    const uint4 e4 = *reinterpret_cast<const uint4 *>(tb + col0 + 4 * i4);
-                    const uint32_t e[4] = {e4.x, e4.y, e4.z, e4.w};
+                    for (int i = 0; i < 32; ++i) {
+                        const int tau = S * (col0 + i) + s;
+                        const int t   = tw + tau;
+                        float y = 0.f;
+                        if (tau < G::WP && t >= 0 && t < T) y = __ldg(yin + (size_t)t * CH);
+                        v[i] = __float_as_uint(y);
+                    }
+                    tmem_st32(tlane + (uint32_t)(NCOL + col0), v);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const __half h = __float2half_rn(lrelu_max(__uint_as_float(v[4 * i4 + q]), p.in_slope));
-                        if (e[q] & mrf::TBL_VALID) *reinterpret_cast<__half *>(dst + mrf::tbl_byte(e[q])) = h;
+                    for (int i = 0; i < 32; ++i) {
+                        const uint32_t e = tb[col0 + i];
+                        const __half h = __float2half_rn(lrelu_max(__uint_as_float(v[i]), p.in_slope));
+                        if (e & mrf::TBL_VALID) *reinterpret_cast<__half *>(dst + mrf::tbl_byte(e)) = h;
                     }
                 }
             }
@@ -158,38 +244,60 @@ __global__ void __launch_bounds__(F_THREADS, 1) mrf_fused_kernel(const mrf::Para
         for (int l = 0; l < p.nlayers; ++l) {
             const mrf::Layer &L = p.L[l];
             const bool last = l == p.nlayers - 1;
-            const float bias = __ldg(L.bias + oc);
-            const uint32_t acc = tlane + (L.accumulate ? 256u : 0u);
+            const uint32_t acc_col = L.accumulate ? (uint32_t)NCOL : 0u;
             if (!last) {
                 // stage this layer's scatter table while the MMAs run (double-buffered: a warp can only
                 // be one layer ahead of the slowest one, which reads the other copy)
                 uint32_t *tdst = tbl_s + (l & 1) * TBL_WORDS;
-                for (int i = tid; i < TBL_WORDS; i += F_EPI) tdst[i] = __ldg(L.tbl + i);
-                epi_bar_sync();
+                for (int i = tid; i < TBL_WORDS; i += C::EPI) tdst[i] = __ldg(L.tbl + i);
+                epi_sync();
             }
             mbar_wait(smem_u32(acc_full), (uint32_t)l & 1u, p.err_flag);
             tc_fence_after_sync();
             if (!last) {
-                const uint32_t *tb = tbl_s + (l & 1) * TBL_WORDS + s * mrf::NCOL;
-                uint8_t *dst = smem + ((l & 1) ? OFF_BUF0 : OFF_BUF1) + toff;
+                const uint32_t obuf_off = (l & 1) ? C::OFF_BUF0 : C::OFF_BUF1;
                 const float slope = L.out_slope;
+                if (interior) {
 #pragma unroll 1
-                for (int b = 0; b < F_BATCHES; ++b) {
-                    const int col0 = part * F_COLS_PER_WARP + b * 32;
-                    uint32_t r[32];
-                    tmem_ld32(acc + (uint32_t)col0, r);
+                    for (int lh = 0; lh < 2; ++lh) {
+                        const int rb  = quarter * 32 + lh * 16;
+                        const int sA  = rb / CH;
+                        const int ocA = rb % CH + (lane >> 2);
+                        const float bA = __ldg(L.bias + ocA), bB = __ldg(L.bias + ocA + 8);
+                        const uint32_t *tb = tbl_s + (l & 1) * TBL_WORDS + sA * NCOL + colw;
+                        uint32_t r[32];
+                        tmem_ld_16x256b_x8(tmem_base + ((uint32_t)rb << 16) + acc_col + (uint32_t)colw, r);
+                        const uint32_t gbase = smem_base + obuf_off + (uint32_t)((rb % CH) >> 3) * LBO_B + (uint32_t)(mi & 1) * LBO_B;
 #pragma unroll
-                    for (int i4 = 0; i4 < 8; ++i4) {
-                        const uint4 e4 = *reinterpret_cast<const uint4 *>(tb + col0 + 4 * i4);
-                        const uint32_t e[4] = {e4.x, e4.y, e4.z, e4.w};
+                        for (int pr = 0; pr < 4; ++pr) {
+                            uint32_t f[4];
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            float v = lrelu_max(__fadd_rn(__uint_as_float(r[4 * i4 + q]), bias), slope);
-                            if (!interior) {
-                                const int t = tw + mrf::tbl_tau(e[q]);
-                                if (t < 0 || t >= T) v = 0.f;
+                            for (int q = 0; q < 4; ++q) {
+                                const int i0 = 8 * pr + 2 * q;
+                                const float b = (q & 1) ? bB : bA;
+                                f[q] = pack_h2(lrelu_max(__fadd_rn(__uint_as_float(r[i0]), b), slope),
+                                               lrelu_max(__fadd_rn(__uint_as_float(r[i0 + 1]), b), slope));
                             }
-                            if (e[q] & mrf::TBL_VALID) *reinterpret_cast<__half *>(dst + mrf::tbl_byte(e[q])) = __float2half_rn(v);
+                            const uint32_t e = tb[8 * (2 * pr + (mi >> 1)) + r8];
+                            stmatrix_x4_trans(gbase + mrf::tbl_byte(e), f[0], f[1], f[2], f[3]);
+                        }
+                    }
+                } else {
+                    const float bias = __ldg(L.bias + oc);
+                    const uint32_t *tb = tbl_s + (l & 1) * TBL_WORDS + s * NCOL;
+                    uint8_t *dst = smem + obuf_off + toff;
+#pragma unroll 1
+                    for (int b = 0; b < 2; ++b) {
+                        const int col0 = colw + b * 32;
+                        uint32_t r[32];
+                        tmem_ld32(tlane + acc_col + (uint32_t)col0, r);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const uint32_t e = tb[col0 + i];
+                            float v = lrelu_max(__fadd_rn(__uint_as_float(r[i]), bias), slope);
+                            const int t = tw + mrf::tbl_tau(e);
+                            if (t < 0 || t >= T) v = 0.f;
+                            if (e & mrf::TBL_VALID) *reinterpret_cast<__half *>(dst + mrf::tbl_byte(e)) = __float2half_rn(v);
                         }
                     }
                 }
@@ -198,13 +306,14 @@ __global__ void __launch_bounds__(F_THREADS, 1) mrf_fused_kernel(const mrf::Para
                 mbar_arrive(smem_u32(act_ready));
             } else {
                 // final: y (+ running branch sum) (* 1/num_blocks) -> global fp32
+                const float bias = __ldg(L.bias + oc);
                 float *out = p.out + row0 * CH + oc;
                 const float *ain = p.acc_in ? p.acc_in + row0 * CH + oc : nullptr;
 #pragma unroll 1
-                for (int b = 0; b < F_BATCHES; ++b) {
-                    const int col0 = part * F_COLS_PER_WARP + b * 32;
+                for (int b = 0; b < 2; ++b) {
+                    const int col0 = colw + b * 32;
                     uint32_t r[32];
-                    tmem_ld32(acc + (uint32_t)col0, r);
+                    tmem_ld32(tlane + acc_col + (uint32_t)col0, r);
                     float a[32];
                     if (ain) {
 #pragma unroll
@@ -228,10 +337,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) mrf_fused_kernel(const mrf::Para
                 }
             }
         }
-    } else if (warp == F_EPI_WARPS) {
+    } else if (warp == EPI_WARPS) {
         // =================== MMA issuer ===================
         const uint32_t leader = elect_one();
-        const uint32_t idesc  = make_idesc_mn(128, mrf::NCOL);
+        const uint32_t idesc  = make_idesc_mn(128, NCOL);
         int it = 0;
 #pragma unroll 1
         for (int l = 0; l < p.nlayers; ++l) {
@@ -240,7 +349,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) mrf_fused_kernel(const mrf::Para
             const int nj = k + S - 1;
             const uint32_t lbo_a = (uint32_t)mrf::tap_blocks(k, S) * CH * 16u;
             const uint32_t ibuf  = (l & 1) ? buf1 : buf0;
-            const uint32_t dcol  = tmem_base + (L.accumulate ? 256u : 0u);
+            const uint32_t dcol  = tmem_base + (L.accumulate ? (uint32_t)NCOL : 0u);
             mbar_wait(smem_u32(act_ready), (uint32_t)l & 1u, p.err_flag);
             tc_fence_after_sync();
 #pragma unroll 1
@@ -251,13 +360,13 @@ __global__ void __launch_bounds__(F_THREADS, 1) mrf_fused_kernel(const mrf::Para
                 tc_fence_after_sync();
                 if (leader) {
                     const uint32_t a_slot = ring + (uint32_t)slot * slot_bytes;
-                    const uint32_t b_c    = ibuf + (uint32_t)(2 * c) * mrf::LBO_B + (uint32_t)mrf::GUARD * 16u;
+                    const uint32_t b_c    = ibuf + (uint32_t)(2 * c) * LBO_B + (uint32_t)mrf::GUARD * 16u;
 #pragma unroll 1
                     for (int j = 0; j < nj; ++j) {
                         int q, ro;
                         mrf::b_step(k, S, j, q, ro);
                         const uint64_t adesc = make_smem_desc(a_slot + (uint32_t)mrf::a_block(k, S, j) * (CH * 16u), lbo_a, 128u);
-                        const uint64_t bdesc = make_smem_desc(b_c + (uint32_t)q * G::SUB + (uint32_t)(ro * 16), mrf::LBO_B, 128u);
+                        const uint64_t bdesc = make_smem_desc(b_c + (uint32_t)q * G::SUB + (uint32_t)(ro * 16), LBO_B, 128u);
                         umma_f16(dcol, adesc, bdesc, idesc, (L.accumulate || c > 0 || j > 0) ? 1u : 0u);
                     }
                     umma_commit(smem_u32(w_empty + slot));
@@ -289,26 +398,31 @@ __global__ void __launch_bounds__(F_THREADS, 1) mrf_fused_kernel(const mrf::Para
 
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == F_EPI_WARPS) {
+    if (warp == EPI_WARPS) {
         tc_fence_after_sync();
-        tmem_dealloc(tmem_base, 512u);
+        tmem_dealloc(tmem_base, 2u * NCOL);
     }
 }
 
-template <int CH>
-cudaError_t launch_ch(const mrf::Params &p, int total_windows, cudaStream_t st)
+template <int CH, int NCOL>
+cudaError_t launch_cfg(const mrf::Params &p, int total_windows, cudaStream_t st)
 {
-    using G = mrf::Geo<CH>;
+    using C = FCfg<CH, NCOL>;
     uint32_t slot = 0;
-    for (int l = 0; l < p.nlayers; ++l) slot = max(slot, mrf::chunk_bytes(p.L[l].k, G::S, CH));
-    const size_t fixed = F_HEADER + f_tables_bytes<CH>() + 2 * (size_t)G::BUF;
-    const size_t budget = 227 * 1024;
-    int nslots = (int)((budget - fixed) / slot);
-    if (nslots < 1) return cudaErrorInvalidConfiguration;
+    for (int l = 0; l < p.nlayers; ++l) slot = max(slot, mrf::chunk_bytes(p.L[l].k, C::G::S, CH));
+    const size_t fixed = C::OFF_RING;
+    if (fixed + slot > C::SMEM_BUDGET) return cudaErrorInvalidConfiguration;
+    int nslots = (int)((C::SMEM_BUDGET - fixed) / slot);
     if (nslots > F_MAX_SLOTS) nslots = F_MAX_SLOTS;
     const size_t smem = fixed + (size_t)nslots * slot;
-    mrf_fused_kernel<CH><<<total_windows, F_THREADS, smem, st>>>(p, nslots, slot);
+    mrf_fused_kernel<CH, NCOL><<<total_windows, C::THREADS, smem, st>>>(p, nslots, slot);
     return cudaGetLastError();
+}
+
+template <int CH, int NCOL>
+cudaError_t init_cfg()
+{
+    return cudaFuncSetAttribute(mrf_fused_kernel<CH, NCOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FCfg<CH, NCOL>::SMEM_BUDGET);
 }
 
 }  // namespace
@@ -316,19 +430,32 @@ cudaError_t launch_ch(const mrf::Params &p, int total_windows, cudaStream_t st)
 cudaError_t mrf_fused_init()
 {
     cudaError_t e;
-    const int kMax = 227 * 1024;
-    if ((e = cudaFuncSetAttribute(mrf_fused_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(mrf_fused_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(mrf_fused_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax)) != cudaSuccess) return e;
+    if ((e = init_cfg<32, 256>()) != cudaSuccess) return e;
+    if ((e = init_cfg<64, 256>()) != cudaSuccess) return e;
+    if ((e = init_cfg<128, 256>()) != cudaSuccess) return e;
+    if ((e = init_cfg<32, 128>()) != cudaSuccess) return e;
+    if ((e = init_cfg<64, 128>()) != cudaSuccess) return e;
     return cudaSuccess;
+}
+
+bool mrf_fused_supported(int CH, int ncol)
+{
+    return (ncol == 256 && (CH == 32 || CH == 64 || CH == 128)) || (ncol == 128 && (CH == 32 || CH == 64));
 }
 
 cudaError_t mrf_fused_launch(int CH, const mrf::Params &p, int total_windows, cudaStream_t st)
 {
-    switch (CH) {
-        case 32:  return launch_ch<32>(p, total_windows, st);
-        case 64:  return launch_ch<64>(p, total_windows, st);
-        case 128: return launch_ch<128>(p, total_windows, st);
+    if (p.ncol == 256) {
+        switch (CH) {
+            case 32:  return launch_cfg<32, 256>(p, total_windows, st);
+            case 64:  return launch_cfg<64, 256>(p, total_windows, st);
+            case 128: return launch_cfg<128, 256>(p, total_windows, st);
+        }
+    } else if (p.ncol == 128) {
+        switch (CH) {
+            case 32:  return launch_cfg<32, 128>(p, total_windows, st);
+            case 64:  return launch_cfg<64, 128>(p, total_windows, st);
+        }
     }
     return cudaErrorInvalidValue;
 }

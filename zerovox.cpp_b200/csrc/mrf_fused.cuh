@@ -36,21 +36,29 @@
 namespace zvx {
 namespace mrf {
 
-constexpr int NCOL       = 256;   // GEMM N: columns n' per window
-constexpr int GUARD      = 8;     // zero rows before / after the 256 data rows of a sub-buffer
-constexpr int NROWS      = 273;   // rows per (sub-buffer, channel group): 8 + 256 + 8, +1 so that the
-                                  // four 16-byte group segments of one warp store hit distinct banks
+constexpr int GUARD      = 8;     // zero rows before / after the NCOL data rows of a sub-buffer
 constexpr int ROW_BYTES  = 16;    // 8 channels x fp16
-constexpr int LBO_B      = NROWS * ROW_BYTES;      // byte distance between channel groups
 constexpr int MAX_LAYERS = 6;
 constexpr int MAX_K      = 11;
 
-template <int CH>
+// rows per (sub-buffer, channel group): 8 + NCOL + 8, +1 so that the 16-byte group segments of
+// one warp-wide store land in distinct banks
+ZVX_HD constexpr int nrows_of(int ncol) { return ncol + 2 * GUARD + 1; }
+ZVX_HD constexpr int lbo_b_of(int ncol) { return nrows_of(ncol) * ROW_BYTES; }
+// window length in time steps: the largest multiple of S*d for d in {1,3,5} that fits S*NCOL positions
+ZVX_HD constexpr int wp_of(int CH, int ncol) { return ((128 / CH) * ncol / (15 * (128 / CH))) * 15 * (128 / CH); }
+// data row used as a dump for elements whose position lies beyond the window (it is only ever read
+// by outputs that are themselves beyond the window)
+ZVX_HD constexpr int trash_unit(int ncol) { return GUARD + ncol + 4; }
+
+// CH channels, NCOL = GEMM N = columns n' per window (256: one CTA per SM; 128: two CTAs per SM)
+template <int CH, int NCOL>
 struct Geo {
     static constexpr int S       = 128 / CH;                 // output shifts stacked along M
     static constexpr int NPOS    = S * NCOL;                 // positions per window
-    static constexpr int WP      = (NPOS / (15 * S)) * 15 * S;   // window length in time steps:
-                                                                 // multiple of S*d for d in {1,3,5}
+    static constexpr int WP      = wp_of(CH, NCOL);
+    static constexpr int NROWS   = nrows_of(NCOL);
+    static constexpr int LBO_B   = lbo_b_of(NCOL);           // byte distance between channel groups
     static constexpr int GROUPS  = CH / 8;                   // 8-channel groups
     static constexpr int SUB     = GROUPS * LBO_B;           // bytes per polyphase sub-buffer
     static constexpr int BUF     = S * SUB;                  // bytes per activation buffer
@@ -89,19 +97,21 @@ ZVX_HD int tau_to_pos(int tau, int d, int Wp)
 // Scatter-table entry: where the element (shift s, column n') of a layer's output goes in the
 // NEXT layer's input buffer.  unit = 16-byte row index inside the buffer (group 0), tau = its
 // time inside the window.
-// Packed as: bit 31 valid, bits 17-30 tau, bits 0-16 byte offset of the row (unit * 16).
+// Packed as: bit 31 valid, bits 17-30 tau, bits 0-16 byte offset of the row (unit * 16).  Entries
+// of positions beyond the window are not valid and point at the trash row.
 constexpr uint32_t TBL_VALID = 0x80000000u;
 ZVX_HD uint32_t tbl_pack(int unit, int tau) { return TBL_VALID | ((uint32_t)tau << 17) | ((uint32_t)unit * 16u); }
 ZVX_HD int tbl_unit(uint32_t e) { return (int)((e & 0x1FFFFu) >> 4); }
 ZVX_HD uint32_t tbl_byte(uint32_t e) { return e & 0x1FFFFu; }
 ZVX_HD int tbl_tau(uint32_t e) { return (int)((e >> 17) & 0x3FFFu); }
+ZVX_HD uint32_t tbl_trash(int ncol) { return (uint32_t)trash_unit(ncol) * 16u; }
 
 // unit index of time tau in a buffer laid out for dilation d
-ZVX_HD int dest_unit(int tau, int d, int Wp, int S, int groups)
+ZVX_HD int dest_unit(int tau, int d, int Wp, int S, int groups, int ncol)
 {
     const int p = tau_to_pos(tau, d, Wp);
     const int q = p % S, row = p / S;
-    return q * groups * NROWS + GUARD + row;
+    return q * groups * nrows_of(ncol) + GUARD + row;
 }
 
 struct Layer {
@@ -111,7 +121,7 @@ struct Layer {
     float           out_slope;  // leaky-relu slope applied to (acc + bias) before the fp16 store
     const uint16_t *w;          // packed fp16: [K-step][2 groups][tap block][oc][8]
     const float    *bias;       // [CH]: conv1: its bias; conv2: cumulative sum of conv2 biases so far
-    const uint32_t *tbl;        // [S][NCOL] scatter into the next layer's buffer (unused for the last)
+    const uint32_t *tbl;        // [S][ncol] scatter into the next layer's buffer (unused for the last)
 };
 
 struct Params {
@@ -121,12 +131,13 @@ struct Params {
     float           scale;      // out = (acc_in + y) * scale when has_scale
     int             has_scale;
     float           in_slope;   // leaky-relu slope of the first conv input (0.1)
-    const uint32_t *tbl0;       // [S][NCOL] scatter of the block input into layer 0's buffer
+    const uint32_t *tbl0;       // [S][ncol] scatter of the block input into layer 0's buffer
     int             nlayers;
     Layer           L[MAX_LAYERS];
     const int      *seg_start;  // [B+1] utterance prefix in frames
     const int      *win_start;  // [B+1] prefix of windows per utterance
     int             B;
+    int             ncol;       // 128 or 256 (must match the kernel instantiation)
     int             rate;       // rows per frame at this stage
     int             halo;       // sum of pads of all layers
     int             valid;      // output time steps per window = WP - 2 halo

@@ -35,17 +35,17 @@ inline std::vector<uint16_t> pack_weights(const uint16_t *raw, int CH, int k)
 
 // Scatter table from a layer whose output positions are laid out for dilation d_cur into a
 // buffer laid out for dilation d_next: entry [s][n'] for output position p = S n' + s.
-inline std::vector<uint32_t> make_table(int CH, int d_cur, int d_next)
+inline std::vector<uint32_t> make_table(int CH, int ncol, int d_cur, int d_next)
 {
     const int S = 128 / CH, groups = CH / 8;
-    const int Wp = (S * NCOL / (15 * S)) * 15 * S;
-    std::vector<uint32_t> t((size_t)S * NCOL, 0u);
+    const int Wp = wp_of(CH, ncol);
+    std::vector<uint32_t> t((size_t)S * ncol, tbl_trash(ncol));
     for (int s = 0; s < S; ++s)
-        for (int n = 0; n < NCOL; ++n) {
+        for (int n = 0; n < ncol; ++n) {
             const int p = S * n + s;
             if (p >= Wp) continue;
             const int tau = pos_to_tau(p, d_cur, Wp);
-            t[(size_t)s * NCOL + n] = tbl_pack(dest_unit(tau, d_next, Wp, S, groups), tau);
+            t[(size_t)s * ncol + n] = tbl_pack(dest_unit(tau, d_next, Wp, S, groups, ncol), tau);
         }
     return t;
 }
@@ -56,17 +56,17 @@ struct ChainPlan { int p0, p1, halo, valid; };
 // Greedy split of the block's P pairs so that every launch keeps at least `min_eff` of its
 // window as valid output (halo recompute is the price of fusing; a split costs one fp32 round
 // trip of y through HBM).
-inline std::vector<ChainPlan> plan_chains(int CH, int k, const int *dil, int P, double min_eff)
+inline std::vector<ChainPlan> plan_chains(int CH, int ncol, int k, const int *dil, int P, double min_eff)
 {
     const int S = 128 / CH;
-    const int Wp = (S * NCOL / (15 * S)) * 15 * S;
+    const int Wp = wp_of(CH, ncol);
     std::vector<ChainPlan> out;
     int p = 0;
     while (p < P) {
         int halo = 0, q = p;
         while (q < P) {
             const int h = (k - 1) / 2 * dil[q] + (k - 1) / 2;
-            if (q > p && (double)(Wp - 2 * (halo + h)) / (S * NCOL) < min_eff) break;
+            if (q > p && (double)(Wp - 2 * (halo + h)) / (S * ncol) < min_eff) break;
             halo += h;
             ++q;
         }

@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -51,7 +52,7 @@ struct FusedChain {
     const uint32_t *tbl0 = nullptr;
     double flops_per_row = 0.0;
 };
-struct FusedBlock { int CH = 0, k = 0; std::vector<FusedChain> chains; };
+struct FusedBlock { int CH = 0, k = 0, ncol = 256; std::vector<FusedChain> chains; };
 struct WinCfg { int rate_idx, valid; };
 
 struct ResBlkW  { ConvLayer conv1, conv2, conv1x1; bool learned_sc = false; const float *n1w, *n1b, *n2w, *n2b; int cin, cout; };
@@ -354,12 +355,12 @@ int upload_vec(zvx_ctx *ctx, const std::vector<T> &v, const T **out)
     return 0;
 }
 
-int get_table(zvx_ctx *ctx, int CH, int d_cur, int d_next, const uint32_t **out)
+int get_table(zvx_ctx *ctx, int CH, int ncol, int d_cur, int d_next, const uint32_t **out)
 {
-    const std::vector<int> key = {CH, d_cur, d_next};
+    const std::vector<int> key = {CH, ncol, d_cur, d_next};
     auto it = ctx->tbl_cache.find(key);
     if (it != ctx->tbl_cache.end()) { *out = it->second; return 0; }
-    if (upload_vec(ctx, mrf::make_table(CH, d_cur, d_next), out)) return 1;
+    if (upload_vec(ctx, mrf::make_table(CH, ncol, d_cur, d_next), out)) return 1;
     ctx->tbl_cache[key] = *out;
     return 0;
 }
@@ -376,6 +377,15 @@ int build_fused(zvx_ctx *ctx, HostW &hw)
         const int CH = ctx->chans[i + 1];
         if (CH != 32 && CH != 64 && CH != 128) continue;
         if (2 * nd > mrf::MAX_LAYERS) continue;
+        // columns per window: 128 -> two CTAs per SM (one's epilogue overlaps the other's MMAs) at the
+        // price of a larger halo fraction; worth it where the MMA phase per layer is short (CH = 32)
+        int ncol = CH == 32 ? 128 : 256;
+        {
+            char key[32];
+            snprintf(key, sizeof key, "ZVX_NCOL_%d", CH);
+            if (const char *e = getenv(key)) ncol = atoi(e);
+        }
+        if (!mrf_fused_supported(CH, ncol)) return fail(ctx, "fused MRF: unsupported (CH=%d, ncol=%d)", CH, ncol);
         for (int j = 0; j < nb; ++j) {
             const size_t idx0 = ((size_t)i * nb + j) * nd;
             const int k = ctx->mrf1[idx0].K;
@@ -389,8 +399,9 @@ int build_fused(zvx_ctx *ctx, HostW &hw)
             if (!ok) continue;
             FusedBlock &fb = ctx->fused[(size_t)i * nb + j];
             fb.k = k;
+            fb.ncol = ncol;
             std::vector<float> cum(CH, 0.f);
-            for (const mrf::ChainPlan &cp : mrf::plan_chains(CH, k, dil, nd, ctx->fused_min_eff)) {
+            for (const mrf::ChainPlan &cp : mrf::plan_chains(CH, ncol, k, dil, nd, ctx->fused_min_eff)) {
                 if (cp.valid <= 0) return fail(ctx, "fused MRF: window too small for kernel %d", k);
                 FusedChain fc;
                 fc.p0 = cp.p0; fc.p1 = cp.p1; fc.halo = cp.halo; fc.valid = cp.valid;
@@ -399,7 +410,7 @@ int build_fused(zvx_ctx *ctx, HostW &hw)
                 for (size_t w = 0; w < ctx->wincfg.size(); ++w)
                     if (ctx->wincfg[w].rate_idx == i + 1 && ctx->wincfg[w].valid == cp.valid) fc.wincfg = (int)w;
                 if (fc.wincfg < 0) { ctx->wincfg.push_back({i + 1, cp.valid}); fc.wincfg = (int)ctx->wincfg.size() - 1; }
-                if (get_table(ctx, CH, 1, dil[cp.p0], &fc.tbl0)) return 1;
+                if (get_table(ctx, CH, ncol, 1, dil[cp.p0], &fc.tbl0)) return 1;
                 for (int l = 0; l < fc.nlayers; ++l) {
                     const int p = cp.p0 + l / 2;
                     const bool second = l & 1;
@@ -423,7 +434,7 @@ int build_fused(zvx_ctx *ctx, HostW &hw)
                     L.tbl = nullptr;
                     if (l + 1 < fc.nlayers) {
                         const int d_next = (l & 1) ? dil[p + 1] : 1;
-                        if (get_table(ctx, CH, L.d, d_next, &L.tbl)) return 1;
+                        if (get_table(ctx, CH, ncol, L.d, d_next, &L.tbl)) return 1;
                     }
                     fc.flops_per_row += 2.0 * CH * CH * k;
                 }
@@ -805,6 +816,7 @@ int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out)
                     fp.seg_start = ctx->d_seg;
                     fp.win_start = ctx->d_wins + (size_t)fc.wincfg * (ctx->cap_batch + 1);
                     fp.B = ctx->last_B;
+                    fp.ncol = fb.ncol;
                     fp.rate = ctx->rates[i + 1];
                     fp.halo = fc.halo;
                     fp.valid = fc.valid;
@@ -951,6 +963,7 @@ int zvx_create(zvx_ctx **out, const zvx_config *cfg, const zvx_tensor_desc *weig
     zvx_ctx *ctx = new zvx_ctx();
     ctx->cfg = *cfg;
     ctx->device = cfg->device;
+    if (const char *e = getenv("ZVX_FUSED_MIN_EFF")) ctx->fused_min_eff = atof(e);
     auto bail = [&](void) { g_create_error = ctx->err; zvx_destroy(ctx); return 1; };
 #define CKC(call)                                                                              \
     do {                                                                                       \

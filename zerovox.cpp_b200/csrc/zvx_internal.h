@@ -21,6 +21,7 @@ cudaError_t conv_ref_launch(const ConvParams &p, int total_tiles, cudaStream_t s
 
 // mrf_fused.cu (fused MRF residual block, swapped-orientation implicit GEMM) -------------------
 cudaError_t mrf_fused_init();   // once per device: opt in to > 48 KB dynamic smem
+bool        mrf_fused_supported(int CH, int ncol);
 cudaError_t mrf_fused_launch(int CH, const mrf::Params &p, int total_windows, cudaStream_t st);
 
 // aux_kernels.cu ---------------------------------------------------------------------
