@@ -135,11 +135,17 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
     const int tw  = wi * p.valid - p.halo;             // time of window position 0 (may be < 0)
     const bool interior = tw >= 0 && tw + G::WP <= T;
 
-    // ---- one-time setup: zero both activation buffers (guard rows and never-written rows must
-    //      read as finite zeros), barriers, tensor memory ----
+    // ---- one-time setup.  Every data row of a buffer that holds a position inside the window is
+    //      rewritten by each layer before it is read; what must read as finite zeros are the guard
+    //      rows and the data rows of positions beyond the window (never written) ----
     {
-        uint4 *z = reinterpret_cast<uint4 *>(smem + C::OFF_BUF0);
-        for (int i = tid; i < 2 * G::BUF / 16; i += C::THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        constexpr int ROW_LO = G::WP / S;                      // first data row not fully covered by the window
+        constexpr int NZ     = mrf::GUARD + (G::NROWS - mrf::GUARD - ROW_LO);   // rows to clear per (buffer, sub-buffer, group)
+        for (int i = tid; i < 2 * S * G::GROUPS * NZ; i += C::THREADS) {
+            const int sg = i / NZ, z = i % NZ;
+            const int row = z < mrf::GUARD ? z : mrf::GUARD + ROW_LO + (z - mrf::GUARD);
+            *reinterpret_cast<uint4 *>(smem + C::OFF_BUF0 + (size_t)sg * LBO_B + (size_t)row * 16) = make_uint4(0u, 0u, 0u, 0u);
+        }
     }
     if (tid == 0) {
         for (int s = 0; s < nslots; ++s) {
@@ -394,6 +400,30 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
             }
         }
         __syncwarp();
+        // L2 prefetch of the inputs of the window that the next wave of CTAs will process (window
+        // index + number of resident CTAs): the prologue / final phases of a window are exposed HBM
+        // latency, pulling the lines into L2 while this window computes hides the DRAM part of it
+        const int nwin = win + p.prefetch_stride;
+        if (p.prefetch_stride > 0 && nwin < (int)gridDim.x) {
+            const int nu  = find_segment(p.win_start, p.B, nwin);
+            const int nwi = nwin - __ldg(p.win_start + nu);
+            const int nf0 = __ldg(p.seg_start + nu);
+            const int nT  = (__ldg(p.seg_start + nu + 1) - nf0) * p.rate;
+            const size_t nrow0 = (size_t)nf0 * p.rate;
+            const int ntw = nwi * p.valid - p.halo;
+            const int lo = max(ntw, 0), hi = min(ntw + G::WP, nT);
+            constexpr int ROWS_PER_LINE = 128 / (CH * 4) > 0 ? 128 / (CH * 4) : 1;   // CH = 32: one row per 128-B line
+            constexpr int LINES_PER_ROW = CH * 4 / 128 > 0 ? CH * 4 / 128 : 1;
+            const char *ybase = reinterpret_cast<const char *>(p.y_in + (nrow0 + (size_t)lo) * CH);
+            const int nlines = (hi - lo) * LINES_PER_ROW / ROWS_PER_LINE;
+            for (int i = lane; i < nlines; i += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(ybase + (size_t)i * 128));
+            if (p.acc_in) {
+                const int alo = max(ntw + p.halo, 0), ahi = min(ntw + p.halo + p.valid, nT);
+                const char *abase = reinterpret_cast<const char *>(p.acc_in + (nrow0 + (size_t)alo) * CH);
+                const int alines = (ahi - alo) * LINES_PER_ROW / ROWS_PER_LINE;
+                for (int i = lane; i < alines; i += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(abase + (size_t)i * 128));
+            }
+        }
     }
 
     tc_fence_before_sync();

@@ -141,6 +141,7 @@ struct Params {
     int             rate;       // rows per frame at this stage
     int             halo;       // sum of pads of all layers
     int             valid;      // output time steps per window = WP - 2 halo
+    int             prefetch_stride;   // resident CTAs of the launch (L2 prefetch distance), 0: off
     int            *err_flag;
 };
 

@@ -88,6 +88,8 @@ struct zvx_ctx {
     std::vector<WinCfg> wincfg;                   // window tilings used by the fused chains
     std::map<std::vector<int>, const uint32_t *> tbl_cache;
     int use_fused = 1;
+    int fused_prefetch = 1;
+    int num_sms = 148;
     double fused_min_eff = 0.8;
     int *d_wins = nullptr;                        // [nwincfg][B+1] window prefixes
     std::vector<int> total_wins;
@@ -379,7 +381,7 @@ int build_fused(zvx_ctx *ctx, HostW &hw)
         if (2 * nd > mrf::MAX_LAYERS) continue;
         // columns per window: 128 -> two CTAs per SM (one's epilogue overlaps the other's MMAs) at the
         // price of a larger halo fraction; worth it where the MMA phase per layer is short (CH = 32)
-        int ncol = CH == 32 ? 128 : 256;
+        int ncol = 256;   // measured on B200 (profiles/): 256 beats 128 for every CH, also CH = 32
         {
             char key[32];
             snprintf(key, sizeof key, "ZVX_NCOL_%d", CH);
@@ -817,6 +819,7 @@ int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out)
                     fp.win_start = ctx->d_wins + (size_t)fc.wincfg * (ctx->cap_batch + 1);
                     fp.B = ctx->last_B;
                     fp.ncol = fb.ncol;
+                    fp.prefetch_stride = ctx->fused_prefetch ? ctx->num_sms * (fb.ncol == 128 ? 2 : 1) : 0;
                     fp.rate = ctx->rates[i + 1];
                     fp.halo = fc.halo;
                     fp.valid = fc.valid;
@@ -964,6 +967,8 @@ int zvx_create(zvx_ctx **out, const zvx_config *cfg, const zvx_tensor_desc *weig
     ctx->cfg = *cfg;
     ctx->device = cfg->device;
     if (const char *e = getenv("ZVX_FUSED_MIN_EFF")) ctx->fused_min_eff = atof(e);
+    if (const char *e = getenv("ZVX_FUSED_PREFETCH")) ctx->fused_prefetch = atoi(e);
+    ctx->num_sms = prop.multiProcessorCount;
     auto bail = [&](void) { g_create_error = ctx->err; zvx_destroy(ctx); return 1; };
 #define CKC(call)                                                                              \
     do {                                                                                       \
