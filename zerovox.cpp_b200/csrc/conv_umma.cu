@@ -7,7 +7,9 @@
 // and the elementwise op that feeds it (leaky_relu / InstanceNorm-affine / AdaIN /
 // mel normalisation) and follows it (bias, residual add, MRF branch sum, 1/sqrt2, 1/3).
 //
-// One CTA computes a [128 time steps] x [NC output channels] tile:
+// One CTA computes a [128 * MT time steps] x [NC output channels] tile (MT = 1 or 2 M-tiles that
+// share every weight stage: with MT = 2 each weight byte fetched from L2 feeds 2 x 128 rows,
+// halving the L2 -> smem weight traffic that bounds the MT = 1 kernel):
 //     D[t, oc] = sum_taps sum_ic  A[t + off(tap), ic] * W[tap][oc, ic]
 //   * A operand: warps 0-3 read a halo tile (128 + (ntaps-1)*dilation rows) of the
 //     channels-last activation ONCE per 64-channel chunk, apply the fused prologue, round
@@ -33,8 +35,7 @@ namespace zvx {
 
 constexpr int TILE_M      = 128;
 constexpr int KCHUNK      = 64;
-constexpr int N_PRODUCERS = 128;
-constexpr int N_THREADS   = 192;
+constexpr int MAX_MT      = 2;
 constexpr int MAX_A_STAGES = 4;
 constexpr int MAX_B_STAGES = 8;
 constexpr int SMEM_HEADER  = 256;
@@ -42,9 +43,12 @@ constexpr int SMEM_HEADER  = 256;
 __device__ __forceinline__ uint32_t make_idesc(int N) { return make_idesc_mn(TILE_M, N); }
 
 // ------------------------------------------------------------------ the kernel
-template <int MODE>
-__global__ void __launch_bounds__(N_THREADS) conv_umma_kernel(const ConvParams p)
+template <int MODE, int MT>
+__global__ void __launch_bounds__(128 * MT + 64) conv_umma_kernel(const ConvParams p)
 {
+    constexpr int N_PRODUCERS = 128 * MT;
+    constexpr int MMA_WARP    = 4 * MT;
+    constexpr int ROWS_CTA    = TILE_M * MT;
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t *bars       = reinterpret_cast<uint64_t *>(smem);
     uint64_t *a_full     = bars;                                  // [MAX_A_STAGES]
@@ -74,7 +78,7 @@ __global__ void __launch_bounds__(N_THREADS) conv_umma_kernel(const ConvParams p
     // ---- which tile of which utterance ----
     const int tile    = blockIdx.x;
     const int u       = find_segment(p.tile_start, p.B, tile);
-    const int t0      = (tile - __ldg(p.tile_start + u)) * TILE_M;
+    const int t0      = (tile - __ldg(p.tile_start + u)) * ROWS_CTA;
     const int seg_f0  = __ldg(p.seg_start + u);
     const int seg_len = (__ldg(p.seg_start + u + 1) - seg_f0) * p.rate_in;
     const size_t seg_row0 = (size_t)seg_f0 * p.rate_in;
@@ -92,15 +96,16 @@ __global__ void __launch_bounds__(N_THREADS) conv_umma_kernel(const ConvParams p
         mbar_init(smem_u32(acc_full), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
+    if (warp == MMA_WARP) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 4) {
+    const uint32_t acc_stride = (uint32_t)((NC + 31) & ~31);   // tensor-memory columns per M-tile accumulator
+    if (warp < MMA_WARP) {
         // =================== A producers ===================
-        const int need_rows = TILE_M + (ntaps - 1) * p.tap_step;
+        const int need_rows = ROWS_CTA + (ntaps - 1) * p.tap_step;
         for (int c = 0; c < nkc; ++c) {
             const int sa = c % p.a_stages;
             const uint32_t ph = (uint32_t)(c / p.a_stages) & 1u;
@@ -134,19 +139,43 @@ __global__ void __launch_bounds__(N_THREADS) conv_umma_kernel(const ConvParams p
                 }
             }
 
-            const uint32_t dst0 = a_base + sa * a_stage_bytes + (uint32_t)j * lbo_a;
-            for (int rho = r0; rho < need_rows; rho += rstep) {
-                const int t_in = t0 + p.tap_off0 + rho;
-                uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                if (t_in >= 0 && t_in < seg_len) {
-                    const size_t e = (seg_row0 + (size_t)t_in) * (size_t)p.ldx + p.x_ch_off + ch;
+            // Rows of this thread: rho = r0 + i * rstep.  Loads of a batch of UNR rows are issued
+            // before any of them is used (memory-level parallelism: the producer is latency-bound
+            // otherwise), then transformed and stored with plain shared-memory stores.
+            uint8_t *dstp = smem + SMEM_HEADER + (size_t)sa * a_stage_bytes + (size_t)j * lbo_a;
+            constexpr int UNR = 4;
+            for (int rho0 = r0; rho0 < need_rows; rho0 += UNR * rstep) {
+                float4 fa[UNR], fb[UNR];
+                uint4  hv[UNR];
+                bool   ok[UNR];
+#pragma unroll
+                for (int q = 0; q < UNR; ++q) {
+                    const int rho  = rho0 + q * rstep;
+                    const int t_in = t0 + p.tap_off0 + rho;
+                    ok[q] = rho < need_rows && t_in >= 0 && t_in < seg_len;
+                    const size_t e = (seg_row0 + (size_t)(ok[q] ? t_in : 0)) * (size_t)p.ldx + p.x_ch_off + ch;
                     if (MODE == PRO_F16) {
-                        v = *reinterpret_cast<const uint4 *>(reinterpret_cast<const __half *>(p.x) + e);
+                        hv[q] = make_uint4(0u, 0u, 0u, 0u);
+                        if (ok[q]) hv[q] = *reinterpret_cast<const uint4 *>(reinterpret_cast<const __half *>(p.x) + e);
                     } else {
-                        const float4 *src = reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(p.x) + e);
-                        const float4 f0 = src[0];
-                        const float4 f1 = src[1];
-                        float f[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+                        fa[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        fb[q] = fa[q];
+                        if (ok[q]) {
+                            const float4 *src = reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(p.x) + e);
+                            fa[q] = src[0];
+                            fb[q] = src[1];
+                        }
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < UNR; ++q) {
+                    const int rho = rho0 + q * rstep;
+                    if (rho >= need_rows) break;
+                    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                    if (MODE == PRO_F16) {
+                        v = hv[q];
+                    } else if (ok[q]) {
+                        float f[8] = {fa[q].x, fa[q].y, fa[q].z, fa[q].w, fb[q].x, fb[q].y, fb[q].z, fb[q].w};
 #pragma unroll
                         for (int i = 0; i < 8; ++i) f[i] = prologue_apply(MODE, f[i], p.pro_slope, pc[i]);
                         v.x = pack_half2(f[0], f[1]);
@@ -154,10 +183,8 @@ __global__ void __launch_bounds__(N_THREADS) conv_umma_kernel(const ConvParams p
                         v.z = pack_half2(f[4], f[5]);
                         v.w = pack_half2(f[6], f[7]);
                     }
+                    *reinterpret_cast<uint4 *>(dstp + (size_t)rho * 16) = v;
                 }
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst0 + (uint32_t)rho * 16u), "r"(v.x),
-                             "r"(v.y), "r"(v.z), "r"(v.w)
-                             : "memory");
             }
             fence_proxy_async_smem();
             mbar_arrive(smem_u32(a_full + sa));
@@ -166,10 +193,11 @@ __global__ void __launch_bounds__(N_THREADS) conv_umma_kernel(const ConvParams p
         // =================== epilogue ===================
         mbar_wait(smem_u32(acc_full), 0u, p.err_flag);
         tc_fence_after_sync();
-        const int  t     = t0 + tid;
+        const int  mt    = warp >> 2;                       // M-tile this warp drains
+        const int  t     = t0 + mt * TILE_M + (warp & 3) * 32 + lane;
         const bool valid = t < seg_len;
         const size_t orow = (seg_row0 + (size_t)t) * (size_t)p.out_mul + p.out_add;
-        const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)mt * acc_stride;
         for (int col = 0; col < NC; col += 16) {
             uint32_t r[16];
             tmem_ld16(trow + (uint32_t)col, r);
@@ -231,38 +259,42 @@ __global__ void __launch_bounds__(N_THREADS) conv_umma_kernel(const ConvParams p
                 o4[1] = make_uint4(h[4], h[5], h[6], h[7]);
             }
         }
-    } else if (warp == 4) {
-        // =================== MMA issuer (one thread) ===================
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc(NC);
-            int it = 0;
-            uint32_t first = 1;
-            for (int c = 0; c < nkc; ++c) {
-                const int sa = c % p.a_stages;
-                const uint32_t pha = (uint32_t)(c / p.a_stages) & 1u;
-                const int kc = min(KCHUNK, Cin - c * KCHUNK);
-                mbar_wait(smem_u32(a_full + sa), pha, p.err_flag);
+    } else if (warp == MMA_WARP) {
+        // =================== MMA issuer (one elected lane of a converged warp) ===================
+        const uint32_t leader = elect_one();
+        const uint32_t idesc = make_idesc(NC);
+        int it = 0;
+        for (int c = 0; c < nkc; ++c) {
+            const int sa = c % p.a_stages;
+            const uint32_t pha = (uint32_t)(c / p.a_stages) & 1u;
+            const int kc = min(KCHUNK, Cin - c * KCHUNK);
+            mbar_wait(smem_u32(a_full + sa), pha, p.err_flag);
+            tc_fence_after_sync();
+            const uint32_t a_stage = a_base + sa * a_stage_bytes;
+            for (int a = 0; a < ntaps; ++a, ++it) {
+                const int sb = it % p.b_stages;
+                const uint32_t phb = (uint32_t)(it / p.b_stages) & 1u;
+                mbar_wait(smem_u32(b_full + sb), phb, p.err_flag);
                 tc_fence_after_sync();
-                const uint32_t a_stage = a_base + sa * a_stage_bytes;
-                for (int a = 0; a < ntaps; ++a, ++it) {
-                    const int sb = it % p.b_stages;
-                    const uint32_t phb = (uint32_t)(it / p.b_stages) & 1u;
-                    mbar_wait(smem_u32(b_full + sb), phb, p.err_flag);
-                    tc_fence_after_sync();
+                if (leader) {
                     const uint32_t b_stage = b_base + sb * b_stage_bytes;
                     const uint32_t a_tap   = a_stage + (uint32_t)(a * p.tap_step) * 16u;
-                    for (int kk = 0; kk < (kc >> 4); ++kk) {
-                        const uint64_t adesc = make_smem_desc(a_tap + (uint32_t)kk * 2u * lbo_a, lbo_a, 128u);
-                        const uint64_t bdesc = make_smem_desc(b_stage + (uint32_t)kk * 2u * lbo_b, lbo_b, 128u);
-                        umma_f16(tmem_base, adesc, bdesc, idesc, first ? 0u : 1u);
-                        first = 0;
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+                        for (int kk = 0; kk < (kc >> 4); ++kk) {
+                            const uint64_t adesc = make_smem_desc(a_tap + (uint32_t)mt * (TILE_M * 16u) + (uint32_t)kk * 2u * lbo_a, lbo_a, 128u);
+                            const uint64_t bdesc = make_smem_desc(b_stage + (uint32_t)kk * 2u * lbo_b, lbo_b, 128u);
+                            umma_f16(tmem_base + (uint32_t)mt * acc_stride, adesc, bdesc, idesc, (it | kk) ? 1u : 0u);
+                        }
                     }
                     umma_commit(smem_u32(b_empty + sb));
                 }
-                umma_commit(smem_u32(a_empty + sa));
+                __syncwarp();
             }
-            umma_commit(smem_u32(acc_full));
+            if (leader) umma_commit(smem_u32(a_empty + sa));
+            __syncwarp();
         }
+        if (leader) umma_commit(smem_u32(acc_full));
         __syncwarp();
     } else {
         // =================== weight (B operand) loader ===================
@@ -287,7 +319,7 @@ __global__ void __launch_bounds__(N_THREADS) conv_umma_kernel(const ConvParams p
 
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == MMA_WARP) {
         tc_fence_after_sync();
         tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
     }
@@ -308,7 +340,7 @@ static int round_a_rows(int need_rows, int kc_max)
 size_t conv_umma_plan(ConvParams &p, size_t smem_budget)
 {
     const int kc_max    = p.Cin < KCHUNK ? p.Cin : KCHUNK;
-    const int need_rows = TILE_M + (p.ntaps - 1) * p.tap_step;
+    const int need_rows = TILE_M * p.mt + (p.ntaps - 1) * p.tap_step;
     p.a_rows            = round_a_rows(need_rows, kc_max);
     const size_t a_stage = (size_t)(kc_max >> 3) * p.a_rows * 16;
     const size_t b_stage = (size_t)kc_max * p.NC * 2;
@@ -332,39 +364,55 @@ size_t conv_umma_plan(ConvParams &p, size_t smem_budget)
     p.a_stages = as;
     p.b_stages = bs;
     int cols = 32;
-    while (cols < p.NC) cols <<= 1;
+    while (cols < p.mt * ((p.NC + 31) & ~31)) cols <<= 1;
     p.tmem_cols = cols;
     return SMEM_HEADER + as * a_stage + bs * b_stage;
 }
 
-template <int MODE>
+template <int MODE, int MT>
 static cudaError_t launch_mode(const ConvParams &p, int total_tiles, size_t smem, cudaStream_t st)
 {
     dim3 grid(total_tiles, p.Cout / p.NC, 1);
-    conv_umma_kernel<MODE><<<grid, N_THREADS, smem, st>>>(p);
+    conv_umma_kernel<MODE, MT><<<grid, 128 * MT + 64, smem, st>>>(p);
     return cudaGetLastError();
+}
+
+template <int MODE>
+static cudaError_t init_mode()
+{
+    cudaError_t e;
+    const int kMax = 227 * 1024;
+    if ((e = cudaFuncSetAttribute(conv_umma_kernel<MODE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax)) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(conv_umma_kernel<MODE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
 }
 
 cudaError_t conv_umma_init()
 {
     cudaError_t e;
-    const int kMax = 227 * 1024;
-    if ((e = cudaFuncSetAttribute(conv_umma_kernel<PRO_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(conv_umma_kernel<PRO_CVT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(conv_umma_kernel<PRO_LRELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(conv_umma_kernel<PRO_NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(conv_umma_kernel<PRO_MEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax)) != cudaSuccess) return e;
+    if ((e = init_mode<PRO_F16>()) != cudaSuccess) return e;
+    if ((e = init_mode<PRO_CVT>()) != cudaSuccess) return e;
+    if ((e = init_mode<PRO_LRELU>()) != cudaSuccess) return e;
+    if ((e = init_mode<PRO_NORM>()) != cudaSuccess) return e;
+    if ((e = init_mode<PRO_MEL>()) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
+template <int MODE>
+static cudaError_t launch_mt(const ConvParams &p, int total_tiles, size_t smem, cudaStream_t st)
+{
+    return p.mt == 2 ? launch_mode<MODE, 2>(p, total_tiles, smem, st) : launch_mode<MODE, 1>(p, total_tiles, smem, st);
+}
+
+// total_tiles counts tiles of 128 * p.mt rows (p.tile_start must be the matching prefix table)
 cudaError_t conv_umma_launch(const ConvParams &p, int total_tiles, size_t smem, cudaStream_t st)
 {
+    if (p.mt != 1 && p.mt != 2) return cudaErrorInvalidValue;
     switch (p.pro_mode) {
-        case PRO_F16:   return launch_mode<PRO_F16>(p, total_tiles, smem, st);
-        case PRO_CVT:   return launch_mode<PRO_CVT>(p, total_tiles, smem, st);
-        case PRO_LRELU: return launch_mode<PRO_LRELU>(p, total_tiles, smem, st);
-        case PRO_NORM:  return launch_mode<PRO_NORM>(p, total_tiles, smem, st);
-        case PRO_MEL:   return launch_mode<PRO_MEL>(p, total_tiles, smem, st);
+        case PRO_F16:   return launch_mt<PRO_F16>(p, total_tiles, smem, st);
+        case PRO_CVT:   return launch_mt<PRO_CVT>(p, total_tiles, smem, st);
+        case PRO_LRELU: return launch_mt<PRO_LRELU>(p, total_tiles, smem, st);
+        case PRO_NORM:  return launch_mt<PRO_NORM>(p, total_tiles, smem, st);
+        case PRO_MEL:   return launch_mt<PRO_MEL>(p, total_tiles, smem, st);
     }
     return cudaErrorInvalidValue;
 }

@@ -89,6 +89,8 @@ struct zvx_ctx {
     std::map<std::vector<int>, const uint32_t *> tbl_cache;
     int use_fused = 1;
     int fused_prefetch = 1;
+    int conv_mt2 = 0;   // two M-tiles per CTA: measured slower on B200 while the A producer is the limit (profiles/)
+    std::vector<int> tile256_cfg;                 // per rate index: wincfg entry of the 256-row tiling
     int num_sms = 148;
     double fused_min_eff = 0.8;
     int *d_wins = nullptr;                        // [nwincfg][B+1] window prefixes
@@ -663,14 +665,23 @@ int run_conv(zvx_ctx *ctx, const ConvCall &cc)
     p.out16 = cc.out16; p.ldo16 = cc.ldo16; p.o16_ch_off = cc.o16_ch_off; p.out16_slope = cc.out16_slope;
     p.out_mul = cc.out_mul; p.out_add = v.out_add;
     p.err_flag = ctx->d_err;
-    const int tiles = ctx->total_tiles[cc.rate_idx];
+    int tiles = ctx->total_tiles[cc.rate_idx];
+    // two M-tiles per CTA (each weight stage feeds 256 rows) whenever that still fills the GPU
+    p.mt = 1;
+    if (!ctx->use_ref_kernels && ctx->conv_mt2 && cc.rate_idx < (int)ctx->tile256_cfg.size() &&
+        (int64_t)tiles * (L.OC / L.NC) >= (int64_t)3 * ctx->num_sms) {
+        const int w = ctx->tile256_cfg[cc.rate_idx];
+        p.mt = 2;
+        p.tile_start = ctx->d_wins + (size_t)w * (ctx->cap_batch + 1);
+        tiles = ctx->total_wins[w];
+    }
     ctx->launches++;
     const double rows = (double)ctx->last_frames * p.rate_in;
     if (prof_begin(ctx, cc.kind, cc.stage, 2.0 * rows * L.OC * L.IC * v.ntaps, 0.0)) return 1;
     if (ctx->use_ref_kernels) {
         CK(ctx, conv_ref_launch(p, tiles, ctx->stream));
     } else {
-        const size_t smem = conv_umma_plan(p, 100 * 1024);
+        const size_t smem = conv_umma_plan(p, p.mt == 2 ? 226 * 1024 : 100 * 1024);
         if (smem > 227 * 1024) return fail(ctx, "conv needs %zu bytes of shared memory", smem);
         CK(ctx, conv_umma_launch(p, tiles, smem, ctx->stream));
     }
@@ -968,6 +979,7 @@ int zvx_create(zvx_ctx **out, const zvx_config *cfg, const zvx_tensor_desc *weig
     ctx->device = cfg->device;
     if (const char *e = getenv("ZVX_FUSED_MIN_EFF")) ctx->fused_min_eff = atof(e);
     if (const char *e = getenv("ZVX_FUSED_PREFETCH")) ctx->fused_prefetch = atoi(e);
+    if (const char *e = getenv("ZVX_CONV_MT2")) ctx->conv_mt2 = atoi(e);
     ctx->num_sms = prop.multiProcessorCount;
     auto bail = [&](void) { g_create_error = ctx->err; zvx_destroy(ctx); return 1; };
 #define CKC(call)                                                                              \
@@ -1014,6 +1026,14 @@ int zvx_create(zvx_ctx **out, const zvx_config *cfg, const zvx_tensor_desc *weig
     if (cfg->with_decoder && build_decoder(ctx, hw)) return bail();
     if (cfg->with_vocoder && build_vocoder(ctx, hw)) return bail();
     if (!cfg->with_vocoder) { ctx->rates.assign(1, 1); ctx->chans.assign(1, 0); }
+    // 256-row tilings (conv_umma with two M-tiles per CTA) for every rate
+    for (int r = 0; r < (int)ctx->rates.size(); ++r) {
+        int w = -1;
+        for (size_t q = 0; q < ctx->wincfg.size(); ++q)
+            if (ctx->wincfg[q].rate_idx == r && ctx->wincfg[q].valid == 256) w = (int)q;
+        if (w < 0) { ctx->wincfg.push_back({r, 256}); w = (int)ctx->wincfg.size() - 1; }
+        ctx->tile256_cfg.push_back(w);
+    }
     if (reserve(ctx, 512, 8)) return bail();
     CKC(cudaStreamSynchronize(ctx->stream));
 #undef CKC

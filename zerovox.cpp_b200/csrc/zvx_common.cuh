@@ -79,7 +79,8 @@ struct ConvParams {
     int          out_mul;     // output row = seg_out_start + t*out_mul + out_add (polyphase up-conv)
     int          out_add;
     // ---- smem geometry (host computed) ----
-    int          a_rows;      // rows per A stage (>= 128 + (ntaps-1)*tap_step)
+    int          mt;          // M-tiles (128 rows each) per CTA: 1 or 2
+    int          a_rows;      // rows per A stage (>= 128*mt + (ntaps-1)*tap_step)
     int          a_stages;
     int          b_stages;
     int          tmem_cols;   // power of two >= max(32, NC)
