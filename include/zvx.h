@@ -88,6 +88,13 @@ int zvx_synth_batch(zvx_ctx *ctx, int32_t B, const float *const *enc_seq, const 
 /* Batched HiFiGAN::eval (hifigan.cpp:358-377) for B independent mels; HOST pointers. */
 int zvx_vocode_batch(zvx_ctx *ctx, int32_t B, const float *const *mel, const int32_t *L, float *const *wav);
 
+/* Long-form synthesis (BASELINE.json configs[2]: 60 s utterances streamed in overlapping mel
+ * chunks): HiFiGAN::eval on a long mel, computed chunk by chunk with `halo_frames` (>= 20: the
+ * vocoder's receptive field is +-19.5 frames) real neighbouring frames on each side; on_chunk
+ * (may be NULL) is called as soon as a chunk's samples are in `wav`.  Same result as zvx_vocode. */
+int zvx_vocode_chunked(zvx_ctx *ctx, const float *mel, int32_t L, int32_t chunk_frames, int32_t halo_frames, float *wav,
+                       void (*on_chunk)(void *user, int64_t first_sample, int64_t n_samples), void *user);
+
 /* Same computation with inputs/outputs already resident in device memory, packed back to
  * back: d_enc [sum L][dim_in], d_style [B][style_dim], d_mel [sum L][num_mels] (may be
  * NULL), d_wav [sum L * hop].  L is a HOST array.  Asynchronous on the ctx stream unless

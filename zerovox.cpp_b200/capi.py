@@ -53,7 +53,7 @@ EXPORTS = [
     "zvx_default_config", "zvx_create", "zvx_destroy", "zvx_last_error", "zvx_decode", "zvx_vocode",
     "zvx_synth_batch", "zvx_synth_batch_device", "zvx_vocode_batch_device", "zvx_stream", "zvx_synchronize",
     "zvx_kernel_launches", "zvx_reserve", "zvx_set_debug_kernels", "zvx_test_conv", "zvx_debug_fetch",
-    "zvx_set_debug_stop", "zvx_profile_begin", "zvx_profile_end", "zvx_set_fused_mrf", "zvx_vocode_batch",
+    "zvx_set_debug_stop", "zvx_profile_begin", "zvx_profile_end", "zvx_set_fused_mrf", "zvx_vocode_batch", "zvx_vocode_chunked",
 ]
 
 _lib = None
@@ -85,6 +85,8 @@ def load_library() -> C.CDLL:
     lib.zvx_synth_batch.restype = i32
     lib.zvx_vocode_batch.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(i32), C.POINTER(vp)]
     lib.zvx_vocode_batch.restype = i32
+    lib.zvx_vocode_chunked.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp]
+    lib.zvx_vocode_chunked.restype = i32
     lib.zvx_synth_batch_device.argtypes = [vp, i32, vp, vp, C.POINTER(i32), vp, vp, i32]
     lib.zvx_synth_batch_device.restype = i32
     lib.zvx_vocode_batch_device.argtypes = [vp, i32, vp, C.POINTER(i32), vp, i32]
@@ -197,6 +199,14 @@ class Context:
         L = mel.shape[0]
         wav = np.empty(L * self.hop, np.float32)
         self._check(self.lib.zvx_vocode(self.h, _ptr(mel), L, _ptr(wav)))
+        return wav
+
+    def vocode_chunked(self, mel: np.ndarray, chunk_frames: int = 256, halo_frames: int = 20) -> np.ndarray:
+        """Long-form vocoding in overlapping mel chunks (configs[2]); equals vocode(mel)."""
+        mel = np.ascontiguousarray(mel, np.float32)
+        L = mel.shape[0]
+        wav = np.empty(L * self.hop, np.float32)
+        self._check(self.lib.zvx_vocode_chunked(self.h, _ptr(mel), L, chunk_frames, halo_frames, _ptr(wav), None, None))
         return wav
 
     def vocode_batch(self, mel_list: Sequence[np.ndarray]):

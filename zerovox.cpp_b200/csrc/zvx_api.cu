@@ -1203,6 +1203,36 @@ int zvx_vocode_batch(zvx_ctx *ctx, int32_t B, const float *const *mel, const int
     return check_device_error(ctx);
 }
 
+// Long-form synthesis (BASELINE.json configs[2]): the vocoder's receptive field is +-19.5 mel
+// frames, so a long mel can be vocoded in chunks of `chunk_frames` frames, each
+// extended by `halo_frames` >= 20 real neighbouring frames on both sides; the halo part of every
+// chunk's output is discarded.  True sequence ends keep the reference's per-layer zero padding.
+// The result equals zvx_vocode on the whole mel; device memory is bounded by the chunk size and
+// the caller receives the waveform chunk by chunk (on_chunk, may be NULL).
+int zvx_vocode_chunked(zvx_ctx *ctx, const float *mel, int32_t L, int32_t chunk_frames, int32_t halo_frames, float *wav,
+                       void (*on_chunk)(void *user, int64_t first_sample, int64_t n_samples), void *user)
+{
+    if (!ctx) return 1;
+    if (!ctx->cfg.with_vocoder) return fail(ctx, "context was built without vocoder");
+    if (!mel || !wav || L <= 0) return fail(ctx, "zvx_vocode_chunked: bad argument");
+    if (chunk_frames <= 0 || halo_frames < 20) return fail(ctx, "zvx_vocode_chunked: chunk_frames must be > 0 and halo_frames >= 20 (receptive field 19.5 frames)");
+    CK(ctx, cudaSetDevice(ctx->device));
+    const zvx_config &c = ctx->cfg;
+    for (int32_t a = 0; a < L; a += chunk_frames) {
+        const int32_t b = std::min(L, a + chunk_frames);
+        const int32_t lo = std::max(0, a - halo_frames), hi = std::min(L, b + halo_frames);
+        const int32_t n = hi - lo;
+        if (set_batch(ctx, 1, &n)) return 1;
+        CK(ctx, cudaMemcpyAsync(ctx->mel, mel + (size_t)lo * c.num_mels, sizeof(float) * (size_t)n * c.num_mels, cudaMemcpyHostToDevice, ctx->stream));
+        if (run_vocoder(ctx, ctx->mel, ctx->wav)) return 1;
+        CK(ctx, cudaMemcpyAsync(wav + (size_t)a * c.hop_size, ctx->wav + (size_t)(a - lo) * c.hop_size, sizeof(float) * (size_t)(b - a) * c.hop_size,
+                                cudaMemcpyDeviceToHost, ctx->stream));
+        if (check_device_error(ctx)) return 1;
+        if (on_chunk) on_chunk(user, (int64_t)a * c.hop_size, (int64_t)(b - a) * c.hop_size);
+    }
+    return 0;
+}
+
 int zvx_debug_fetch(zvx_ctx *ctx, const char *what, float *dst, int64_t n)
 {
     if (!ctx || !what || !dst) return 1;
