@@ -18,8 +18,10 @@ __global__ void __launch_bounds__(256) stats_kernel(const float *__restrict__ x,
                                                     const int *__restrict__ seg_start, int rate,
                                                     float *__restrict__ mu, float *__restrict__ rstd)
 {
-    __shared__ double red[8][33];
-    __shared__ float mean_s[32];
+    // One pass: sum and sum of squares in double.  The reference makes two passes (mean first,
+    // then sum((float)(x - mean)^2) in double); the two variances differ by O(1e-7) relative
+    // (the fp32 rounding of x - mean), far below the fp16 operand rounding that follows.
+    __shared__ double red[2][8][33];
     const int u  = blockIdx.y;
     const int c  = blockIdx.x * 32 + threadIdx.x;
     const int ty = threadIdx.y;
@@ -28,34 +30,33 @@ __global__ void __launch_bounds__(256) stats_kernel(const float *__restrict__ x,
     const double n = (double)(r1 - r0);
     const bool ok = c < C;
 
-    double s = 0.0;
-    if (ok)
-        for (size_t r = r0 + ty; r < r1; r += 8) s += (double)x[r * ld + ch_off + c];
-    red[ty][threadIdx.x] = s;
-    __syncthreads();
-    if (ty == 0) {
-        double t = 0.0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
-        mean_s[threadIdx.x] = (float)(t / n);
-    }
-    __syncthreads();
-    const float mean = mean_s[threadIdx.x];
-    double s2 = 0.0;
-    if (ok)
-        for (size_t r = r0 + ty; r < r1; r += 8) {
-            const float v = __fsub_rn(x[r * ld + ch_off + c], mean);
-            s2 += (double)__fmul_rn(v, v);
+    double s = 0.0, s2 = 0.0;
+    if (ok) {
+        const float *px = x + ch_off + c;
+        size_t r = r0 + ty;
+        for (; r + 24 < r1; r += 32) {             // 4 independent loads in flight per thread
+            const float a0 = px[r * ld], a1 = px[(r + 8) * ld], a2 = px[(r + 16) * ld], a3 = px[(r + 24) * ld];
+            s += (double)a0 + (double)a1 + (double)a2 + (double)a3;
+            s2 += (double)a0 * a0 + (double)a1 * a1 + (double)a2 * a2 + (double)a3 * a3;
         }
-    __syncthreads();
-    red[ty][threadIdx.x] = s2;
+        for (; r < r1; r += 8) {
+            const float a0 = px[r * ld];
+            s += (double)a0;
+            s2 += (double)a0 * a0;
+        }
+    }
+    red[0][ty][threadIdx.x] = s;
+    red[1][ty][threadIdx.x] = s2;
     __syncthreads();
     if (ty == 0 && ok) {
-        double t = 0.0;
+        double t = 0.0, t2 = 0.0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
-        const float variance = (float)(t / n);
-        mu[(size_t)u * C + c]   = mean;
+        for (int i = 0; i < 8; ++i) { t += red[0][i][threadIdx.x]; t2 += red[1][i][threadIdx.x]; }
+        const double mean_d = t / n;
+        double var_d = t2 / n - mean_d * mean_d;
+        if (var_d < 0.0) var_d = 0.0;
+        const float variance = (float)var_d;
+        mu[(size_t)u * C + c]   = (float)mean_d;
         rstd[(size_t)u * C + c] = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(variance, 1e-5f)));
     }
 }
@@ -171,6 +172,7 @@ cudaError_t norm_affine_launch(const float *x, int ldx, int C, const int *seg_st
 constexpr int OC_MAX_C = 64;
 constexpr int OC_MAX_K = 16;
 
+// Generic shape: weights staged in shared memory.
 __global__ void __launch_bounds__(128) out_conv_kernel(const float *__restrict__ x, int C, int K,
                                                        const __half *__restrict__ w_raw, const float *__restrict__ bias,
                                                        float slope, const int *__restrict__ seg_start,
@@ -211,10 +213,62 @@ __global__ void __launch_bounds__(128) out_conv_kernel(const float *__restrict__
     wav[row0 + t] = tanhf(__fadd_rn(acc, __ldg(bias)));
 }
 
-cudaError_t out_conv_launch(const float *x, int C, int K, const __half *w_raw, const float *bias, float slope,
-                            const int *seg_start, const int *tile_start, int B, int rate, int total_tiles, float *wav,
-                            cudaStream_t st)
+// The shipped shape (32 channels, 7 taps): the 224 weights travel as a kernel parameter, i.e. in the
+// constant bank, so every FFMA takes its weight as an immediate constant operand and the inner loop
+// is one conflict-free LDS + one FFMA per MAC; the input tile is staged with float4 loads.
+struct OutConvW { float w[7 * 32]; float bias; };      // [k][c]
+
+__global__ void __launch_bounds__(128) out_conv_32x7_kernel(const float *__restrict__ x, const OutConvW W, float slope,
+                                                            const int *__restrict__ seg_start,
+                                                            const int *__restrict__ tile_start, int B, int rate,
+                                                            float *__restrict__ wav)
 {
+    constexpr int C = 32, K = 7, ROWS = 128 + K - 1, LD = C + 1;
+    __shared__ float tile[ROWS * LD];
+    const int tile_id = blockIdx.x;
+    const int u       = find_segment(tile_start, B, tile_id);
+    const int t0      = (tile_id - __ldg(tile_start + u)) * 128;
+    const size_t row0 = (size_t)__ldg(seg_start + u) * rate;
+    const int seg_len = (__ldg(seg_start + u + 1) - __ldg(seg_start + u)) * rate;
+
+    for (int i = threadIdx.x; i < ROWS * (C / 4); i += 128) {
+        const int r = i >> 3, c4 = (i & 7) * 4;
+        const int t = t0 - (K - 1) / 2 + r;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t >= 0 && t < seg_len) v = *reinterpret_cast<const float4 *>(x + (row0 + t) * C + c4);
+        float *d = tile + r * LD + c4;
+        d[0] = __half2float(__float2half_rn(lrelu_f(v.x, slope)));
+        d[1] = __half2float(__float2half_rn(lrelu_f(v.y, slope)));
+        d[2] = __half2float(__float2half_rn(lrelu_f(v.z, slope)));
+        d[3] = __half2float(__float2half_rn(lrelu_f(v.w, slope)));
+    }
+    __syncthreads();
+    const int t = t0 + threadIdx.x;
+    if (t >= seg_len) return;
+    float acc0 = 0.f, acc1 = 0.f;
+    const float *row = tile + threadIdx.x * LD;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+#pragma unroll
+        for (int c = 0; c < C; c += 2) {
+            acc0 = fmaf(row[k * LD + c], W.w[k * C + c], acc0);
+            acc1 = fmaf(row[k * LD + c + 1], W.w[k * C + c + 1], acc1);
+        }
+    }
+    wav[row0 + t] = tanhf(__fadd_rn(__fadd_rn(acc0, acc1), W.bias));
+}
+
+cudaError_t out_conv_launch(const float *x, int C, int K, const __half *w_raw, const float *bias, const float *w_host_kc,
+                            float bias_host, float slope, const int *seg_start, const int *tile_start, int B, int rate,
+                            int total_tiles, float *wav, cudaStream_t st)
+{
+    if (C == 32 && K == 7 && w_host_kc) {
+        OutConvW W;
+        for (int i = 0; i < 7 * 32; ++i) W.w[i] = w_host_kc[i];
+        W.bias = bias_host;
+        out_conv_32x7_kernel<<<total_tiles, 128, 0, st>>>(x, W, slope, seg_start, tile_start, B, rate, wav);
+        return cudaGetLastError();
+    }
     if (C > OC_MAX_C || K > OC_MAX_K) return cudaErrorInvalidValue;
     const size_t smem = (OC_MAX_K * OC_MAX_C + (128 + OC_MAX_K) * (OC_MAX_C + 1)) * sizeof(float);
     out_conv_kernel<<<total_tiles, 128, smem, st>>>(x, C, K, w_raw, bias, slope, seg_start, tile_start, B, rate, wav);

@@ -82,8 +82,12 @@ struct zvx_ctx {
     const float *mel_mean = nullptr, *mel_scale = nullptr;
     ConvLayer input_conv;
     std::vector<ConvLayer> up;                    // per stage, var = phases
+    std::vector<ConvLayer> upf;                   // per stage: all phases fused into one conv (OC == 0: not used)
+    int use_fused_upconv = 1;
     std::vector<ConvLayer> mrf1, mrf2;            // [stage*nb*nd + j*nd + d]
     ConvLayer output_conv;
+    std::vector<float> out_w_kc;                  // host fp32 copy [K][C] of the output conv (constant-bank path)
+    float out_b_host = 0.f;
     std::vector<FusedBlock> fused;                // [stage*nb + j]; CH == 0: not fused
     std::vector<WinCfg> wincfg;                   // window tilings used by the fused chains
     std::map<std::vector<int>, const uint32_t *> tbl_cache;
@@ -279,6 +283,54 @@ int make_upconv(zvx_ctx *ctx, HostW &hw, const std::string &prefix, int s, ConvL
     return 0;
 }
 
+template <typename T>
+int upload_vec(zvx_ctx *ctx, const std::vector<T> &v, const T **out)
+{
+    T *d = nullptr;
+    if (dev_alloc(ctx, &d, v.size())) return 1;
+    CK(ctx, cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = d;
+    return 0;
+}
+
+// All s output phases of a ConvTranspose1d in ONE implicit GEMM: "output channel" (phi, oc), taps =
+// the union of the phases' input offsets (3 for K = 2s), zero weights where a phase does not use an
+// offset.  Row t of the fused output [rows_in][s*OC] is exactly rows t*s .. t*s+s-1 of the true
+// output [rows_in*s][OC], so no scatter is needed.  Used where s*OC <= 256 (one N-chunk): there
+// the per-phase launches are dominated by per-CTA overhead and re-read the input s times.
+int make_upconv_fused(zvx_ctx *ctx, HostW &hw, const std::string &prefix, int s, const ConvLayer &L, ConvLayer &F)
+{
+    if (s * L.OC > 256) return 0;
+    int dmin = 1 << 30, dmax = -(1 << 30);
+    for (const ConvVariant &v : L.var) { dmin = std::min(dmin, v.tap_off0); dmax = std::max(dmax, v.tap_off0 + v.ntaps - 1); }
+    const int KF = dmax - dmin + 1, OCF = s * L.OC;
+    const std::vector<__half> &raw = hw.h[prefix + ".w"];
+    const std::vector<float> &bias = hw.f[prefix + ".b"];
+    if ((int)bias.size() != L.OC) return fail(ctx, "%s: bias not available for the fused up-conv", prefix.c_str());
+    std::vector<__half> rf((size_t)OCF * L.IC * KF, __float2half(0.f));
+    std::vector<float> bf(OCF);
+    for (int phi = 0; phi < s; ++phi) {
+        const ConvVariant &v = L.var[phi];
+        for (int oc = 0; oc < L.OC; ++oc) {
+            bf[phi * L.OC + oc] = bias[oc];
+            for (int ic = 0; ic < L.IC; ++ic)
+                for (int t = 0; t < v.ntaps; ++t)
+                    rf[((size_t)(phi * L.OC + oc) * L.IC + ic) * KF + (v.tap_off0 - dmin + t)] =
+                        raw[((size_t)oc * L.IC + ic) * L.K + v.w_tap0 + t * v.w_tap_stride];
+        }
+    }
+    F.OC = OCF; F.IC = L.IC; F.K = KF; F.NC = pick_nc(OCF);
+    if (F.NC == 0) return 0;
+    const __half *d_raw; const float *d_bias;
+    if (upload_vec(ctx, rf, &d_raw) || upload_vec(ctx, bf, &d_bias)) return 1;
+    F.raw = d_raw; F.bias = d_bias;
+    ConvVariant fv;
+    fv.ntaps = KF; fv.w_tap0 = 0; fv.w_tap_stride = 1; fv.tap_off0 = dmin; fv.tap_step = 1; fv.out_add = 0;
+    if (pack_variant(ctx, rf, OCF, L.IC, KF, F.NC, fv)) return 1;
+    F.var.push_back(fv);
+    return 0;
+}
+
 int f32_ptr(zvx_ctx *ctx, const std::string &name, int64_t n, const float **out)
 {
     const DevTensor *t;
@@ -346,16 +398,6 @@ int build_decoder(zvx_ctx *ctx, HostW &hw)
     }
     if (make_conv(ctx, hw, "_mel_decoder.to_out.0", true, 1, ctx->to_out)) return 1;
     if (ctx->to_out.OC != ctx->cfg.num_mels) return fail(ctx, "to_out.0 has %d output channels, expected %d", ctx->to_out.OC, ctx->cfg.num_mels);
-    return 0;
-}
-
-template <typename T>
-int upload_vec(zvx_ctx *ctx, const std::vector<T> &v, const T **out)
-{
-    T *d = nullptr;
-    if (dev_alloc(ctx, &d, v.size())) return 1;
-    CK(ctx, cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
-    *out = d;
     return 0;
 }
 
@@ -464,11 +506,13 @@ int build_vocoder(zvx_ctx *ctx, HostW &hw)
     char nm[128];
     const int nb = c.num_resblocks, nd = c.num_resblock_dilations;
     ctx->up.resize(c.num_upsamples);
+    ctx->upf.assign(c.num_upsamples, ConvLayer());
     ctx->mrf1.resize((size_t)c.num_upsamples * nb * nd);
     ctx->mrf2.resize((size_t)c.num_upsamples * nb * nd);
     for (int i = 0; i < c.num_upsamples; ++i) {
         snprintf(nm, sizeof nm, "_meldec.upsamples.%d.1", i);
         if (make_upconv(ctx, hw, nm, c.upsample_scales[i], ctx->up[i])) return 1;
+        if (make_upconv_fused(ctx, hw, nm, c.upsample_scales[i], ctx->up[i], ctx->upf[i])) return 1;
         if (ctx->up[i].IC != ctx->chans.back()) return fail(ctx, "%s: expects %d input channels, have %d", nm, ctx->up[i].IC, ctx->chans.back());
         ctx->rates.push_back(ctx->rates.back() * c.upsample_scales[i]);
         ctx->chans.push_back(ctx->up[i].OC);
@@ -489,6 +533,17 @@ int build_vocoder(zvx_ctx *ctx, HostW &hw)
     if (ctx->rates.back() != c.hop_size) return fail(ctx, "product of upsample_scales (%d) != hop_size (%d)", ctx->rates.back(), c.hop_size);
     if (make_conv(ctx, hw, "_meldec.output_conv.1", true, 1, ctx->output_conv, (c.kernel_size - 1) / 2)) return 1;
     if (ctx->output_conv.OC != 1 || ctx->output_conv.IC != ctx->chans.back()) return fail(ctx, "output_conv shape mismatch");
+    {
+        const std::vector<__half> &ow = hw.h["_meldec.output_conv.1.w"];
+        const std::vector<float> &ob = hw.f["_meldec.output_conv.1.b"];
+        const int C = ctx->output_conv.IC, K = ctx->output_conv.K;
+        if ((int)ow.size() == C * K && ob.size() == 1) {
+            ctx->out_w_kc.resize((size_t)K * C);
+            for (int cc = 0; cc < C; ++cc)
+                for (int k = 0; k < K; ++k) ctx->out_w_kc[(size_t)k * C + cc] = __half2float(ow[(size_t)cc * K + k]);
+            ctx->out_b_host = ob[0];
+        }
+    }
     return 0;
 }
 
@@ -638,6 +693,7 @@ struct ConvCall {
     float *out32 = nullptr; int ldo32 = 0, o32_ch_off = 0;
     __half *out16 = nullptr; int ldo16 = 0, o16_ch_off = 0; float out16_slope = 0.f;
     int out_mul = 1;
+    double flops = 0.0;        // algorithmic FLOPs of the launch when they differ from 2*rows*OC*IC*taps
 };
 
 int run_conv(zvx_ctx *ctx, const ConvCall &cc)
@@ -677,7 +733,7 @@ int run_conv(zvx_ctx *ctx, const ConvCall &cc)
     }
     ctx->launches++;
     const double rows = (double)ctx->last_frames * p.rate_in;
-    if (prof_begin(ctx, cc.kind, cc.stage, 2.0 * rows * L.OC * L.IC * v.ntaps, 0.0)) return 1;
+    if (prof_begin(ctx, cc.kind, cc.stage, cc.flops > 0.0 ? cc.flops : 2.0 * rows * L.OC * L.IC * v.ntaps, 0.0)) return 1;
     if (ctx->use_ref_kernels) {
         CK(ctx, conv_ref_launch(p, tiles, ctx->stream));
     } else {
@@ -804,6 +860,12 @@ int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out)
         const int cin = ctx->chans[i], ch = ctx->chans[i + 1];
         const int s = c.upsample_scales[i];
         // leaky_relu(0.1) -> ConvTranspose1d, one launch per output phase (hifigan.cpp:281-297, :22-71)
+        if (ctx->use_fused_upconv && ctx->upf[i].OC) {
+            ConvCall u; u.kind = ZVX_K_UPCONV; u.stage = i; u.L = &ctx->upf[i]; u.x = vin; u.ldx = cin; u.rate_idx = i;
+            u.pro_mode = PRO_LRELU; u.pro_slope = 0.1f; u.out32 = ctx->U; u.ldo32 = s * ch; u.out_mul = 1;
+            u.flops = 2.0 * (double)ctx->last_frames * ctx->rates[i] * s * ch * cin * (ctx->up[i].K / s);
+            if (run_conv(ctx, u)) return 1;
+        } else
         for (int phi = 0; phi < s; ++phi) {
             ConvCall u; u.kind = ZVX_K_UPCONV; u.stage = i; u.L = &ctx->up[i]; u.variant = phi; u.x = vin; u.ldx = cin; u.rate_idx = i;
             u.pro_mode = PRO_LRELU; u.pro_slope = 0.1f; u.out32 = ctx->U; u.ldo32 = ch; u.out_mul = s;
@@ -887,7 +949,8 @@ int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out)
                        rows * (ctx->chans[last] + 1) * sizeof(float)))
             return 1;
     }
-    CK(ctx, out_conv_launch(vin, ctx->chans[last], ctx->output_conv.K, ctx->output_conv.raw, ctx->output_conv.bias, 0.01f,
+    CK(ctx, out_conv_launch(vin, ctx->chans[last], ctx->output_conv.K, ctx->output_conv.raw, ctx->output_conv.bias,
+                            ctx->out_w_kc.empty() ? nullptr : ctx->out_w_kc.data(), ctx->out_b_host, 0.01f,
                             ctx->d_seg, ctx->d_tiles + (size_t)last * (ctx->cap_batch + 1), ctx->last_B, ctx->rates[last],
                             ctx->total_tiles[last], wav_out, ctx->stream));
     return prof_end(ctx);
@@ -980,6 +1043,7 @@ int zvx_create(zvx_ctx **out, const zvx_config *cfg, const zvx_tensor_desc *weig
     if (const char *e = getenv("ZVX_FUSED_MIN_EFF")) ctx->fused_min_eff = atof(e);
     if (const char *e = getenv("ZVX_FUSED_PREFETCH")) ctx->fused_prefetch = atoi(e);
     if (const char *e = getenv("ZVX_CONV_MT2")) ctx->conv_mt2 = atoi(e);
+    if (const char *e = getenv("ZVX_FUSED_UPCONV")) ctx->use_fused_upconv = atoi(e);
     ctx->num_sms = prop.multiProcessorCount;
     auto bail = [&](void) { g_create_error = ctx->err; zvx_destroy(ctx); return 1; };
 #define CKC(call)                                                                              \
