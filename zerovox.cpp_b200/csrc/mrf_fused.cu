@@ -125,15 +125,21 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
     const uint32_t buf1      = smem_base + C::OFF_BUF1;
     const uint32_t ring      = smem_base + C::OFF_RING;
 
-    // ---- which window of which utterance ----
-    const int win = blockIdx.x;
-    const int u   = find_segment(p.win_start, p.B, win);
-    const int wi  = win - __ldg(p.win_start + u);
-    const int f0  = __ldg(p.seg_start + u);
-    const int T   = (__ldg(p.seg_start + u + 1) - f0) * p.rate;
-    const size_t row0 = (size_t)f0 * p.rate;
-    const int tw  = wi * p.valid - p.halo;             // time of window position 0 (may be < 0)
-    const bool interior = tw >= 0 && tw + G::WP <= T;
+    // ---- persistent CTA: windows blockIdx.x, blockIdx.x + gridDim.x, ... of the launch ----
+    struct Win { int T; size_t row0; int tw; bool interior; };
+    auto window = [&](int win) {
+        Win w;
+        const int u  = find_segment(p.win_start, p.B, win);
+        const int wi = win - __ldg(p.win_start + u);
+        const int f0 = __ldg(p.seg_start + u);
+        w.T    = (__ldg(p.seg_start + u + 1) - f0) * p.rate;
+        w.row0 = (size_t)f0 * p.rate;
+        w.tw   = wi * p.valid - p.halo;                // time of window position 0 (may be < 0)
+        w.interior = w.tw >= 0 && w.tw + G::WP <= w.T;
+        return w;
+    };
+    const int nwin = p.total_windows;
+    const int nl   = p.nlayers;
 
     // ---- one-time setup.  Every data row of a buffer that holds a position inside the window is
     //      rewritten by each layer before it is read; what must read as finite zeros are the guard
@@ -162,6 +168,11 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    // The two halves of tensor memory swap roles every window: y of window i lives where the conv1
+    // accumulator of window i-1 lived, so that the next window's y can be written while the current
+    // window's last conv still accumulates into its own y.
+    auto ycol = [&](int iter) { return (uint32_t)((iter & 1) ? 0 : NCOL); };
+    auto hcol = [&](int iter) { return (uint32_t)((iter & 1) ? NCOL : 0); };
 
     if (warp < EPI_WARPS) {
         // =================== prologue + epilogues ===================
@@ -178,17 +189,18 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
 
         auto epi_sync = []() { asm volatile("bar.sync 1, %0;" ::"n"(C::EPI) : "memory"); };
 
-        // ---- prologue: y window -> tensor memory (fp32), lrelu(y) -> buffer 0 (fp16) ----
-        {
+        // y window -> tensor memory columns [ybase, ybase + NCOL) (fp32), lrelu(y) -> buffer 0 (fp16).
+        // Uses table slot 1; does NOT arrive on act_ready.
+        auto prologue = [&](const Win &w, uint32_t ybase) {
             for (int i = tid; i < TBL_WORDS; i += C::EPI) tbl_s[TBL_WORDS + i] = __ldg(p.tbl0 + i);
             epi_sync();
-            if (interior) {
+            if (w.interior && !(p.flags & 1)) {
 #pragma unroll 1
                 for (int lh = 0; lh < 2; ++lh) {
                     const int rb  = quarter * 32 + lh * 16;
                     const int sA  = rb / CH;
                     const int ocA = rb % CH + (lane >> 2);
-                    const float *yA = p.y_in + (row0 + (size_t)tw) * CH + ocA;
+                    const float *yA = p.y_in + (w.row0 + (size_t)w.tw) * CH + ocA;
                     const uint32_t *tb = tbl_s + TBL_WORDS + sA * NCOL + colw;
                     uint32_t v[32];
 #pragma unroll
@@ -200,7 +212,7 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
                         v[4 * cg + 2] = tau0 < G::WP ? __float_as_uint(__ldg(yA + (size_t)tau0 * CH + 8)) : 0u;
                         v[4 * cg + 3] = tau1 < G::WP ? __float_as_uint(__ldg(yA + (size_t)tau1 * CH + 8)) : 0u;
                     }
-                    tmem_st_16x256b_x8(tmem_base + ((uint32_t)rb << 16) + (uint32_t)(NCOL + colw), v);
+                    tmem_st_16x256b_x8(tmem_base + ((uint32_t)rb << 16) + ybase + (uint32_t)colw, v);
                     const uint32_t gbase = buf0 + (uint32_t)((rb % CH) >> 3) * LBO_B + (uint32_t)(mi & 1) * LBO_B;
 #pragma unroll
                     for (int pr = 0; pr < 4; ++pr) {
@@ -215,7 +227,7 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
                     }
                 }
             } else {
-                const float *yin = p.y_in + row0 * CH + oc;
+                const float *yin = p.y_in + w.row0 * CH + oc;
                 const uint32_t *tb = tbl_s + TBL_WORDS + s * NCOL;
                 uint8_t *dst = smem + C::OFF_BUF0 + toff;
 #pragma unroll 1
@@ -225,12 +237,12 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         const int tau = S * (col0 + i) + s;
-                        const int t   = tw + tau;
+                        const int t   = w.tw + tau;
                         float y = 0.f;
-                        if (tau < G::WP && t >= 0 && t < T) y = __ldg(yin + (size_t)t * CH);
+                        if (tau < G::WP && t >= 0 && t < w.T) y = __ldg(yin + (size_t)t * CH);
                         v[i] = __float_as_uint(y);
                     }
-                    tmem_st32(tlane + (uint32_t)(NCOL + col0), v);
+                    tmem_st32(tlane + ybase + (uint32_t)col0, v);
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         const uint32_t e = tb[col0 + i];
@@ -241,103 +253,132 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
             }
             tmem_wait_st();
             fence_proxy_async_smem();
+        };
+        auto publish = [&]() {
             tc_fence_before_sync();
             mbar_arrive(smem_u32(act_ready));
-        }
+        };
 
-        // ---- per-layer epilogues ----
+        int iter = 0;
+        int win = blockIdx.x;
+        if (win < nwin) {
+            const Win w0 = window(win);
+            prologue(w0, ycol(0));
+            publish();
+        }
 #pragma unroll 1
-        for (int l = 0; l < p.nlayers; ++l) {
-            const mrf::Layer &L = p.L[l];
-            const bool last = l == p.nlayers - 1;
-            const uint32_t acc_col = L.accumulate ? (uint32_t)NCOL : 0u;
-            if (!last) {
-                // stage this layer's scatter table while the MMAs run (double-buffered: a warp can only
-                // be one layer ahead of the slowest one, which reads the other copy)
-                uint32_t *tdst = tbl_s + (l & 1) * TBL_WORDS;
-                for (int i = tid; i < TBL_WORDS; i += C::EPI) tdst[i] = __ldg(L.tbl + i);
-                epi_sync();
-            }
-            mbar_wait(smem_u32(acc_full), (uint32_t)l & 1u, p.err_flag);
-            tc_fence_after_sync();
-            if (!last) {
-                const uint32_t obuf_off = (l & 1) ? C::OFF_BUF0 : C::OFF_BUF1;
-                const float slope = L.out_slope;
-                if (interior) {
+        for (; win < nwin; win += gridDim.x, ++iter) {
+            const Win w = window(win);
+            const int tw = w.tw, T = w.T;
+            const bool interior = w.interior;
+            const bool has_next = win + (int)gridDim.x < nwin;
 #pragma unroll 1
-                    for (int lh = 0; lh < 2; ++lh) {
-                        const int rb  = quarter * 32 + lh * 16;
-                        const int sA  = rb / CH;
-                        const int ocA = rb % CH + (lane >> 2);
-                        const float bA = __ldg(L.bias + ocA), bB = __ldg(L.bias + ocA + 8);
-                        const uint32_t *tb = tbl_s + (l & 1) * TBL_WORDS + sA * NCOL + colw;
-                        uint32_t r[32];
-                        tmem_ld_16x256b_x8(tmem_base + ((uint32_t)rb << 16) + acc_col + (uint32_t)colw, r);
-                        const uint32_t gbase = smem_base + obuf_off + (uint32_t)((rb % CH) >> 3) * LBO_B + (uint32_t)(mi & 1) * LBO_B;
+            for (int l = 0; l < nl; ++l) {
+                const mrf::Layer &L = p.L[l];
+                const bool last = l == nl - 1;
+                const uint32_t acc_col = L.accumulate ? ycol(iter) : hcol(iter);
+                const uint32_t gl = (uint32_t)(iter * nl + l);      // completions of acc_full before this one
+                if (!last) {
+                    // stage this layer's scatter table while the MMAs run (double-buffered: a warp can only
+                    // be one layer ahead of the slowest one, which reads the other copy)
+                    uint32_t *tdst = tbl_s + (l & 1) * TBL_WORDS;
+                    for (int i = tid; i < TBL_WORDS; i += C::EPI) tdst[i] = __ldg(L.tbl + i);
+                    epi_sync();
+                } else if (has_next) {
+                    // While the last conv of this window accumulates into y, bring in the NEXT window: its
+                    // y goes to the (now idle) conv1 accumulator columns, lrelu(y) to buffer 0 (the last
+                    // layer reads buffer 1; nlayers is even).  Published after this window's y is read.
+                    const Win wn = window(win + (int)gridDim.x);
+                    prologue(wn, hcol(iter));
+                }
+                mbar_wait(smem_u32(acc_full), gl & 1u, p.err_flag);
+                tc_fence_after_sync();
+                if (!last) {
+                    const uint32_t obuf_off = (l & 1) ? C::OFF_BUF0 : C::OFF_BUF1;
+                    const float slope = L.out_slope;
+                    if (interior) {
+#pragma unroll 1
+                        for (int lh = 0; lh < 2; ++lh) {
+                            const int rb  = quarter * 32 + lh * 16;
+                            const int sA  = rb / CH;
+                            const int ocA = rb % CH + (lane >> 2);
+                            const float bA = __ldg(L.bias + ocA), bB = __ldg(L.bias + ocA + 8);
+                            const uint32_t *tb = tbl_s + (l & 1) * TBL_WORDS + sA * NCOL + colw;
+                            uint32_t r[32];
+                            tmem_ld_16x256b_x8(tmem_base + ((uint32_t)rb << 16) + acc_col + (uint32_t)colw, r);
+                            const uint32_t gbase = smem_base + obuf_off + (uint32_t)((rb % CH) >> 3) * LBO_B + (uint32_t)(mi & 1) * LBO_B;
 #pragma unroll
-                        for (int pr = 0; pr < 4; ++pr) {
-                            uint32_t f[4];
+                            for (int pr = 0; pr < 4; ++pr) {
+                                uint32_t f[4];
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const int i0 = 8 * pr + 2 * q;
-                                const float b = (q & 1) ? bB : bA;
-                                f[q] = pack_h2(lrelu_max(__fadd_rn(__uint_as_float(r[i0]), b), slope),
-                                               lrelu_max(__fadd_rn(__uint_as_float(r[i0 + 1]), b), slope));
+                                for (int q = 0; q < 4; ++q) {
+                                    const int i0 = 8 * pr + 2 * q;
+                                    const float b = (q & 1) ? bB : bA;
+                                    f[q] = pack_h2(lrelu_max(__fadd_rn(__uint_as_float(r[i0]), b), slope),
+                                                   lrelu_max(__fadd_rn(__uint_as_float(r[i0 + 1]), b), slope));
+                                }
+                                const uint32_t e = tb[8 * (2 * pr + (mi >> 1)) + r8];
+                                stmatrix_x4_trans(gbase + mrf::tbl_byte(e), f[0], f[1], f[2], f[3]);
                             }
-                            const uint32_t e = tb[8 * (2 * pr + (mi >> 1)) + r8];
-                            stmatrix_x4_trans(gbase + mrf::tbl_byte(e), f[0], f[1], f[2], f[3]);
+                        }
+                    } else {
+                        const float bias = __ldg(L.bias + oc);
+                        const uint32_t *tb = tbl_s + (l & 1) * TBL_WORDS + s * NCOL;
+                        uint8_t *dst = smem + obuf_off + toff;
+#pragma unroll 1
+                        for (int b = 0; b < 2; ++b) {
+                            const int col0 = colw + b * 32;
+                            uint32_t r[32];
+                            tmem_ld32(tlane + acc_col + (uint32_t)col0, r);
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) {
+                                const uint32_t e = tb[col0 + i];
+                                float v = lrelu_max(__fadd_rn(__uint_as_float(r[i]), bias), slope);
+                                const int t = tw + mrf::tbl_tau(e);
+                                if (t < 0 || t >= T) v = 0.f;
+                                if (e & mrf::TBL_VALID) *reinterpret_cast<__half *>(dst + mrf::tbl_byte(e)) = __float2half_rn(v);
+                            }
                         }
                     }
+                    fence_proxy_async_smem();
+                    publish();
                 } else {
+                    // final: y (+ running branch sum) (* 1/num_blocks) -> global fp32.  Both 32-column
+                    // batches are pulled out of tensor memory first, then the next window is published
+                    // (its first conv may overwrite these columns), then the global traffic follows.
                     const float bias = __ldg(L.bias + oc);
-                    const uint32_t *tb = tbl_s + (l & 1) * TBL_WORDS + s * NCOL;
-                    uint8_t *dst = smem + obuf_off + toff;
-#pragma unroll 1
+                    float *out = p.out + w.row0 * CH + oc;
+                    const float *ain = p.acc_in ? p.acc_in + w.row0 * CH + oc : nullptr;
+                    uint32_t r0[32], r1[32];
+                    tmem_ld32(tlane + acc_col + (uint32_t)colw, r0);
+                    tmem_ld32(tlane + acc_col + (uint32_t)(colw + 32), r1);
+                    if (has_next) publish();
+#pragma unroll
                     for (int b = 0; b < 2; ++b) {
                         const int col0 = colw + b * 32;
-                        uint32_t r[32];
-                        tmem_ld32(tlane + acc_col + (uint32_t)col0, r);
+                        const uint32_t (&r)[32] = b ? r1 : r0;
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const uint32_t e = tb[col0 + i];
-                            float v = lrelu_max(__fadd_rn(__uint_as_float(r[i]), bias), slope);
-                            const int t = tw + mrf::tbl_tau(e);
-                            if (t < 0 || t >= T) v = 0.f;
-                            if (e & mrf::TBL_VALID) *reinterpret_cast<__half *>(dst + mrf::tbl_byte(e)) = __float2half_rn(v);
-                        }
-                    }
-                }
-                fence_proxy_async_smem();
-                tc_fence_before_sync();
-                mbar_arrive(smem_u32(act_ready));
-            } else {
-                // final: y (+ running branch sum) (* 1/num_blocks) -> global fp32
-                const float bias = __ldg(L.bias + oc);
-                float *out = p.out + row0 * CH + oc;
-                const float *ain = p.acc_in ? p.acc_in + row0 * CH + oc : nullptr;
-#pragma unroll 1
-                for (int b = 0; b < 2; ++b) {
-                    const int col0 = colw + b * 32;
-                    uint32_t r[32];
-                    tmem_ld32(tlane + acc_col + (uint32_t)col0, r);
-                    float a[32];
-                    if (ain) {
+                        for (int h = 0; h < 2; ++h) {
+                            float a[16];
+                            if (ain) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const int tau = S * (col0 + i) + s;
-                            const int t   = tw + tau;
-                            a[i] = (tau >= p.halo && tau < p.halo + p.valid && t < T) ? ain[(size_t)t * CH] : 0.f;
-                        }
-                    }
+                                for (int i = 0; i < 16; ++i) {
+                                    const int tau = S * (col0 + 16 * h + i) + s;
+                                    const int t   = tw + tau;
+                                    a[i] = (tau >= p.halo && tau < p.halo + p.valid && t < T) ? ain[(size_t)t * CH] : 0.f;
+                                }
+                            }
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const int tau = S * (col0 + i) + s;
-                        const int t   = tw + tau;
-                        if (tau >= p.halo && tau < p.halo + p.valid && t < T) {
-                            float v = __fadd_rn(__uint_as_float(r[i]), bias);
-                            if (ain) v = __fadd_rn(a[i], v);
-                            if (p.has_scale) v = __fmul_rn(v, p.scale);
-                            out[(size_t)t * CH] = v;
+                            for (int i = 0; i < 16; ++i) {
+                                const int tau = S * (col0 + 16 * h + i) + s;
+                                const int t   = tw + tau;
+                                if (tau >= p.halo && tau < p.halo + p.valid && t < T) {
+                                    float v = __fadd_rn(__uint_as_float(r[16 * h + i]), bias);
+                                    if (ain) v = __fadd_rn(a[i], v);
+                                    if (p.has_scale) v = __fmul_rn(v, p.scale);
+                                    out[(size_t)t * CH] = v;
+                                }
+                            }
                         }
                     }
                 }
@@ -347,82 +388,80 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
         // =================== MMA issuer ===================
         const uint32_t leader = elect_one();
         const uint32_t idesc  = make_idesc_mn(128, NCOL);
-        int it = 0;
+        int it = 0, iter = 0;
 #pragma unroll 1
-        for (int l = 0; l < p.nlayers; ++l) {
-            const mrf::Layer &L = p.L[l];
-            const int k  = L.k;
-            const int nj = k + S - 1;
-            const uint32_t lbo_a = (uint32_t)mrf::tap_blocks(k, S) * CH * 16u;
-            const uint32_t ibuf  = (l & 1) ? buf1 : buf0;
-            const uint32_t dcol  = tmem_base + (L.accumulate ? (uint32_t)NCOL : 0u);
-            mbar_wait(smem_u32(act_ready), (uint32_t)l & 1u, p.err_flag);
-            tc_fence_after_sync();
+        for (int win = blockIdx.x; win < nwin; win += gridDim.x, ++iter) {
 #pragma unroll 1
-            for (int c = 0; c < G::KSTEPS; ++c, ++it) {
-                const int slot = it % nslots;
-                const uint32_t ph = (uint32_t)(it / nslots) & 1u;
-                mbar_wait(smem_u32(w_full + slot), ph, p.err_flag);
-                tc_fence_after_sync();
-                if (leader) {
-                    const uint32_t a_slot = ring + (uint32_t)slot * slot_bytes;
-                    const uint32_t b_c    = ibuf + (uint32_t)(2 * c) * LBO_B + (uint32_t)mrf::GUARD * 16u;
-#pragma unroll 1
-                    for (int j = 0; j < nj; ++j) {
-                        int q, ro;
-                        mrf::b_step(k, S, j, q, ro);
-                        const uint64_t adesc = make_smem_desc(a_slot + (uint32_t)mrf::a_block(k, S, j) * (CH * 16u), lbo_a, 128u);
-                        const uint64_t bdesc = make_smem_desc(b_c + (uint32_t)q * G::SUB + (uint32_t)(ro * 16), LBO_B, 128u);
-                        umma_f16(dcol, adesc, bdesc, idesc, (L.accumulate || c > 0 || j > 0) ? 1u : 0u);
-                    }
-                    umma_commit(smem_u32(w_empty + slot));
-                }
-                __syncwarp();
-            }
-            if (leader) umma_commit(smem_u32(acc_full));
-            __syncwarp();
-        }
-    } else {
-        // =================== weight loader ===================
-        if (lane == 0) {
-            int it = 0;
-            for (int l = 0; l < p.nlayers; ++l) {
+            for (int l = 0; l < nl; ++l) {
                 const mrf::Layer &L = p.L[l];
-                const uint32_t bytes = mrf::chunk_bytes(L.k, S, CH);
+                const int k  = L.k;
+                const int nj = k + S - 1;
+                const uint32_t lbo_a = (uint32_t)mrf::tap_blocks(k, S) * CH * 16u;
+                const uint32_t ibuf  = (l & 1) ? buf1 : buf0;
+                const uint32_t dcol  = tmem_base + (L.accumulate ? ycol(iter) : hcol(iter));
+                mbar_wait(smem_u32(act_ready), (uint32_t)(iter * nl + l) & 1u, p.err_flag);
+                tc_fence_after_sync();
+#pragma unroll 1
                 for (int c = 0; c < G::KSTEPS; ++c, ++it) {
                     const int slot = it % nslots;
                     const uint32_t ph = (uint32_t)(it / nslots) & 1u;
-                    mbar_wait(smem_u32(w_empty + slot), ph ^ 1u, p.err_flag);
-                    mbar_arrive_expect_tx(smem_u32(w_full + slot), bytes);
-                    bulk_copy_g2s(ring + (uint32_t)slot * slot_bytes, reinterpret_cast<const uint8_t *>(L.w) + (size_t)c * bytes, bytes,
-                                  smem_u32(w_full + slot));
+                    mbar_wait(smem_u32(w_full + slot), ph, p.err_flag);
+                    tc_fence_after_sync();
+                    if (leader) {
+                        const uint32_t a_slot = ring + (uint32_t)slot * slot_bytes;
+                        const uint32_t b_c    = ibuf + (uint32_t)(2 * c) * LBO_B + (uint32_t)mrf::GUARD * 16u;
+#pragma unroll 1
+                        for (int j = 0; j < nj; ++j) {
+                            int q, ro;
+                            mrf::b_step(k, S, j, q, ro);
+                            const uint64_t adesc = make_smem_desc(a_slot + (uint32_t)mrf::a_block(k, S, j) * (CH * 16u), lbo_a, 128u);
+                            const uint64_t bdesc = make_smem_desc(b_c + (uint32_t)q * G::SUB + (uint32_t)(ro * 16), LBO_B, 128u);
+                            umma_f16(dcol, adesc, bdesc, idesc, (L.accumulate || c > 0 || j > 0) ? 1u : 0u);
+                        }
+                        umma_commit(smem_u32(w_empty + slot));
+                    }
+                    __syncwarp();
                 }
+                if (leader) umma_commit(smem_u32(acc_full));
+                __syncwarp();
             }
         }
-        __syncwarp();
-        // L2 prefetch of the inputs of the window that the next wave of CTAs will process (window
-        // index + number of resident CTAs): the prologue / final phases of a window are exposed HBM
-        // latency, pulling the lines into L2 while this window computes hides the DRAM part of it
-        const int nwin = win + p.prefetch_stride;
-        if (p.prefetch_stride > 0 && nwin < (int)gridDim.x) {
-            const int nu  = find_segment(p.win_start, p.B, nwin);
-            const int nwi = nwin - __ldg(p.win_start + nu);
-            const int nf0 = __ldg(p.seg_start + nu);
-            const int nT  = (__ldg(p.seg_start + nu + 1) - nf0) * p.rate;
-            const size_t nrow0 = (size_t)nf0 * p.rate;
-            const int ntw = nwi * p.valid - p.halo;
-            const int lo = max(ntw, 0), hi = min(ntw + G::WP, nT);
-            constexpr int ROWS_PER_LINE = 128 / (CH * 4) > 0 ? 128 / (CH * 4) : 1;   // CH = 32: one row per 128-B line
-            constexpr int LINES_PER_ROW = CH * 4 / 128 > 0 ? CH * 4 / 128 : 1;
-            const char *ybase = reinterpret_cast<const char *>(p.y_in + (nrow0 + (size_t)lo) * CH);
-            const int nlines = (hi - lo) * LINES_PER_ROW / ROWS_PER_LINE;
-            for (int i = lane; i < nlines; i += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(ybase + (size_t)i * 128));
-            if (p.acc_in) {
-                const int alo = max(ntw + p.halo, 0), ahi = min(ntw + p.halo + p.valid, nT);
-                const char *abase = reinterpret_cast<const char *>(p.acc_in + (nrow0 + (size_t)alo) * CH);
-                const int alines = (ahi - alo) * LINES_PER_ROW / ROWS_PER_LINE;
-                for (int i = lane; i < alines; i += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(abase + (size_t)i * 128));
+    } else {
+        // =================== weight loader + L2 prefetcher ===================
+        int it = 0;
+#pragma unroll 1
+        for (int win = blockIdx.x; win < nwin; win += gridDim.x) {
+            // L2 prefetch of the inputs of this CTA's NEXT window (requested a whole window ahead of
+            // the prologue that reads them): the y rows and, for the final phase, the running sum
+            const int nw = win + (int)gridDim.x;
+            if (p.prefetch && nw < nwin) {
+                const Win wn = window(nw);
+                const int lo = max(wn.tw, 0), hi = min(wn.tw + G::WP, wn.T);
+                const char *ybase = reinterpret_cast<const char *>(p.y_in + (wn.row0 + (size_t)lo) * CH);
+                const int nlines = (hi - lo) * (CH * 4) / 128;
+                for (int i = lane; i < nlines; i += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(ybase + (size_t)i * 128));
+                if (p.acc_in) {
+                    const int alo = max(wn.tw + p.halo, 0), ahi = min(wn.tw + p.halo + p.valid, wn.T);
+                    const char *abase = reinterpret_cast<const char *>(p.acc_in + (wn.row0 + (size_t)alo) * CH);
+                    const int alines = (ahi - alo) * (CH * 4) / 128;
+                    for (int i = lane; i < alines; i += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(abase + (size_t)i * 128));
+                }
             }
+            if (lane == 0) {
+                for (int l = 0; l < nl; ++l) {
+                    const mrf::Layer &L = p.L[l];
+                    const uint32_t bytes = mrf::chunk_bytes(L.k, S, CH);
+                    for (int c = 0; c < G::KSTEPS; ++c, ++it) {
+                        const int slot = it % nslots;
+                        const uint32_t ph = (uint32_t)(it / nslots) & 1u;
+                        mbar_wait(smem_u32(w_empty + slot), ph ^ 1u, p.err_flag);
+                        mbar_arrive_expect_tx(smem_u32(w_full + slot), bytes);
+                        bulk_copy_g2s(ring + (uint32_t)slot * slot_bytes, reinterpret_cast<const uint8_t *>(L.w) + (size_t)c * bytes, bytes,
+                                      smem_u32(w_full + slot));
+                    }
+                }
+            }
+            __syncwarp();
         }
     }
 
@@ -445,7 +484,11 @@ cudaError_t launch_cfg(const mrf::Params &p, int total_windows, cudaStream_t st)
     int nslots = (int)((C::SMEM_BUDGET - fixed) / slot);
     if (nslots > F_MAX_SLOTS) nslots = F_MAX_SLOTS;
     const size_t smem = fixed + (size_t)nslots * slot;
-    mrf_fused_kernel<CH, NCOL><<<total_windows, C::THREADS, smem, st>>>(p, nslots, slot);
+    const int resident = p.resident_ctas > 0 ? p.resident_ctas : total_windows;
+    const int grid = total_windows < resident ? total_windows : resident;
+    mrf::Params q = p;
+    q.total_windows = total_windows;
+    mrf_fused_kernel<CH, NCOL><<<grid, C::THREADS, smem, st>>>(q, nslots, slot);
     return cudaGetLastError();
 }
 

@@ -141,7 +141,10 @@ struct Params {
     int             rate;       // rows per frame at this stage
     int             halo;       // sum of pads of all layers
     int             valid;      // output time steps per window = WP - 2 halo
-    int             prefetch_stride;   // resident CTAs of the launch (L2 prefetch distance), 0: off
+    int             flags;             // experiment switches (bit 0: scalar prologue also for interior windows)
+    int             prefetch;          // 1: L2-prefetch the next window's inputs
+    int             resident_ctas;     // persistent grid size (SMs x CTAs per SM); 0: one CTA per window
+    int             total_windows;     // filled in by the launcher
     int            *err_flag;
 };
 

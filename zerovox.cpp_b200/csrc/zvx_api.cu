@@ -93,6 +93,8 @@ struct zvx_ctx {
     std::map<std::vector<int>, const uint32_t *> tbl_cache;
     int use_fused = 1;
     int fused_prefetch = 1;
+    int fused_persistent = 1;
+    int fused_flags = 0;
     int conv_mt2 = 0;   // two M-tiles per CTA: measured slower on B200 while the A producer is the limit (profiles/)
     std::vector<int> tile256_cfg;                 // per rate index: wincfg entry of the 256-row tiling
     int num_sms = 148;
@@ -892,7 +894,9 @@ int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out)
                     fp.win_start = ctx->d_wins + (size_t)fc.wincfg * (ctx->cap_batch + 1);
                     fp.B = ctx->last_B;
                     fp.ncol = fb.ncol;
-                    fp.prefetch_stride = ctx->fused_prefetch ? ctx->num_sms * (fb.ncol == 128 ? 2 : 1) : 0;
+                    fp.prefetch = ctx->fused_prefetch;
+                    fp.flags = ctx->fused_flags;
+                    fp.resident_ctas = ctx->fused_persistent ? ctx->num_sms * (fb.ncol == 128 ? 2 : 1) : 0;
                     fp.rate = ctx->rates[i + 1];
                     fp.halo = fc.halo;
                     fp.valid = fc.valid;
@@ -1042,6 +1046,8 @@ int zvx_create(zvx_ctx **out, const zvx_config *cfg, const zvx_tensor_desc *weig
     ctx->device = cfg->device;
     if (const char *e = getenv("ZVX_FUSED_MIN_EFF")) ctx->fused_min_eff = atof(e);
     if (const char *e = getenv("ZVX_FUSED_PREFETCH")) ctx->fused_prefetch = atoi(e);
+    if (const char *e = getenv("ZVX_FUSED_PERSISTENT")) ctx->fused_persistent = atoi(e);
+    if (const char *e = getenv("ZVX_FUSED_FLAGS")) ctx->fused_flags = atoi(e);
     if (const char *e = getenv("ZVX_CONV_MT2")) ctx->conv_mt2 = atoi(e);
     if (const char *e = getenv("ZVX_FUSED_UPCONV")) ctx->use_fused_upconv = atoi(e);
     ctx->num_sms = prop.multiProcessorCount;
