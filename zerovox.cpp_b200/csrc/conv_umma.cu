@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(128 * MT + 64) conv_umma_kernel(const ConvPara
             // before any of them is used (memory-level parallelism: the producer is latency-bound
             // otherwise), then transformed and stored with plain shared-memory stores.
             uint8_t *dstp = smem + SMEM_HEADER + (size_t)sa * a_stage_bytes + (size_t)j * lbo_a;
-            constexpr int UNR = 4;
+            constexpr int UNR = 8;
             for (int rho0 = r0; rho0 < need_rows; rho0 += UNR * rstep) {
                 float4 fa[UNR], fb[UNR];
                 uint4  hv[UNR];
