@@ -173,7 +173,8 @@ constexpr int OC_MAX_C = 64;
 constexpr int OC_MAX_K = 16;
 
 // Generic shape: weights staged in shared memory.
-__global__ void __launch_bounds__(128) out_conv_kernel(const float *__restrict__ x, int C, int K,
+__global__ void __launch_bounds__(128) out_conv_kernel(const float *__restrict__ x, const float *__restrict__ x2,
+                                                       const float *__restrict__ x3, float sum_scale, int C, int K,
                                                        const __half *__restrict__ w_raw, const float *__restrict__ bias,
                                                        float slope, const int *__restrict__ seg_start,
                                                        const int *__restrict__ tile_start, int B, int rate,
@@ -198,7 +199,11 @@ __global__ void __launch_bounds__(128) out_conv_kernel(const float *__restrict__
         const int r = i / C, c = i % C;
         const int t = t0 - pad + r;
         float v = 0.f;
-        if (t >= 0 && t < seg_len) v = __half2float(__float2half_rn(lrelu_f(x[(row0 + t) * C + c], slope)));
+        if (t >= 0 && t < seg_len) {
+            float xv = x[(row0 + t) * C + c];
+            if (x2) xv = __fmul_rn(__fadd_rn(__fadd_rn(xv, x2[(row0 + t) * C + c]), x3[(row0 + t) * C + c]), sum_scale);
+            v = __half2float(__float2half_rn(lrelu_f(xv, slope)));
+        }
         tile[r * (C + 1) + c] = v;
     }
     __syncthreads();
@@ -218,7 +223,8 @@ __global__ void __launch_bounds__(128) out_conv_kernel(const float *__restrict__
 // is one conflict-free LDS + one FFMA per MAC; the input tile is staged with float4 loads.
 struct OutConvW { float w[7 * 32]; float bias; };      // [k][c]
 
-__global__ void __launch_bounds__(128) out_conv_32x7_kernel(const float *__restrict__ x, const OutConvW W, float slope,
+__global__ void __launch_bounds__(128) out_conv_32x7_kernel(const float *__restrict__ x, const float *__restrict__ x2,
+                                                            const float *__restrict__ x3, float sum_scale, const OutConvW W, float slope,
                                                             const int *__restrict__ seg_start,
                                                             const int *__restrict__ tile_start, int B, int rate,
                                                             float *__restrict__ wav)
@@ -235,7 +241,18 @@ __global__ void __launch_bounds__(128) out_conv_32x7_kernel(const float *__restr
         const int r = i >> 3, c4 = (i & 7) * 4;
         const int t = t0 - (K - 1) / 2 + r;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (t >= 0 && t < seg_len) v = *reinterpret_cast<const float4 *>(x + (row0 + t) * C + c4);
+        if (t >= 0 && t < seg_len) {
+            v = *reinterpret_cast<const float4 *>(x + (row0 + t) * C + c4);
+            if (x2) {
+                // branch sum / average of the last MRF stage (hifigan.cpp:300-315), same order as the reference
+                const float4 b = *reinterpret_cast<const float4 *>(x2 + (row0 + t) * C + c4);
+                const float4 c = *reinterpret_cast<const float4 *>(x3 + (row0 + t) * C + c4);
+                v.x = __fmul_rn(__fadd_rn(__fadd_rn(v.x, b.x), c.x), sum_scale);
+                v.y = __fmul_rn(__fadd_rn(__fadd_rn(v.y, b.y), c.y), sum_scale);
+                v.z = __fmul_rn(__fadd_rn(__fadd_rn(v.z, b.z), c.z), sum_scale);
+                v.w = __fmul_rn(__fadd_rn(__fadd_rn(v.w, b.w), c.w), sum_scale);
+            }
+        }
         float *d = tile + r * LD + c4;
         d[0] = __half2float(__float2half_rn(lrelu_f(v.x, slope)));
         d[1] = __half2float(__float2half_rn(lrelu_f(v.y, slope)));
@@ -258,7 +275,7 @@ __global__ void __launch_bounds__(128) out_conv_32x7_kernel(const float *__restr
     wav[row0 + t] = tanhf(__fadd_rn(__fadd_rn(acc0, acc1), W.bias));
 }
 
-cudaError_t out_conv_launch(const float *x, int C, int K, const __half *w_raw, const float *bias, const float *w_host_kc,
+cudaError_t out_conv_launch(const float *x, const float *x2, const float *x3, float sum_scale, int C, int K, const __half *w_raw, const float *bias, const float *w_host_kc,
                             float bias_host, float slope, const int *seg_start, const int *tile_start, int B, int rate,
                             int total_tiles, float *wav, cudaStream_t st)
 {
@@ -266,12 +283,12 @@ cudaError_t out_conv_launch(const float *x, int C, int K, const __half *w_raw, c
         OutConvW W;
         for (int i = 0; i < 7 * 32; ++i) W.w[i] = w_host_kc[i];
         W.bias = bias_host;
-        out_conv_32x7_kernel<<<total_tiles, 128, 0, st>>>(x, W, slope, seg_start, tile_start, B, rate, wav);
+        out_conv_32x7_kernel<<<total_tiles, 128, 0, st>>>(x, x2, x3, sum_scale, W, slope, seg_start, tile_start, B, rate, wav);
         return cudaGetLastError();
     }
     if (C > OC_MAX_C || K > OC_MAX_K) return cudaErrorInvalidValue;
     const size_t smem = (OC_MAX_K * OC_MAX_C + (128 + OC_MAX_K) * (OC_MAX_C + 1)) * sizeof(float);
-    out_conv_kernel<<<total_tiles, 128, smem, st>>>(x, C, K, w_raw, bias, slope, seg_start, tile_start, B, rate, wav);
+    out_conv_kernel<<<total_tiles, 128, smem, st>>>(x, x2, x3, sum_scale, C, K, w_raw, bias, slope, seg_start, tile_start, B, rate, wav);
     return cudaGetLastError();
 }
 

@@ -43,7 +43,11 @@ __global__ void __launch_bounds__(128) conv_ref_kernel(const ConvParams p)
                     pc.g = p.p_g[(size_t)u * p.p_gb_stride + ic];
                     pc.b = p.p_b[(size_t)u * p.p_gb_stride + ic];
                 }
-                const float x = reinterpret_cast<const float *>(p.x)[e0 + ic];
+                float x = reinterpret_cast<const float *>(p.x)[e0 + ic];
+                if (p.pro_mode == PRO_SUM3) {
+                    x = __fmul_rn(__fadd_rn(__fadd_rn(x, p.x2[e0 + ic]), p.x3[e0 + ic]), p.sum_scale);
+                    xq = __half2float(__float2half_rn(lrelu_f(x, p.pro_slope)));
+                } else
                 xq = __half2float(__float2half_rn(prologue_apply(p.pro_mode, x, p.pro_slope, pc)));
             }
             const float w = __half2float(p.w_raw[((size_t)oc * p.Cin + ic) * p.w_taps_total + wt]);

@@ -143,6 +143,51 @@ __global__ void __launch_bounds__(128 * MT + 64) conv_umma_kernel(const ConvPara
             // before any of them is used (memory-level parallelism: the producer is latency-bound
             // otherwise), then transformed and stored with plain shared-memory stores.
             uint8_t *dstp = smem + SMEM_HEADER + (size_t)sa * a_stage_bytes + (size_t)j * lbo_a;
+            if (MODE == PRO_SUM3) {
+                // three fp32 sources per element: smaller batches (2 rows x 3 sources x 2 float4 in flight)
+                const float *x1 = reinterpret_cast<const float *>(p.x);
+                for (int rho0 = r0; rho0 < need_rows; rho0 += 2 * rstep) {
+                    float4 f[2][6];
+                    bool ok[2];
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const int rho  = rho0 + q * rstep;
+                        const int t_in = t0 + p.tap_off0 + rho;
+                        ok[q] = rho < need_rows && t_in >= 0 && t_in < seg_len;
+                        const size_t e = (seg_row0 + (size_t)(ok[q] ? t_in : 0)) * (size_t)p.ldx + p.x_ch_off + ch;
+#pragma unroll
+                        for (int i = 0; i < 6; ++i) f[q][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (ok[q]) {
+                            f[q][0] = *reinterpret_cast<const float4 *>(x1 + e);
+                            f[q][1] = *reinterpret_cast<const float4 *>(x1 + e + 4);
+                            f[q][2] = *reinterpret_cast<const float4 *>(p.x2 + e);
+                            f[q][3] = *reinterpret_cast<const float4 *>(p.x2 + e + 4);
+                            f[q][4] = *reinterpret_cast<const float4 *>(p.x3 + e);
+                            f[q][5] = *reinterpret_cast<const float4 *>(p.x3 + e + 4);
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const int rho = rho0 + q * rstep;
+                        if (rho >= need_rows) break;
+                        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                        if (ok[q]) {
+                            const float a[8] = {f[q][0].x, f[q][0].y, f[q][0].z, f[q][0].w, f[q][1].x, f[q][1].y, f[q][1].z, f[q][1].w};
+                            const float b[8] = {f[q][2].x, f[q][2].y, f[q][2].z, f[q][2].w, f[q][3].x, f[q][3].y, f[q][3].z, f[q][3].w};
+                            const float c[8] = {f[q][4].x, f[q][4].y, f[q][4].z, f[q][4].w, f[q][5].x, f[q][5].y, f[q][5].z, f[q][5].w};
+                            float o[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                o[i] = lrelu_f(__fmul_rn(__fadd_rn(__fadd_rn(a[i], b[i]), c[i]), p.sum_scale), p.pro_slope);
+                            v.x = pack_half2(o[0], o[1]);
+                            v.y = pack_half2(o[2], o[3]);
+                            v.z = pack_half2(o[4], o[5]);
+                            v.w = pack_half2(o[6], o[7]);
+                        }
+                        *reinterpret_cast<uint4 *>(dstp + (size_t)rho * 16) = v;
+                    }
+                }
+            } else {
             constexpr int UNR = 8;
             for (int rho0 = r0; rho0 < need_rows; rho0 += UNR * rstep) {
                 float4 fa[UNR], fb[UNR];
@@ -185,6 +230,7 @@ __global__ void __launch_bounds__(128 * MT + 64) conv_umma_kernel(const ConvPara
                     }
                     *reinterpret_cast<uint4 *>(dstp + (size_t)rho * 16) = v;
                 }
+            }
             }
             fence_proxy_async_smem();
             mbar_arrive(smem_u32(a_full + sa));
@@ -394,6 +440,7 @@ cudaError_t conv_umma_init()
     if ((e = init_mode<PRO_LRELU>()) != cudaSuccess) return e;
     if ((e = init_mode<PRO_NORM>()) != cudaSuccess) return e;
     if ((e = init_mode<PRO_MEL>()) != cudaSuccess) return e;
+    if ((e = init_mode<PRO_SUM3>()) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
@@ -413,6 +460,7 @@ cudaError_t conv_umma_launch(const ConvParams &p, int total_tiles, size_t smem, 
         case PRO_LRELU: return launch_mt<PRO_LRELU>(p, total_tiles, smem, st);
         case PRO_NORM:  return launch_mt<PRO_NORM>(p, total_tiles, smem, st);
         case PRO_MEL:   return launch_mt<PRO_MEL>(p, total_tiles, smem, st);
+        case PRO_SUM3:  return launch_mt<PRO_SUM3>(p, total_tiles, smem, st);
     }
     return cudaErrorInvalidValue;
 }

@@ -110,7 +110,9 @@ struct zvx_ctx {
     float *enc_in = nullptr, *sc = nullptr, *h528 = nullptr, *e0 = nullptr, *h1056 = nullptr, *catA = nullptr,
           *catB = nullptr, *asr = nullptr, *d1 = nullptr, *d2 = nullptr, *mel = nullptr, *style = nullptr;
     float *mu = nullptr, *rstd = nullptr, *adain_gb = nullptr;
-    float *v0 = nullptr, *U = nullptr, *CS = nullptr, *Y1 = nullptr, *VA = nullptr, *VB = nullptr, *wav = nullptr;
+    float *v0 = nullptr, *U = nullptr, *CS = nullptr, *Y1 = nullptr, *VA = nullptr, *VB = nullptr, *T2 = nullptr, *wav = nullptr;
+    int branch_sum_in_consumer = 1;               // fused stages: write the 3 branch outputs, the next kernel sums them
+    int stage_is_split[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // set per run: stage i's output lives in CS/VA/VB (3 buffers)
     __half *H16 = nullptr;
     int *d_seg = nullptr;                         // [B+1] frames prefix
     int *d_tiles = nullptr;                       // [nrates][B+1] tile prefixes
@@ -583,7 +585,7 @@ int reserve(zvx_ctx *ctx, int64_t frames, int batch)
     if (frames > ctx->cap_frames) {
         const int64_t F = std::max<int64_t>(frames, 256);
         float **bufs[] = {&ctx->enc_in, &ctx->sc, &ctx->h528, &ctx->e0, &ctx->h1056, &ctx->catA, &ctx->catB, &ctx->asr,
-                          &ctx->d1, &ctx->d2, &ctx->mel, &ctx->v0, &ctx->U, &ctx->CS, &ctx->Y1, &ctx->VA, &ctx->VB, &ctx->wav};
+                          &ctx->d1, &ctx->d2, &ctx->mel, &ctx->v0, &ctx->U, &ctx->CS, &ctx->Y1, &ctx->VA, &ctx->VB, &ctx->T2, &ctx->wav};
         for (float **b : bufs) { dev_free(ctx, *b); *b = nullptr; }
         dev_free(ctx, ctx->H16); ctx->H16 = nullptr;
         const int D = c.dim_in, BN = 2 * D, R = c.residual_dim;
@@ -599,6 +601,7 @@ int reserve(zvx_ctx *ctx, int64_t frames, int batch)
             const int64_t S = max_stage_elems(ctx);
             if (dev_alloc(ctx, &ctx->v0, F * ctx->chans[0]) || dev_alloc(ctx, &ctx->U, F * S) || dev_alloc(ctx, &ctx->CS, F * S) ||
                 dev_alloc(ctx, &ctx->Y1, F * S) || dev_alloc(ctx, &ctx->VA, F * S) || dev_alloc(ctx, &ctx->VB, F * S) ||
+                dev_alloc(ctx, &ctx->T2, F * S) ||
                 dev_alloc(ctx, &ctx->H16, F * S) || dev_alloc(ctx, &ctx->wav, F * c.hop_size))
                 return 1;
         }
@@ -684,6 +687,7 @@ struct ConvCall {
     const ConvLayer *L = nullptr;
     int variant = 0;
     const void *x = nullptr; int ldx = 0, x_ch_off = 0;
+    const float *x2 = nullptr, *x3 = nullptr; float sum_scale = 0.f;   // PRO_SUM3
     int rate_idx = 0;          // index into ctx->rates of the INPUT rate
     int pro_mode = PRO_CVT; float pro_slope = 0.f;
     const float *mu = nullptr, *rstd = nullptr; int stat_stride = 0;
@@ -705,6 +709,7 @@ int run_conv(zvx_ctx *ctx, const ConvCall &cc)
     ConvParams p;
     memset(&p, 0, sizeof p);
     p.x = cc.x; p.ldx = cc.ldx; p.x_ch_off = cc.x_ch_off; p.Cin = L.IC;
+    p.x2 = cc.x2; p.x3 = cc.x3; p.sum_scale = cc.sum_scale;
     p.seg_start = ctx->d_seg;
     p.tile_start = ctx->d_tiles + (size_t)cc.rate_idx * (ctx->cap_batch + 1);
     p.B = ctx->last_B;
@@ -854,9 +859,10 @@ int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out)
         ic.out32 = ctx->v0; ic.ldo32 = ctx->chans[0];
         if (run_conv(ctx, ic)) return 1;
     }
-    const float *vin = ctx->v0;
+    const float *vin = ctx->v0, *vin2 = nullptr, *vin3 = nullptr;   // vin2/vin3: stage output still split in 3 branches
     float *vout[2] = {ctx->VA, ctx->VB};
     const float third = (float)(1.0 / (float)nb);
+    for (int i = 0; i < 8; ++i) ctx->stage_is_split[i] = 0;
     for (int i = 0; i < c.num_upsamples; ++i) {
         if (ctx->debug_stop >= 0 && i >= ctx->debug_stop) return 0;
         const int cin = ctx->chans[i], ch = ctx->chans[i + 1];
@@ -865,20 +871,28 @@ int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out)
         if (ctx->use_fused_upconv && ctx->upf[i].OC) {
             ConvCall u; u.kind = ZVX_K_UPCONV; u.stage = i; u.L = &ctx->upf[i]; u.x = vin; u.ldx = cin; u.rate_idx = i;
             u.pro_mode = PRO_LRELU; u.pro_slope = 0.1f; u.out32 = ctx->U; u.ldo32 = s * ch; u.out_mul = 1;
+            if (vin2) { u.pro_mode = PRO_SUM3; u.x2 = vin2; u.x3 = vin3; u.sum_scale = third; }
             u.flops = 2.0 * (double)ctx->last_frames * ctx->rates[i] * s * ch * cin * (ctx->up[i].K / s);
             if (run_conv(ctx, u)) return 1;
         } else
         for (int phi = 0; phi < s; ++phi) {
             ConvCall u; u.kind = ZVX_K_UPCONV; u.stage = i; u.L = &ctx->up[i]; u.variant = phi; u.x = vin; u.ldx = cin; u.rate_idx = i;
             u.pro_mode = PRO_LRELU; u.pro_slope = 0.1f; u.out32 = ctx->U; u.ldo32 = ch; u.out_mul = s;
+            if (vin2) { u.pro_mode = PRO_SUM3; u.x2 = vin2; u.x3 = vin3; u.sum_scale = third; }
             if (run_conv(ctx, u)) return 1;
         }
-        // MRF: three residual blocks on U, averaged (hifigan.cpp:300-315, :97-183)
+        // MRF: three residual blocks on U, averaged (hifigan.cpp:300-315, :97-183).  When all three run as
+        // fused chains, each writes its own output buffer and the branch sum / average is applied by the
+        // consumer (next up-conv or the output conv, PRO_SUM3): the fused kernel's final phase is then pure
+        // stores instead of a read-modify-write of the running sum.
+        bool split = ctx->branch_sum_in_consumer && ctx->use_fused && !ctx->use_ref_kernels && nb == 3;
+        for (int j = 0; j < nb; ++j) split = split && ctx->fused[(size_t)i * nb + j].CH != 0;
+        float *branch_out[3] = {ctx->CS, ctx->VA, ctx->VB};
         for (int j = 0; j < nb; ++j) {
             const FusedBlock &fb = ctx->fused[(size_t)i * nb + j];
             if (ctx->use_fused && !ctx->use_ref_kernels && fb.CH) {
                 // whole residual block (or chains of its conv pairs) on chip: mrf_fused.cu
-                float *tmp[2] = {ctx->Y1, vout[(i + 1) & 1]};     // the stage-input buffer is free after the up-conv
+                float *tmp[2] = {ctx->Y1, split ? ctx->T2 : vout[(i + 1) & 1]};   // (the stage-input buffer is free after the up-conv)
                 const float *yin = ctx->U;
                 for (size_t q = 0; q < fb.chains.size(); ++q) {
                     const FusedChain &fc = fb.chains[q];
@@ -903,6 +917,8 @@ int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out)
                     fp.err_flag = ctx->d_err;
                     if (!lastc) {
                         fp.out = tmp[q & 1];
+                    } else if (split) {
+                        fp.out = branch_out[j];                        // y_j; summed by the consumer
                     } else if (j == 0 && nb > 1) {
                         fp.out = ctx->CS;                              // cs = y_0
                     } else {
@@ -941,7 +957,8 @@ int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out)
                 if (run_conv(ctx, c2)) return 1;
             }
         }
-        vin = vout[i & 1];
+        if (split) { vin = branch_out[0]; vin2 = branch_out[1]; vin3 = branch_out[2]; ctx->stage_is_split[i] = 1; }
+        else { vin = vout[i & 1]; vin2 = vin3 = nullptr; }
     }
     if (ctx->debug_stop >= 0) return 0;
     // leaky_relu(0.01) -> output_conv -> tanh (hifigan.cpp:324-345)
@@ -953,7 +970,7 @@ int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out)
                        rows * (ctx->chans[last] + 1) * sizeof(float)))
             return 1;
     }
-    CK(ctx, out_conv_launch(vin, ctx->chans[last], ctx->output_conv.K, ctx->output_conv.raw, ctx->output_conv.bias,
+    CK(ctx, out_conv_launch(vin, vin2, vin3, third, ctx->chans[last], ctx->output_conv.K, ctx->output_conv.raw, ctx->output_conv.bias,
                             ctx->out_w_kc.empty() ? nullptr : ctx->out_w_kc.data(), ctx->out_b_host, 0.01f,
                             ctx->d_seg, ctx->d_tiles + (size_t)last * (ctx->cap_batch + 1), ctx->last_B, ctx->rates[last],
                             ctx->total_tiles[last], wav_out, ctx->stream));
@@ -1048,6 +1065,7 @@ int zvx_create(zvx_ctx **out, const zvx_config *cfg, const zvx_tensor_desc *weig
     if (const char *e = getenv("ZVX_FUSED_PREFETCH")) ctx->fused_prefetch = atoi(e);
     if (const char *e = getenv("ZVX_FUSED_PERSISTENT")) ctx->fused_persistent = atoi(e);
     if (const char *e = getenv("ZVX_FUSED_FLAGS")) ctx->fused_flags = atoi(e);
+    if (const char *e = getenv("ZVX_BRANCH_SUM_IN_CONSUMER")) ctx->branch_sum_in_consumer = atoi(e);
     if (const char *e = getenv("ZVX_CONV_MT2")) ctx->conv_mt2 = atoi(e);
     if (const char *e = getenv("ZVX_FUSED_UPCONV")) ctx->use_fused_upconv = atoi(e);
     ctx->num_sms = prop.multiProcessorCount;
@@ -1319,6 +1337,18 @@ int zvx_debug_fetch(zvx_ctx *ctx, const char *what, float *dst, int64_t n)
         if (i < 0 || i >= ctx->cfg.num_upsamples) return fail(ctx, "bad stage");
         src = (i & 1) ? ctx->VB : ctx->VA;
         have = F * ctx->rates[i + 1] * ctx->chans[i + 1];
+        if (ctx->stage_is_split[i]) {
+            // the stage output is still split into its three branches: combine like the consumer does
+            if (n > have) return fail(ctx, "debug tensor '%s' has %lld floats, asked for %lld", what, (long long)have, (long long)n);
+            CK(ctx, cudaStreamSynchronize(ctx->stream));
+            std::vector<float> b1((size_t)n), b2((size_t)n);
+            CK(ctx, cudaMemcpy(dst, ctx->CS, sizeof(float) * n, cudaMemcpyDeviceToHost));
+            CK(ctx, cudaMemcpy(b1.data(), ctx->VA, sizeof(float) * n, cudaMemcpyDeviceToHost));
+            CK(ctx, cudaMemcpy(b2.data(), ctx->VB, sizeof(float) * n, cudaMemcpyDeviceToHost));
+            const float third = (float)(1.0 / 3.0);
+            for (int64_t q = 0; q < n; ++q) dst[q] = ((dst[q] + b1[q]) + b2[q]) * third;
+            return 0;
+        }
     } else return fail(ctx, "unknown debug tensor '%s'", what);
     if (n > have) return fail(ctx, "debug tensor '%s' has %lld floats, asked for %lld", what, (long long)have, (long long)n);
     CK(ctx, cudaStreamSynchronize(ctx->stream));

@@ -27,11 +27,15 @@ enum ProMode : int {
     PRO_LRELU = 2,   // leaky_relu(x, slope) -> fp16              (hifigan.cpp:108,281,324)
     PRO_NORM  = 3,   // ((x-mu)*rstd)*g + b -> leaky_relu(slope)  (stylettsdec.cpp:94-104,191-197,253)
     PRO_MEL   = 4,   // (x - mean) / scale                        (hifigan.cpp:242-243)
+    PRO_SUM3  = 5,   // leaky_relu(((x + x2) + x3) * sum_scale, slope): the MRF branch sum / average of
+                     // hifigan.cpp:300-315 applied by the CONSUMER of the three residual-block outputs
 };
 
 struct ConvParams {
     // ---- input ----
     const void  *x;           // fp32 (or fp16 when pro_mode == PRO_F16), [rows][ldx]
+    const float *x2, *x3;     // PRO_SUM3: the other two branch outputs, same layout as x
+    float        sum_scale;   // PRO_SUM3: 1 / num_resblocks
     int          ldx;         // elements per input row
     int          x_ch_off;    // first input channel inside a row
     int          Cin;
