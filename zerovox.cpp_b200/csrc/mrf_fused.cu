@@ -91,9 +91,9 @@ struct FCfg {
     static constexpr int CTAS      = NCOL == 128 ? 2 : 1;
     static constexpr int TBL_WORDS = G::S * NCOL;
     static constexpr uint32_t OFF_TBL  = F_HEADER;
-    static constexpr uint32_t OFF_BUF0 = OFF_TBL + 2 * TBL_WORDS * 4;
-    static constexpr uint32_t OFF_BUF1 = OFF_BUF0 + G::BUF;
-    static constexpr uint32_t OFF_RING = OFF_BUF1 + G::BUF;
+    // compact (16-bit row unit) copies of the scatter tables of all layers stay resident: tbl0 + one per
+    // non-final layer
+    __host__ __device__ static constexpr uint32_t tbl_bytes(int nlayers) { return (uint32_t)((nlayers * TBL_WORDS * 2 + 511) & ~511); }
     static constexpr size_t   SMEM_BUDGET = NCOL == 128 ? 112 * 1024 : 227 * 1024;
 };
 
@@ -114,16 +114,19 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
     uint64_t *acc_full  = bars + 2 * F_MAX_SLOTS;
     uint64_t *act_ready = bars + 2 * F_MAX_SLOTS + 1;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 256);
-    uint32_t *tbl_s     = reinterpret_cast<uint32_t *>(smem + C::OFF_TBL);     // [2][S][NCOL]
+    uint16_t *tbl_s     = reinterpret_cast<uint16_t *>(smem + C::OFF_TBL);     // [nlayers][S][NCOL] row units
+    const uint32_t OFF_BUF0 = C::OFF_TBL + C::tbl_bytes(p.nlayers);
+    const uint32_t OFF_BUF1 = OFF_BUF0 + G::BUF;
+    const uint32_t OFF_RING = OFF_BUF1 + G::BUF;
 
     const int tid  = threadIdx.x;
     const int warp = tid >> 5;
     const int lane = tid & 31;
 
     const uint32_t smem_base = smem_u32(smem);
-    const uint32_t buf0      = smem_base + C::OFF_BUF0;
-    const uint32_t buf1      = smem_base + C::OFF_BUF1;
-    const uint32_t ring      = smem_base + C::OFF_RING;
+    const uint32_t buf0      = smem_base + OFF_BUF0;
+    const uint32_t buf1      = smem_base + OFF_BUF1;
+    const uint32_t ring      = smem_base + OFF_RING;
 
     // ---- persistent CTA: windows blockIdx.x, blockIdx.x + gridDim.x, ... of the launch ----
     struct Win { int T; size_t row0; int tw; bool interior; };
@@ -150,8 +153,12 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
         for (int i = tid; i < 2 * S * G::GROUPS * NZ; i += C::THREADS) {
             const int sg = i / NZ, z = i % NZ;
             const int row = z < mrf::GUARD ? z : mrf::GUARD + ROW_LO + (z - mrf::GUARD);
-            *reinterpret_cast<uint4 *>(smem + C::OFF_BUF0 + (size_t)sg * LBO_B + (size_t)row * 16) = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4 *>(smem + OFF_BUF0 + (size_t)sg * LBO_B + (size_t)row * 16) = make_uint4(0u, 0u, 0u, 0u);
         }
+    }
+    for (int t = 0; t < nl; ++t) {
+        const uint32_t *src = t == 0 ? p.tbl0 : p.L[t - 1].tbl;
+        for (int i = tid; i < TBL_WORDS; i += C::THREADS) tbl_s[t * TBL_WORDS + i] = (uint16_t)(mrf::tbl_byte(__ldg(src + i)) >> 4);
     }
     if (tid == 0) {
         for (int s = 0; s < nslots; ++s) {
@@ -187,13 +194,9 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
         // ---- fragment-path coordinates: per 16-lane half lh, rows rb + lane/4 and rb + lane/4 + 8 ----
         const int mi = lane >> 3, r8 = lane & 7;       // stmatrix: this thread addresses row r8 of matrix mi
 
-        auto epi_sync = []() { asm volatile("bar.sync 1, %0;" ::"n"(C::EPI) : "memory"); };
-
         // y window -> tensor memory columns [ybase, ybase + NCOL) (fp32), lrelu(y) -> buffer 0 (fp16).
         // Uses table slot 1; does NOT arrive on act_ready.
         auto prologue = [&](const Win &w, uint32_t ybase) {
-            for (int i = tid; i < TBL_WORDS; i += C::EPI) tbl_s[TBL_WORDS + i] = __ldg(p.tbl0 + i);
-            epi_sync();
             if (w.interior && !(p.flags & 1)) {
 #pragma unroll 1
                 for (int lh = 0; lh < 2; ++lh) {
@@ -201,7 +204,7 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
                     const int sA  = rb / CH;
                     const int ocA = rb % CH + (lane >> 2);
                     const float *yA = p.y_in + (w.row0 + (size_t)w.tw) * CH + ocA;
-                    const uint32_t *tb = tbl_s + TBL_WORDS + sA * NCOL + colw;
+                    const uint16_t *tb = tbl_s + sA * NCOL + colw;
                     uint32_t v[32];
 #pragma unroll
                     for (int cg = 0; cg < 8; ++cg) {
@@ -223,13 +226,13 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
                             f[q] = pack_h2(lrelu_max(__uint_as_float(v[i0]), p.in_slope), lrelu_max(__uint_as_float(v[i0 + 1]), p.in_slope));
                         }
                         const uint32_t e = tb[8 * (2 * pr + (mi >> 1)) + r8];
-                        stmatrix_x4_trans(gbase + mrf::tbl_byte(e), f[0], f[1], f[2], f[3]);
+                        stmatrix_x4_trans(gbase + e * 16u, f[0], f[1], f[2], f[3]);
                     }
                 }
             } else {
                 const float *yin = p.y_in + w.row0 * CH + oc;
-                const uint32_t *tb = tbl_s + TBL_WORDS + s * NCOL;
-                uint8_t *dst = smem + C::OFF_BUF0 + toff;
+                const uint32_t *tb = p.tbl0 + s * NCOL;             // full entries (tau for the edge mask) from global
+                uint8_t *dst = smem + OFF_BUF0 + toff;
 #pragma unroll 1
                 for (int b = 0; b < 2; ++b) {
                     const int col0 = colw + b * 32;
@@ -245,7 +248,7 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
                     tmem_st32(tlane + ybase + (uint32_t)col0, v);
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
-                        const uint32_t e = tb[col0 + i];
+                        const uint32_t e = __ldg(tb + col0 + i);
                         const __half h = __float2half_rn(lrelu_max(__uint_as_float(v[i]), p.in_slope));
                         if (e & mrf::TBL_VALID) *reinterpret_cast<__half *>(dst + mrf::tbl_byte(e)) = h;
                     }
@@ -278,13 +281,7 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
                 const bool last = l == nl - 1;
                 const uint32_t acc_col = L.accumulate ? ycol(iter) : hcol(iter);
                 const uint32_t gl = (uint32_t)(iter * nl + l);      // completions of acc_full before this one
-                if (!last) {
-                    // stage this layer's scatter table while the MMAs run (double-buffered: a warp can only
-                    // be one layer ahead of the slowest one, which reads the other copy)
-                    uint32_t *tdst = tbl_s + (l & 1) * TBL_WORDS;
-                    for (int i = tid; i < TBL_WORDS; i += C::EPI) tdst[i] = __ldg(L.tbl + i);
-                    epi_sync();
-                } else if (has_next) {
+                if (last && has_next) {
                     // While the last conv of this window accumulates into y, bring in the NEXT window: its
                     // y goes to the (now idle) conv1 accumulator columns, lrelu(y) to buffer 0 (the last
                     // layer reads buffer 1; nlayers is even).  Published after this window's y is read.
@@ -294,7 +291,7 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
                 mbar_wait(smem_u32(acc_full), gl & 1u, p.err_flag);
                 tc_fence_after_sync();
                 if (!last) {
-                    const uint32_t obuf_off = (l & 1) ? C::OFF_BUF0 : C::OFF_BUF1;
+                    const uint32_t obuf_off = (l & 1) ? OFF_BUF0 : OFF_BUF1;
                     const float slope = L.out_slope;
                     if (interior) {
 #pragma unroll 1
@@ -303,7 +300,7 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
                             const int sA  = rb / CH;
                             const int ocA = rb % CH + (lane >> 2);
                             const float bA = __ldg(L.bias + ocA), bB = __ldg(L.bias + ocA + 8);
-                            const uint32_t *tb = tbl_s + (l & 1) * TBL_WORDS + sA * NCOL + colw;
+                            const uint16_t *tb = tbl_s + (l + 1) * TBL_WORDS + sA * NCOL + colw;
                             uint32_t r[32];
                             tmem_ld_16x256b_x8(tmem_base + ((uint32_t)rb << 16) + acc_col + (uint32_t)colw, r);
                             const uint32_t gbase = smem_base + obuf_off + (uint32_t)((rb % CH) >> 3) * LBO_B + (uint32_t)(mi & 1) * LBO_B;
@@ -318,12 +315,12 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
                                                    lrelu_max(__fadd_rn(__uint_as_float(r[i0 + 1]), b), slope));
                                 }
                                 const uint32_t e = tb[8 * (2 * pr + (mi >> 1)) + r8];
-                                stmatrix_x4_trans(gbase + mrf::tbl_byte(e), f[0], f[1], f[2], f[3]);
+                                stmatrix_x4_trans(gbase + e * 16u, f[0], f[1], f[2], f[3]);
                             }
                         }
                     } else {
                         const float bias = __ldg(L.bias + oc);
-                        const uint32_t *tb = tbl_s + (l & 1) * TBL_WORDS + s * NCOL;
+                        const uint32_t *tb = L.tbl + s * NCOL;              // full entries from global
                         uint8_t *dst = smem + obuf_off + toff;
 #pragma unroll 1
                         for (int b = 0; b < 2; ++b) {
@@ -332,7 +329,7 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
                             tmem_ld32(tlane + acc_col + (uint32_t)col0, r);
 #pragma unroll
                             for (int i = 0; i < 32; ++i) {
-                                const uint32_t e = tb[col0 + i];
+                                const uint32_t e = __ldg(tb + col0 + i);
                                 float v = lrelu_max(__fadd_rn(__uint_as_float(r[i]), bias), slope);
                                 const int t = tw + mrf::tbl_tau(e);
                                 if (t < 0 || t >= T) v = 0.f;
@@ -479,7 +476,7 @@ cudaError_t launch_cfg(const mrf::Params &p, int total_windows, cudaStream_t st)
     using C = FCfg<CH, NCOL>;
     uint32_t slot = 0;
     for (int l = 0; l < p.nlayers; ++l) slot = max(slot, mrf::chunk_bytes(p.L[l].k, C::G::S, CH));
-    const size_t fixed = C::OFF_RING;
+    const size_t fixed = C::OFF_TBL + C::tbl_bytes(p.nlayers) + 2 * (size_t)C::G::BUF;
     if (fixed + slot > C::SMEM_BUDGET) return cudaErrorInvalidConfiguration;
     int nslots = (int)((C::SMEM_BUDGET - fixed) / slot);
     if (nslots > F_MAX_SLOTS) nslots = F_MAX_SLOTS;
