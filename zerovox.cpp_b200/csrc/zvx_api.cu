@@ -429,13 +429,15 @@ int build_fused(zvx_ctx *ctx, HostW &hw)
         if (2 * nd > mrf::MAX_LAYERS) continue;
         // columns per window: 128 -> two CTAs per SM (one's epilogue overlaps the other's MMAs) at the
         // price of a larger halo fraction; worth it where the MMA phase per layer is short (CH = 32)
-        int ncol = 256;   // measured on B200 (profiles/): 256 beats 128 for every CH, also CH = 32
+        // columns per window, chosen per residual block below: 128 -> two CTAs per SM (one's epilogue
+        // overlaps the other's MMAs) at the price of a larger halo fraction; pays off only for short kernels
+        int ncol128_maxk = CH == 32 ? 3 : 0;      // measured on B200 (profiles/): CH = 32, k = 3 only
         {
-            char key[32];
-            snprintf(key, sizeof key, "ZVX_NCOL_%d", CH);
-            if (const char *e = getenv(key)) ncol = atoi(e);
+            char key[40];
+            snprintf(key, sizeof key, "ZVX_NCOL128_MAXK_%d", CH);
+            if (const char *e = getenv(key)) ncol128_maxk = atoi(e);
         }
-        if (!mrf_fused_supported(CH, ncol)) return fail(ctx, "fused MRF: unsupported (CH=%d, ncol=%d)", CH, ncol);
+
         for (int j = 0; j < nb; ++j) {
             const size_t idx0 = ((size_t)i * nb + j) * nd;
             const int k = ctx->mrf1[idx0].K;
@@ -448,6 +450,7 @@ int build_fused(zvx_ctx *ctx, HostW &hw)
             }
             if (!ok) continue;
             FusedBlock &fb = ctx->fused[(size_t)i * nb + j];
+            const int ncol = (k <= ncol128_maxk && mrf_fused_supported(CH, 128)) ? 128 : 256;
             fb.k = k;
             fb.ncol = ncol;
             std::vector<float> cum(CH, 0.f);
