@@ -5,6 +5,8 @@
 #include "zvx_common.cuh"
 #include "zvx_internal.h"
 
+#include <algorithm>
+
 namespace zvx {
 
 // ---------------------------------------------------------------------------------
@@ -160,6 +162,71 @@ cudaError_t norm_affine_launch(const float *x, int ldx, int C, const int *seg_st
 {
     dim3 grid(32, B);
     norm_affine_kernel<<<grid, 256, 0, st>>>(x, ldx, C, seg_start, B, mu, rstd, w, b, dst0, dst1, ld_dst, dst_ch_off);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------
+// InstanceNorm / AdaIN apply + leaky-ReLU + fp16 rounding as a stand-alone pass:
+//   y16 = fp16(lrelu(((x - mu) * rstd) * g + b, slope))      (same arithmetic and rounding order as
+// the fused PRO_NORM prologue of conv_umma.cu; stylettsdec.cpp:94-104,191-197,253).
+// The decoder convs split their output channels over 3-6 CTAs per time tile; with the prologue
+// fused each of them re-did this math on the same rows, which made the A-operand producers the
+// bottleneck (profiles/).  One pass here (10 B of HBM traffic per element) lets the convs load
+// ready-made fp16 operands.
+// ---------------------------------------------------------------------------------
+constexpr int NA_ROWS = 32;      // rows per block
+
+// grid (ceil(max_len / NA_ROWS), B), block = C/8 threads (one 8-channel group each, <= 256): a thread
+// keeps its group's mean / rstd / gain / shift in registers and streams over the rows of its chunk;
+// a warp reads / writes consecutive 32-byte / 16-byte pieces of one row.
+__global__ void __launch_bounds__(256) norm_act_f16_kernel(const float *__restrict__ x, int ldx, int ch_off, int C,
+                                                           const int *__restrict__ seg_start,
+                                                           const float *__restrict__ mu, const float *__restrict__ rstd,
+                                                           const float *__restrict__ g, const float *__restrict__ b,
+                                                           int gb_stride, float slope, __half *__restrict__ y16)
+{
+    const int u = blockIdx.y;
+    const size_t r0 = (size_t)seg_start[u] + (size_t)blockIdx.x * NA_ROWS;
+    const size_t r1 = min(r0 + NA_ROWS, (size_t)seg_start[u + 1]);
+    const int c = threadIdx.x * 8;
+    if (r0 >= r1 || c >= C) return;
+    ProCh pc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        pc[q].mu = __ldg(mu + (size_t)u * C + c + q);
+        pc[q].rstd = __ldg(rstd + (size_t)u * C + c + q);
+        pc[q].g = __ldg(g + (size_t)u * gb_stride + c + q);
+        pc[q].b = __ldg(b + (size_t)u * gb_stride + c + q);
+    }
+    const float *px = x + ch_off + c;
+    for (size_t r = r0; r < r1; r += 4) {
+        float4 xa[4], xb[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const size_t rr = r + k < r1 ? r + k : r1 - 1;
+            xa[k] = *reinterpret_cast<const float4 *>(px + rr * ldx);
+            xb[k] = *reinterpret_cast<const float4 *>(px + rr * ldx + 4);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (r + k >= r1) break;
+            const float xv[8] = {xa[k].x, xa[k].y, xa[k].z, xa[k].w, xb[k].x, xb[k].y, xb[k].z, xb[k].w};
+            __half h[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) h[q] = __float2half_rn(prologue_apply(PRO_NORM, xv[q], slope, pc[q]));
+            *reinterpret_cast<uint4 *>(y16 + (r + k) * C + c) = *reinterpret_cast<const uint4 *>(h);
+        }
+    }
+}
+
+cudaError_t norm_act_f16_launch(const float *x, int ldx, int ch_off, int C, const int *seg_start, int B, int max_len,
+                                const float *mu, const float *rstd, const float *g, const float *b, int gb_stride, float slope,
+                                __half *y16, cudaStream_t st)
+{
+    if (C % 8 || C / 8 > 256) return cudaErrorInvalidValue;
+    dim3 grid((max_len + NA_ROWS - 1) / NA_ROWS, B);
+    const int threads = ((C / 8 + 31) / 32) * 32;
+    norm_act_f16_kernel<<<grid, threads, 0, st>>>(x, ldx, ch_off, C, seg_start, mu, rstd, g, b, gb_stride, slope, y16);
     return cudaGetLastError();
 }
 

@@ -113,7 +113,8 @@ struct zvx_ctx {
     float *v0 = nullptr, *U = nullptr, *CS = nullptr, *Y1 = nullptr, *VA = nullptr, *VB = nullptr, *T2 = nullptr, *wav = nullptr;
     int branch_sum_in_consumer = 1;               // fused stages: write the 3 branch outputs, the next kernel sums them
     int stage_is_split[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // set per run: stage i's output lives in CS/VA/VB (3 buffers)
-    __half *H16 = nullptr;
+    __half *H16 = nullptr, *X16 = nullptr;       // X16: decoder conv operand (normalised, activated, fp16)
+    int dec_prepass = 1;
     int *d_seg = nullptr;                         // [B+1] frames prefix
     int *d_tiles = nullptr;                       // [nrates][B+1] tile prefixes
     int *d_err = nullptr;
@@ -125,6 +126,7 @@ struct zvx_ctx {
     float *pin_in = nullptr, *pin_out = nullptr;  // pinned staging for host-pointer API
     size_t pin_in_cap = 0, pin_out_cap = 0;
     int last_B = 0;
+    int last_max_len = 0;
     int64_t last_frames = 0;
     // ---- per-launch profiling (CUDA events on the launch stream) ----
     bool prof = false;
@@ -591,8 +593,10 @@ int reserve(zvx_ctx *ctx, int64_t frames, int batch)
                           &ctx->d1, &ctx->d2, &ctx->mel, &ctx->v0, &ctx->U, &ctx->CS, &ctx->Y1, &ctx->VA, &ctx->VB, &ctx->T2, &ctx->wav};
         for (float **b : bufs) { dev_free(ctx, *b); *b = nullptr; }
         dev_free(ctx, ctx->H16); ctx->H16 = nullptr;
+        dev_free(ctx, ctx->X16); ctx->X16 = nullptr;
         const int D = c.dim_in, BN = 2 * D, R = c.residual_dim;
         if (c.with_decoder) {
+            if (dev_alloc(ctx, &ctx->X16, F * (BN + R))) return 1;
             if (dev_alloc(ctx, &ctx->enc_in, F * D) || dev_alloc(ctx, &ctx->sc, F * BN) || dev_alloc(ctx, &ctx->h528, F * D) ||
                 dev_alloc(ctx, &ctx->e0, F * BN) || dev_alloc(ctx, &ctx->h1056, F * BN) || dev_alloc(ctx, &ctx->catA, F * (BN + R)) ||
                 dev_alloc(ctx, &ctx->catB, F * (BN + R)) || dev_alloc(ctx, &ctx->asr, F * R) || dev_alloc(ctx, &ctx->d1, F * D) ||
@@ -659,6 +663,8 @@ int set_batch(zvx_ctx *ctx, int B, const int32_t *L, bool reserve_workspace = tr
     ctx->tables_pending = true;
     ctx->last_B = B;
     ctx->last_frames = frames;
+    ctx->last_max_len = 0;
+    for (int b = 0; b < B; ++b) ctx->last_max_len = std::max(ctx->last_max_len, (int)L[b]);
     return 0;
 }
 
@@ -762,6 +768,22 @@ int run_stats(zvx_ctx *ctx, const float *x, int ld, int ch_off, int C)
     return prof_end(ctx);
 }
 
+// A decoder conv whose input is InstanceNorm/AdaIN-affine + leaky-ReLU of x (stats already in ctx->mu/rstd):
+// either fused into the conv's prologue (PRO_NORM) or as a stand-alone fp16 pass + PRO_F16 conv.
+int run_norm_conv(zvx_ctx *ctx, ConvCall cc)
+{
+    if (!ctx->dec_prepass || ctx->use_ref_kernels) return run_conv(ctx, cc);
+    const int C = cc.L->IC;
+    ctx->launches++;
+    if (prof_begin(ctx, ZVX_K_NORM_AFFINE, 0, 0.0, 6.0 * (double)ctx->last_frames * C)) return 1;
+    CK(ctx, norm_act_f16_launch(reinterpret_cast<const float *>(cc.x), cc.ldx, cc.x_ch_off, C, ctx->d_seg, ctx->last_B, ctx->last_max_len,
+                                cc.mu, cc.rstd, cc.g, cc.b, cc.gb_stride, cc.pro_slope, ctx->X16, ctx->stream));
+    if (prof_end(ctx)) return 1;
+    cc.x = ctx->X16; cc.ldx = C; cc.x_ch_off = 0; cc.pro_mode = PRO_F16;
+    cc.mu = cc.rstd = cc.g = cc.b = nullptr;
+    return run_conv(ctx, cc);
+}
+
 // ---------------------------------------------------------------- decoder schedule
 // enc_in [F][D] and style [B][S] are already on the device.
 int run_decoder(zvx_ctx *ctx, float *mel_out)
@@ -795,13 +817,13 @@ int run_decoder(zvx_ctx *ctx, float *mel_out)
         ConvCall c1; c1.L = &b.conv1; c1.x = x; c1.ldx = ldx; c1.pro_mode = PRO_NORM; c1.pro_slope = 0.2f;
         c1.mu = ctx->mu; c1.rstd = ctx->rstd; c1.stat_stride = b.cin; c1.g = b.n1w; c1.b = b.n1b; c1.gb_stride = 0;
         c1.out32 = enc_h[i]; c1.ldo32 = b.cin;
-        if (run_conv(ctx, c1)) return 1;
+        if (run_norm_conv(ctx, c1)) return 1;
         if (run_stats(ctx, enc_h[i], b.cin, 0, b.cin)) return 1;
         ConvCall c2; c2.L = &b.conv2; c2.x = enc_h[i]; c2.ldx = b.cin; c2.pro_mode = PRO_NORM; c2.pro_slope = 0.2f;
         c2.mu = ctx->mu; c2.rstd = ctx->rstd; c2.stat_stride = b.cin; c2.g = b.n2w; c2.b = b.n2b; c2.gb_stride = 0;
         c2.res = sc; c2.ldres = ldsc; c2.scale = inv_sqrt2;
         c2.out32 = enc_out[i]; c2.ldo32 = enc_ld[i];
-        if (run_conv(ctx, c2)) return 1;
+        if (run_norm_conv(ctx, c2)) return 1;
         x = enc_out[i]; ldx = enc_ld[i];
     }
     // ---- asr_res = IN_affine(conv1x1(enc_seq) + b)  (stylettsdec.cpp:382-396), into both concat buffers ----
@@ -829,7 +851,7 @@ int run_decoder(zvx_ctx *ctx, float *mel_out)
         c1.mu = ctx->mu; c1.rstd = ctx->rstd; c1.stat_stride = b.cin;
         c1.g = ctx->adain_gb + a1.out_off; c1.b = ctx->adain_gb + a1.out_off + a1.C; c1.gb_stride = ctx->adain.total;
         c1.out32 = h; c1.ldo32 = b.cout;
-        if (run_conv(ctx, c1)) return 1;
+        if (run_norm_conv(ctx, c1)) return 1;
         const float *sc = din[i]; int ldsc = dinl[i];
         if (b.learned_sc) {
             ConvCall s; s.L = &b.conv1x1; s.x = din[i]; s.ldx = dinl[i]; s.pro_mode = PRO_CVT; s.use_bias = false;
@@ -843,7 +865,7 @@ int run_decoder(zvx_ctx *ctx, float *mel_out)
         c2.g = ctx->adain_gb + a2.out_off; c2.b = ctx->adain_gb + a2.out_off + a2.C; c2.gb_stride = ctx->adain.total;
         c2.res = sc; c2.ldres = ldsc; c2.scale = inv_sqrt2;
         c2.out32 = dout[i]; c2.ldo32 = doutl[i];
-        if (run_conv(ctx, c2)) return 1;
+        if (run_norm_conv(ctx, c2)) return 1;
     }
     // ---- to_out (stylettsdec.cpp:432-441) ----
     ConvCall o; o.L = &ctx->to_out; o.x = dout[4]; o.ldx = D; o.pro_mode = PRO_CVT; o.out32 = mel_out; o.ldo32 = c.num_mels;
@@ -1068,6 +1090,7 @@ int zvx_create(zvx_ctx **out, const zvx_config *cfg, const zvx_tensor_desc *weig
     if (const char *e = getenv("ZVX_FUSED_PREFETCH")) ctx->fused_prefetch = atoi(e);
     if (const char *e = getenv("ZVX_FUSED_PERSISTENT")) ctx->fused_persistent = atoi(e);
     if (const char *e = getenv("ZVX_FUSED_FLAGS")) ctx->fused_flags = atoi(e);
+    if (const char *e = getenv("ZVX_DEC_PREPASS")) ctx->dec_prepass = atoi(e);
     if (const char *e = getenv("ZVX_BRANCH_SUM_IN_CONSUMER")) ctx->branch_sum_in_consumer = atoi(e);
     if (const char *e = getenv("ZVX_CONV_MT2")) ctx->conv_mt2 = atoi(e);
     if (const char *e = getenv("ZVX_FUSED_UPCONV")) ctx->use_fused_upconv = atoi(e);

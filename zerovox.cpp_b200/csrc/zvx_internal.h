@@ -49,6 +49,11 @@ cudaError_t norm_affine_launch(const float *x, int ldx, int C, const int *seg_st
                                const float *rstd, const float *w, const float *b, float *dst0, float *dst1, int ld_dst,
                                int dst_ch_off, cudaStream_t st);
 
+// y16 = fp16(lrelu(((x-mu)*rstd)*g + b, slope)) for an [rows][C] slice; stats / affine per utterance
+cudaError_t norm_act_f16_launch(const float *x, int ldx, int ch_off, int C, const int *seg_start, int B, int max_len,
+                                const float *mu, const float *rstd, const float *g, const float *b, int gb_stride, float slope,
+                                __half *y16, cudaStream_t st);
+
 // wav = tanh(conv_k(leaky_relu(x, slope)) + b), single output channel
 // w_host_kc: host copy of the weights as fp32 [K][C] (constant-bank fast path for C = 32, K = 7), may be null
 // x2 / x3 non-null: input = ((x + x2) + x3) * sum_scale (MRF branch average applied by the consumer)
