@@ -219,6 +219,33 @@ __global__ void __launch_bounds__(256) norm_act_f16_kernel(const float *__restri
     }
 }
 
+// fp32 -> fp16 copy of an [rows][C] slice (operand of the 1x1 shortcut convs, which take the raw input)
+__global__ void __launch_bounds__(256) cvt_f16_kernel(const float *__restrict__ x, int ldx, int ch_off, int C, size_t rows,
+                                                      __half *__restrict__ y16)
+{
+    const int G = C >> 3;
+    const size_t total = rows * (size_t)G;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t row = i / G;
+        const int c = (int)(i % G) * 8;
+        const float4 a = *reinterpret_cast<const float4 *>(x + row * ldx + ch_off + c);
+        const float4 b = *reinterpret_cast<const float4 *>(x + row * ldx + ch_off + c + 4);
+        __half h[8] = {__float2half_rn(a.x), __float2half_rn(a.y), __float2half_rn(a.z), __float2half_rn(a.w),
+                       __float2half_rn(b.x), __float2half_rn(b.y), __float2half_rn(b.z), __float2half_rn(b.w)};
+        *reinterpret_cast<uint4 *>(y16 + row * C + c) = *reinterpret_cast<const uint4 *>(h);
+    }
+}
+
+cudaError_t cvt_f16_launch(const float *x, int ldx, int ch_off, int C, size_t rows, __half *y16, cudaStream_t st)
+{
+    if (C % 8) return cudaErrorInvalidValue;
+    const size_t total = rows * (size_t)(C / 8);
+    int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)148 * 8);
+    if (blocks < 1) blocks = 1;
+    cvt_f16_kernel<<<blocks, 256, 0, st>>>(x, ldx, ch_off, C, rows, y16);
+    return cudaGetLastError();
+}
+
 cudaError_t norm_act_f16_launch(const float *x, int ldx, int ch_off, int C, const int *seg_start, int B, int max_len,
                                 const float *mu, const float *rstd, const float *g, const float *b, int gb_stride, float slope,
                                 __half *y16, cudaStream_t st)

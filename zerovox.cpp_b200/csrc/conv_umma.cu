@@ -42,6 +42,230 @@ constexpr int SMEM_HEADER  = 256;
 
 __device__ __forceinline__ uint32_t make_idesc(int N) { return make_idesc_mn(TILE_M, N); }
 
+// completion of this thread's earlier cp.async copies counts as its arrival on the barrier
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar)
+{
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// ------------------------------------------------------------------ shared pieces
+struct TileCoord {
+    int u;            // utterance
+    int t0;           // first output row of the tile inside the utterance (input-rate rows)
+    int seg_len;      // rows of the utterance
+    size_t seg_row0;  // first row of the utterance in the packed tensors
+    int nchunk;       // N-chunk (output channels [nchunk*NC, +NC))
+};
+
+// One 64-channel K-chunk of the A operand: read the halo tile, apply the fused prologue, round to
+// fp16 and store it in the no-swizzle K-major layout (8-row groups 128 B apart, channel groups
+// lbo_a apart).  `tid` is the producer-thread index in [0, NPROD).
+template <int MODE, int NPROD, int UNR_>
+__device__ __forceinline__ void produce_chunk(const ConvParams &p, const TileCoord &tc, int c, uint8_t *stage, uint32_t lbo_a,
+                                              int need_rows, int tid)
+{
+    const int kc   = min(KCHUNK, p.Cin - c * KCHUNK);
+    const int G    = kc >> 3;                 // 8-channel groups in this chunk: 8, 4 or 2
+    const int lg   = (G == 8) ? 3 : (G == 4) ? 2 : 1;
+    const int j    = tid & (G - 1);
+    const int r0   = tid >> lg;
+    const int rstep = NPROD >> lg;
+    const int ch   = c * KCHUNK + j * 8;      // channel (relative to x_ch_off) of this thread's group
+
+    ProCh pc[8];
+    if (MODE == PRO_NORM || MODE == PRO_MEL) {
+        const float *mu = p.p_mu + (size_t)tc.u * p.p_stat_stride + ch;
+        const float *rs = p.p_rstd + (size_t)tc.u * p.p_stat_stride + ch;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            pc[i].mu = __ldg(mu + i);
+            pc[i].rstd = __ldg(rs + i);
+        }
+        if (MODE == PRO_NORM) {
+            const float *g = p.p_g + (size_t)tc.u * p.p_gb_stride + ch;
+            const float *b = p.p_b + (size_t)tc.u * p.p_gb_stride + ch;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                pc[i].g = __ldg(g + i);
+                pc[i].b = __ldg(b + i);
+            }
+        }
+    }
+
+    // Rows of this thread: rho = r0 + i * rstep.  Loads of a batch of UNR rows are issued
+    // before any of them is used (memory-level parallelism: the producer is latency-bound
+    // otherwise), then transformed and stored with plain shared-memory stores.
+    uint8_t *dstp = stage + (size_t)j * lbo_a;
+    if (MODE == PRO_F16) {
+        // ready-made fp16 operand: asynchronous 16-byte copies global -> shared (zero-filled outside the
+        // utterance); the caller makes the stage's mbarrier track their completion, so a producer
+        // thread can have several K-chunks in flight instead of one batch of loads at a time
+        const uint32_t dst0 = smem_u32(dstp);
+        for (int rho = r0; rho < need_rows; rho += rstep) {
+            const int t_in = tc.t0 + p.tap_off0 + rho;
+            const bool ok = t_in >= 0 && t_in < tc.seg_len;
+            const size_t e = (tc.seg_row0 + (size_t)(ok ? t_in : 0)) * (size_t)p.ldx + p.x_ch_off + ch;
+            const __half *src = reinterpret_cast<const __half *>(p.x) + e;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + (uint32_t)rho * 16u), "l"(src), "r"(ok ? 16 : 0) : "memory");
+        }
+    } else if (MODE == PRO_SUM3) {
+        // three fp32 sources per element: smaller batches (2 rows x 3 sources x 2 float4 in flight)
+        const float *x1 = reinterpret_cast<const float *>(p.x);
+        for (int rho0 = r0; rho0 < need_rows; rho0 += 2 * rstep) {
+            float4 f[2][6];
+            bool ok[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int rho  = rho0 + q * rstep;
+                const int t_in = tc.t0 + p.tap_off0 + rho;
+                ok[q] = rho < need_rows && t_in >= 0 && t_in < tc.seg_len;
+                const size_t e = (tc.seg_row0 + (size_t)(ok[q] ? t_in : 0)) * (size_t)p.ldx + p.x_ch_off + ch;
+#pragma unroll
+                for (int i = 0; i < 6; ++i) f[q][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ok[q]) {
+                    f[q][0] = *reinterpret_cast<const float4 *>(x1 + e);
+                    f[q][1] = *reinterpret_cast<const float4 *>(x1 + e + 4);
+                    f[q][2] = *reinterpret_cast<const float4 *>(p.x2 + e);
+                    f[q][3] = *reinterpret_cast<const float4 *>(p.x2 + e + 4);
+                    f[q][4] = *reinterpret_cast<const float4 *>(p.x3 + e);
+                    f[q][5] = *reinterpret_cast<const float4 *>(p.x3 + e + 4);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int rho = rho0 + q * rstep;
+                if (rho >= need_rows) break;
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                if (ok[q]) {
+                    const float a[8] = {f[q][0].x, f[q][0].y, f[q][0].z, f[q][0].w, f[q][1].x, f[q][1].y, f[q][1].z, f[q][1].w};
+                    const float b[8] = {f[q][2].x, f[q][2].y, f[q][2].z, f[q][2].w, f[q][3].x, f[q][3].y, f[q][3].z, f[q][3].w};
+                    const float c[8] = {f[q][4].x, f[q][4].y, f[q][4].z, f[q][4].w, f[q][5].x, f[q][5].y, f[q][5].z, f[q][5].w};
+                    float o[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        o[i] = lrelu_f(__fmul_rn(__fadd_rn(__fadd_rn(a[i], b[i]), c[i]), p.sum_scale), p.pro_slope);
+                    v.x = pack_half2(o[0], o[1]);
+                    v.y = pack_half2(o[2], o[3]);
+                    v.z = pack_half2(o[4], o[5]);
+                    v.w = pack_half2(o[6], o[7]);
+                }
+                *reinterpret_cast<uint4 *>(dstp + (size_t)rho * 16) = v;
+            }
+        }
+    } else {
+    constexpr int UNR = UNR_;
+    for (int rho0 = r0; rho0 < need_rows; rho0 += UNR * rstep) {
+        float4 fa[UNR], fb[UNR];
+        uint4  hv[UNR];
+        bool   ok[UNR];
+#pragma unroll
+        for (int q = 0; q < UNR; ++q) {
+            const int rho  = rho0 + q * rstep;
+            const int t_in = tc.t0 + p.tap_off0 + rho;
+            ok[q] = rho < need_rows && t_in >= 0 && t_in < tc.seg_len;
+            const size_t e = (tc.seg_row0 + (size_t)(ok[q] ? t_in : 0)) * (size_t)p.ldx + p.x_ch_off + ch;
+            if (MODE == PRO_F16) {
+                hv[q] = make_uint4(0u, 0u, 0u, 0u);
+                if (ok[q]) hv[q] = *reinterpret_cast<const uint4 *>(reinterpret_cast<const __half *>(p.x) + e);
+            } else {
+                fa[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                fb[q] = fa[q];
+                if (ok[q]) {
+                    const float4 *src = reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(p.x) + e);
+                    fa[q] = src[0];
+                    fb[q] = src[1];
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < UNR; ++q) {
+            const int rho = rho0 + q * rstep;
+            if (rho >= need_rows) break;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (MODE == PRO_F16) {
+                v = hv[q];
+            } else if (ok[q]) {
+                float f[8] = {fa[q].x, fa[q].y, fa[q].z, fa[q].w, fb[q].x, fb[q].y, fb[q].z, fb[q].w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] = prologue_apply(MODE, f[i], p.pro_slope, pc[i]);
+                v.x = pack_half2(f[0], f[1]);
+                v.y = pack_half2(f[2], f[3]);
+                v.z = pack_half2(f[4], f[5]);
+                v.w = pack_half2(f[6], f[7]);
+            }
+            *reinterpret_cast<uint4 *>(dstp + (size_t)rho * 16) = v;
+        }
+    }
+    }
+}
+
+// Drain one accumulator row (thread = output time step) from tensor memory and apply the fused
+// epilogue: bias, residual, branch sum, scale; fp32 and / or fp16(leaky-ReLU) outputs.
+__device__ __forceinline__ void epilogue_row(const ConvParams &p, uint32_t trow, bool valid, size_t orow, int nchunk, int NC)
+{
+    for (int col = 0; col < NC; col += 16) {
+        uint32_t r[16];
+        tmem_ld16(trow + (uint32_t)col, r);
+        if (!valid) continue;
+        const int oc = nchunk * NC + col;
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+        if (p.bias) {
+            const float4 *b4 = reinterpret_cast<const float4 *>(p.bias + oc);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 b = __ldg(b4 + q);
+                v[4 * q + 0] = __fadd_rn(v[4 * q + 0], b.x);
+                v[4 * q + 1] = __fadd_rn(v[4 * q + 1], b.y);
+                v[4 * q + 2] = __fadd_rn(v[4 * q + 2], b.z);
+                v[4 * q + 3] = __fadd_rn(v[4 * q + 3], b.w);
+            }
+        }
+        if (p.res) {
+            const float4 *r4 = reinterpret_cast<const float4 *>(p.res + orow * (size_t)p.ldres + p.res_ch_off + oc);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 b = r4[q];
+                v[4 * q + 0] = __fadd_rn(v[4 * q + 0], b.x);
+                v[4 * q + 1] = __fadd_rn(v[4 * q + 1], b.y);
+                v[4 * q + 2] = __fadd_rn(v[4 * q + 2], b.z);
+                v[4 * q + 3] = __fadd_rn(v[4 * q + 3], b.w);
+            }
+        }
+        if (p.acc_in) {
+            const float4 *r4 =
+                reinterpret_cast<const float4 *>(p.acc_in + orow * (size_t)p.ldo32 + p.o32_ch_off + oc);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 b = r4[q];
+                v[4 * q + 0] = __fadd_rn(b.x, v[4 * q + 0]);
+                v[4 * q + 1] = __fadd_rn(b.y, v[4 * q + 1]);
+                v[4 * q + 2] = __fadd_rn(b.z, v[4 * q + 2]);
+                v[4 * q + 3] = __fadd_rn(b.w, v[4 * q + 3]);
+            }
+        }
+        if (p.has_scale) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __fmul_rn(v[i], p.scale);
+        }
+        if (p.out32) {
+            float4 *o4 = reinterpret_cast<float4 *>(p.out32 + orow * (size_t)p.ldo32 + p.o32_ch_off + oc);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) o4[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
+        if (p.out16) {
+            uint4 *o4 = reinterpret_cast<uint4 *>(p.out16 + orow * (size_t)p.ldo16 + p.o16_ch_off + oc);
+            uint32_t h[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                h[i] = pack_half2(lrelu_f(v[2 * i], p.out16_slope), lrelu_f(v[2 * i + 1], p.out16_slope));
+            o4[0] = make_uint4(h[0], h[1], h[2], h[3]);
+            o4[1] = make_uint4(h[4], h[5], h[6], h[7]);
+        }
+    }
+}
+
 // ------------------------------------------------------------------ the kernel
 template <int MODE, int MT>
 __global__ void __launch_bounds__(128 * MT + 64) conv_umma_kernel(const ConvParams p)
@@ -83,6 +307,7 @@ __global__ void __launch_bounds__(128 * MT + 64) conv_umma_kernel(const ConvPara
     const int seg_len = (__ldg(p.seg_start + u + 1) - seg_f0) * p.rate_in;
     const size_t seg_row0 = (size_t)seg_f0 * p.rate_in;
     const int nchunk  = blockIdx.y;
+    const TileCoord tc = {u, t0, seg_len, seg_row0, nchunk};
 
     if (tid == 0) {
         for (int s = 0; s < p.a_stages; ++s) {
@@ -111,129 +336,13 @@ __global__ void __launch_bounds__(128 * MT + 64) conv_umma_kernel(const ConvPara
             const uint32_t ph = (uint32_t)(c / p.a_stages) & 1u;
             mbar_wait(smem_u32(a_empty + sa), ph ^ 1u, p.err_flag);
 
-            const int kc   = min(KCHUNK, Cin - c * KCHUNK);
-            const int G    = kc >> 3;                 // 8-channel groups in this chunk: 8, 4 or 2
-            const int lg   = (G == 8) ? 3 : (G == 4) ? 2 : 1;
-            const int j    = tid & (G - 1);
-            const int r0   = tid >> lg;
-            const int rstep = N_PRODUCERS >> lg;
-            const int ch   = c * KCHUNK + j * 8;      // channel (relative to x_ch_off) of this thread's group
-
-            ProCh pc[8];
-            if (MODE == PRO_NORM || MODE == PRO_MEL) {
-                const float *mu = p.p_mu + (size_t)u * p.p_stat_stride + ch;
-                const float *rs = p.p_rstd + (size_t)u * p.p_stat_stride + ch;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    pc[i].mu = __ldg(mu + i);
-                    pc[i].rstd = __ldg(rs + i);
-                }
-                if (MODE == PRO_NORM) {
-                    const float *g = p.p_g + (size_t)u * p.p_gb_stride + ch;
-                    const float *b = p.p_b + (size_t)u * p.p_gb_stride + ch;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        pc[i].g = __ldg(g + i);
-                        pc[i].b = __ldg(b + i);
-                    }
-                }
-            }
-
-            // Rows of this thread: rho = r0 + i * rstep.  Loads of a batch of UNR rows are issued
-            // before any of them is used (memory-level parallelism: the producer is latency-bound
-            // otherwise), then transformed and stored with plain shared-memory stores.
-            uint8_t *dstp = smem + SMEM_HEADER + (size_t)sa * a_stage_bytes + (size_t)j * lbo_a;
-            if (MODE == PRO_SUM3) {
-                // three fp32 sources per element: smaller batches (2 rows x 3 sources x 2 float4 in flight)
-                const float *x1 = reinterpret_cast<const float *>(p.x);
-                for (int rho0 = r0; rho0 < need_rows; rho0 += 2 * rstep) {
-                    float4 f[2][6];
-                    bool ok[2];
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        const int rho  = rho0 + q * rstep;
-                        const int t_in = t0 + p.tap_off0 + rho;
-                        ok[q] = rho < need_rows && t_in >= 0 && t_in < seg_len;
-                        const size_t e = (seg_row0 + (size_t)(ok[q] ? t_in : 0)) * (size_t)p.ldx + p.x_ch_off + ch;
-#pragma unroll
-                        for (int i = 0; i < 6; ++i) f[q][i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (ok[q]) {
-                            f[q][0] = *reinterpret_cast<const float4 *>(x1 + e);
-                            f[q][1] = *reinterpret_cast<const float4 *>(x1 + e + 4);
-                            f[q][2] = *reinterpret_cast<const float4 *>(p.x2 + e);
-                            f[q][3] = *reinterpret_cast<const float4 *>(p.x2 + e + 4);
-                            f[q][4] = *reinterpret_cast<const float4 *>(p.x3 + e);
-                            f[q][5] = *reinterpret_cast<const float4 *>(p.x3 + e + 4);
-                        }
-                    }
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        const int rho = rho0 + q * rstep;
-                        if (rho >= need_rows) break;
-                        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                        if (ok[q]) {
-                            const float a[8] = {f[q][0].x, f[q][0].y, f[q][0].z, f[q][0].w, f[q][1].x, f[q][1].y, f[q][1].z, f[q][1].w};
-                            const float b[8] = {f[q][2].x, f[q][2].y, f[q][2].z, f[q][2].w, f[q][3].x, f[q][3].y, f[q][3].z, f[q][3].w};
-                            const float c[8] = {f[q][4].x, f[q][4].y, f[q][4].z, f[q][4].w, f[q][5].x, f[q][5].y, f[q][5].z, f[q][5].w};
-                            float o[8];
-#pragma unroll
-                            for (int i = 0; i < 8; ++i)
-                                o[i] = lrelu_f(__fmul_rn(__fadd_rn(__fadd_rn(a[i], b[i]), c[i]), p.sum_scale), p.pro_slope);
-                            v.x = pack_half2(o[0], o[1]);
-                            v.y = pack_half2(o[2], o[3]);
-                            v.z = pack_half2(o[4], o[5]);
-                            v.w = pack_half2(o[6], o[7]);
-                        }
-                        *reinterpret_cast<uint4 *>(dstp + (size_t)rho * 16) = v;
-                    }
-                }
+            produce_chunk<MODE, N_PRODUCERS, 8>(p, tc, c, smem + SMEM_HEADER + (size_t)sa * a_stage_bytes, lbo_a, need_rows, tid);
+            if (MODE == PRO_F16) {
+                cp_async_mbar_arrive_noinc(smem_u32(a_full + sa));
             } else {
-            constexpr int UNR = 8;
-            for (int rho0 = r0; rho0 < need_rows; rho0 += UNR * rstep) {
-                float4 fa[UNR], fb[UNR];
-                uint4  hv[UNR];
-                bool   ok[UNR];
-#pragma unroll
-                for (int q = 0; q < UNR; ++q) {
-                    const int rho  = rho0 + q * rstep;
-                    const int t_in = t0 + p.tap_off0 + rho;
-                    ok[q] = rho < need_rows && t_in >= 0 && t_in < seg_len;
-                    const size_t e = (seg_row0 + (size_t)(ok[q] ? t_in : 0)) * (size_t)p.ldx + p.x_ch_off + ch;
-                    if (MODE == PRO_F16) {
-                        hv[q] = make_uint4(0u, 0u, 0u, 0u);
-                        if (ok[q]) hv[q] = *reinterpret_cast<const uint4 *>(reinterpret_cast<const __half *>(p.x) + e);
-                    } else {
-                        fa[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        fb[q] = fa[q];
-                        if (ok[q]) {
-                            const float4 *src = reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(p.x) + e);
-                            fa[q] = src[0];
-                            fb[q] = src[1];
-                        }
-                    }
-                }
-#pragma unroll
-                for (int q = 0; q < UNR; ++q) {
-                    const int rho = rho0 + q * rstep;
-                    if (rho >= need_rows) break;
-                    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                    if (MODE == PRO_F16) {
-                        v = hv[q];
-                    } else if (ok[q]) {
-                        float f[8] = {fa[q].x, fa[q].y, fa[q].z, fa[q].w, fb[q].x, fb[q].y, fb[q].z, fb[q].w};
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) f[i] = prologue_apply(MODE, f[i], p.pro_slope, pc[i]);
-                        v.x = pack_half2(f[0], f[1]);
-                        v.y = pack_half2(f[2], f[3]);
-                        v.z = pack_half2(f[4], f[5]);
-                        v.w = pack_half2(f[6], f[7]);
-                    }
-                    *reinterpret_cast<uint4 *>(dstp + (size_t)rho * 16) = v;
-                }
+                fence_proxy_async_smem();
+                mbar_arrive(smem_u32(a_full + sa));
             }
-            }
-            fence_proxy_async_smem();
-            mbar_arrive(smem_u32(a_full + sa));
         }
 
         // =================== epilogue ===================
@@ -244,67 +353,7 @@ __global__ void __launch_bounds__(128 * MT + 64) conv_umma_kernel(const ConvPara
         const bool valid = t < seg_len;
         const size_t orow = (seg_row0 + (size_t)t) * (size_t)p.out_mul + p.out_add;
         const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)mt * acc_stride;
-        for (int col = 0; col < NC; col += 16) {
-            uint32_t r[16];
-            tmem_ld16(trow + (uint32_t)col, r);
-            if (!valid) continue;
-            const int oc = nchunk * NC + col;
-            float v[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-            if (p.bias) {
-                const float4 *b4 = reinterpret_cast<const float4 *>(p.bias + oc);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float4 b = __ldg(b4 + q);
-                    v[4 * q + 0] = __fadd_rn(v[4 * q + 0], b.x);
-                    v[4 * q + 1] = __fadd_rn(v[4 * q + 1], b.y);
-                    v[4 * q + 2] = __fadd_rn(v[4 * q + 2], b.z);
-                    v[4 * q + 3] = __fadd_rn(v[4 * q + 3], b.w);
-                }
-            }
-            if (p.res) {
-                const float4 *r4 = reinterpret_cast<const float4 *>(p.res + orow * (size_t)p.ldres + p.res_ch_off + oc);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float4 b = r4[q];
-                    v[4 * q + 0] = __fadd_rn(v[4 * q + 0], b.x);
-                    v[4 * q + 1] = __fadd_rn(v[4 * q + 1], b.y);
-                    v[4 * q + 2] = __fadd_rn(v[4 * q + 2], b.z);
-                    v[4 * q + 3] = __fadd_rn(v[4 * q + 3], b.w);
-                }
-            }
-            if (p.acc_in) {
-                const float4 *r4 =
-                    reinterpret_cast<const float4 *>(p.acc_in + orow * (size_t)p.ldo32 + p.o32_ch_off + oc);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float4 b = r4[q];
-                    v[4 * q + 0] = __fadd_rn(b.x, v[4 * q + 0]);
-                    v[4 * q + 1] = __fadd_rn(b.y, v[4 * q + 1]);
-                    v[4 * q + 2] = __fadd_rn(b.z, v[4 * q + 2]);
-                    v[4 * q + 3] = __fadd_rn(b.w, v[4 * q + 3]);
-                }
-            }
-            if (p.has_scale) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = __fmul_rn(v[i], p.scale);
-            }
-            if (p.out32) {
-                float4 *o4 = reinterpret_cast<float4 *>(p.out32 + orow * (size_t)p.ldo32 + p.o32_ch_off + oc);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) o4[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-            }
-            if (p.out16) {
-                uint4 *o4 = reinterpret_cast<uint4 *>(p.out16 + orow * (size_t)p.ldo16 + p.o16_ch_off + oc);
-                uint32_t h[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    h[i] = pack_half2(lrelu_f(v[2 * i], p.out16_slope), lrelu_f(v[2 * i + 1], p.out16_slope));
-                o4[0] = make_uint4(h[0], h[1], h[2], h[3]);
-                o4[1] = make_uint4(h[4], h[5], h[6], h[7]);
-            }
-        }
+        epilogue_row(p, trow, valid, orow, nchunk, NC);
     } else if (warp == MMA_WARP) {
         // =================== MMA issuer (one elected lane of a converged warp) ===================
         const uint32_t leader = elect_one();
@@ -315,6 +364,7 @@ __global__ void __launch_bounds__(128 * MT + 64) conv_umma_kernel(const ConvPara
             const uint32_t pha = (uint32_t)(c / p.a_stages) & 1u;
             const int kc = min(KCHUNK, Cin - c * KCHUNK);
             mbar_wait(smem_u32(a_full + sa), pha, p.err_flag);
+            if (MODE == PRO_F16) fence_proxy_async_smem();    // cp.async wrote through the generic proxy
             tc_fence_after_sync();
             const uint32_t a_stage = a_base + sa * a_stage_bytes;
             for (int a = 0; a < ntaps; ++a, ++it) {
@@ -371,6 +421,190 @@ __global__ void __launch_bounds__(128 * MT + 64) conv_umma_kernel(const ConvPara
     }
 }
 
+// ------------------------------------------------------------------ persistent variant
+// Same math, different schedule: one CTA per SM loops over work items (tile, N-chunk) and the
+// roles are fully separated -- warps 0-3 produce A stages, warps 4-7 drain accumulators, warp 8
+// issues MMAs, warp 9 streams weights.  Two accumulators in tensor memory alternate, so the
+// epilogue of item i (HBM traffic: residual read, fp32 write) runs under the main loop of item
+// i+1, and with the whole shared memory for one CTA the weight ring is deep enough to cover the
+// L2 round trip of cp.async.bulk.  (Two co-resident one-tile CTAs run in lockstep and reach their
+// epilogues together; the per-launch timings in profiles/ show conv2-type launches paying their
+// whole epilogue.)
+constexpr int PK_THREADS = 320;
+
+template <int MODE>
+__global__ void __launch_bounds__(PK_THREADS, 1) conv_umma_pk_kernel(const ConvParams p, const int total_tiles, const int nchunks)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t *bars       = reinterpret_cast<uint64_t *>(smem);
+    uint64_t *a_full     = bars;                                  // [MAX_A_STAGES]
+    uint64_t *a_empty    = bars + MAX_A_STAGES;                   // [MAX_A_STAGES]
+    uint64_t *b_full     = bars + 2 * MAX_A_STAGES;               // [MAX_B_STAGES]
+    uint64_t *b_empty    = bars + 2 * MAX_A_STAGES + MAX_B_STAGES;
+    uint64_t *acc_full   = bars + 2 * MAX_A_STAGES + 2 * MAX_B_STAGES;        // [2]
+    uint64_t *acc_empty  = acc_full + 2;                                      // [2]
+    uint32_t *tmem_slot  = reinterpret_cast<uint32_t *>(smem + 248);
+
+    const int tid  = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+
+    const int Cin    = p.Cin;
+    const int NC     = p.NC;
+    const int ntaps  = p.ntaps;
+    const int kc_max = Cin < KCHUNK ? Cin : KCHUNK;
+    const int nkc    = (Cin + KCHUNK - 1) / KCHUNK;
+    const uint32_t lbo_a         = (uint32_t)p.a_rows * 16u;
+    const uint32_t a_stage_bytes = (uint32_t)(kc_max >> 3) * lbo_a;
+    const uint32_t lbo_b         = (uint32_t)NC * 16u;
+    const uint32_t b_stage_bytes = (uint32_t)kc_max * NC * 2u;
+    const uint32_t smem_base     = smem_u32(smem);
+    const uint32_t a_base        = smem_base + SMEM_HEADER;
+    const uint32_t b_base        = a_base + p.a_stages * a_stage_bytes;
+    const int total_items        = total_tiles * nchunks;
+    const uint32_t acc_stride    = (uint32_t)((NC + 31) & ~31);
+
+    auto coord = [&](int w) {
+        TileCoord tc;
+        const int tile = w / nchunks;
+        tc.nchunk  = w - tile * nchunks;
+        tc.u       = find_segment(p.tile_start, p.B, tile);
+        tc.t0      = (tile - __ldg(p.tile_start + tc.u)) * TILE_M;
+        const int seg_f0 = __ldg(p.seg_start + tc.u);
+        tc.seg_len  = (__ldg(p.seg_start + tc.u + 1) - seg_f0) * p.rate_in;
+        tc.seg_row0 = (size_t)seg_f0 * p.rate_in;
+        return tc;
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < p.a_stages; ++s) {
+            mbar_init(smem_u32(a_full + s), 128);
+            mbar_init(smem_u32(a_empty + s), 1);
+        }
+        for (int s = 0; s < p.b_stages; ++s) {
+            mbar_init(smem_u32(b_full + s), 1);
+            mbar_init(smem_u32(b_empty + s), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(smem_u32(acc_full + s), 1);
+            mbar_init(smem_u32(acc_empty + s), 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        // =================== A producers ===================
+        const int need_rows = TILE_M + (ntaps - 1) * p.tap_step;
+        int ca = 0;
+        for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+            const TileCoord tc = coord(w);
+            for (int c = 0; c < nkc; ++c, ++ca) {
+                const int sa = ca % p.a_stages;
+                const uint32_t ph = (uint32_t)(ca / p.a_stages) & 1u;
+                mbar_wait(smem_u32(a_empty + sa), ph ^ 1u, p.err_flag);
+                produce_chunk<MODE, 128, 8>(p, tc, c, smem + SMEM_HEADER + (size_t)sa * a_stage_bytes, lbo_a, need_rows, tid);
+                if (MODE == PRO_F16) {
+                    cp_async_mbar_arrive_noinc(smem_u32(a_full + sa));
+                } else {
+                    fence_proxy_async_smem();
+                    mbar_arrive(smem_u32(a_full + sa));
+                }
+            }
+        }
+    } else if (warp < 8) {
+        // =================== epilogue ===================
+        int n = 0;
+        for (int w = blockIdx.x; w < total_items; w += gridDim.x, ++n) {
+            const TileCoord tc = coord(w);
+            const int buf = n & 1;
+            mbar_wait(smem_u32(acc_full + buf), (uint32_t)(n >> 1) & 1u, p.err_flag);
+            tc_fence_after_sync();
+            const int  t     = tc.t0 + (warp & 3) * 32 + lane;
+            const bool valid = t < tc.seg_len;
+            const size_t orow = (tc.seg_row0 + (size_t)t) * (size_t)p.out_mul + p.out_add;
+            const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)buf * acc_stride;
+            epilogue_row(p, trow, valid, orow, tc.nchunk, NC);
+            tc_fence_before_sync();
+            mbar_arrive(smem_u32(acc_empty + buf));
+        }
+    } else if (warp == 8) {
+        // =================== MMA issuer ===================
+        const uint32_t leader = elect_one();
+        const uint32_t idesc = make_idesc(NC);
+        int it = 0, ca = 0, n = 0;
+        for (int w = blockIdx.x; w < total_items; w += gridDim.x, ++n) {
+            const int buf = n & 1;
+            mbar_wait(smem_u32(acc_empty + buf), ((uint32_t)(n >> 1) & 1u) ^ 1u, p.err_flag);
+            tc_fence_after_sync();
+            const uint32_t dcol = tmem_base + (uint32_t)buf * acc_stride;
+            for (int c = 0; c < nkc; ++c, ++ca) {
+                const int sa = ca % p.a_stages;
+                const uint32_t pha = (uint32_t)(ca / p.a_stages) & 1u;
+                const int kc = min(KCHUNK, Cin - c * KCHUNK);
+                mbar_wait(smem_u32(a_full + sa), pha, p.err_flag);
+                if (MODE == PRO_F16) fence_proxy_async_smem();    // cp.async wrote through the generic proxy
+                tc_fence_after_sync();
+                const uint32_t a_stage = a_base + sa * a_stage_bytes;
+                for (int a = 0; a < ntaps; ++a, ++it) {
+                    const int sb = it % p.b_stages;
+                    const uint32_t phb = (uint32_t)(it / p.b_stages) & 1u;
+                    mbar_wait(smem_u32(b_full + sb), phb, p.err_flag);
+                    tc_fence_after_sync();
+                    if (leader) {
+                        const uint32_t b_stage = b_base + sb * b_stage_bytes;
+                        const uint32_t a_tap   = a_stage + (uint32_t)(a * p.tap_step) * 16u;
+                        for (int kk = 0; kk < (kc >> 4); ++kk) {
+                            const uint64_t adesc = make_smem_desc(a_tap + (uint32_t)kk * 2u * lbo_a, lbo_a, 128u);
+                            const uint64_t bdesc = make_smem_desc(b_stage + (uint32_t)kk * 2u * lbo_b, lbo_b, 128u);
+                            umma_f16(dcol, adesc, bdesc, idesc, (c | a | kk) ? 1u : 0u);
+                        }
+                        umma_commit(smem_u32(b_empty + sb));
+                    }
+                    __syncwarp();
+                }
+                if (leader) umma_commit(smem_u32(a_empty + sa));
+                __syncwarp();
+            }
+            if (leader) umma_commit(smem_u32(acc_full + buf));
+            __syncwarp();
+        }
+    } else {
+        // =================== weight (B operand) loader ===================
+        if (lane == 0) {
+            int it = 0;
+            for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+                const int nchunk = w % nchunks;
+                const __half *wbase = p.w_packed + (size_t)nchunk * ((size_t)Cin * ntaps * NC);
+                for (int c = 0; c < nkc; ++c) {
+                    const int kc = min(KCHUNK, Cin - c * KCHUNK);
+                    const uint32_t bytes = (uint32_t)kc * NC * 2u;
+                    for (int a = 0; a < ntaps; ++a, ++it) {
+                        const int sb = it % p.b_stages;
+                        const uint32_t phb = (uint32_t)(it / p.b_stages) & 1u;
+                        mbar_wait(smem_u32(b_empty + sb), phb ^ 1u, p.err_flag);
+                        const __half *src = wbase + ((size_t)c * KCHUNK * ntaps + (size_t)a * kc) * NC;
+                        mbar_arrive_expect_tx(smem_u32(b_full + sb), bytes);
+                        bulk_copy_g2s(b_base + sb * b_stage_bytes, src, bytes, smem_u32(b_full + sb));
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after_sync();
+        tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    }
+}
+
 // ------------------------------------------------------------------ host side
 static int round_a_rows(int need_rows, int kc_max)
 {
@@ -415,6 +649,50 @@ size_t conv_umma_plan(ConvParams &p, size_t smem_budget)
     return SMEM_HEADER + as * a_stage + bs * b_stage;
 }
 
+// smem plan of the persistent kernel: the whole SM for one CTA, weight ring as deep as it fits
+size_t conv_umma_pk_plan(ConvParams &p, size_t smem_budget)
+{
+    p.mt = 1;
+    const int kc_max    = p.Cin < KCHUNK ? p.Cin : KCHUNK;
+    const int need_rows = TILE_M + (p.ntaps - 1) * p.tap_step;
+    p.a_rows            = round_a_rows(need_rows, kc_max);
+    const size_t a_stage = (size_t)(kc_max >> 3) * p.a_rows * 16;
+    const size_t b_stage = (size_t)kc_max * p.NC * 2;
+    int as = 3, bs = 2;
+    while (bs < MAX_B_STAGES && SMEM_HEADER + as * a_stage + (bs + 1) * b_stage <= smem_budget) ++bs;
+    while (as < MAX_A_STAGES && SMEM_HEADER + (as + 1) * a_stage + bs * b_stage <= smem_budget) ++as;
+    p.a_stages = as;
+    p.b_stages = bs;
+    int cols = 32;
+    while (cols < 2 * ((p.NC + 31) & ~31)) cols <<= 1;
+    p.tmem_cols = cols;
+    return SMEM_HEADER + as * a_stage + bs * b_stage;
+}
+
+template <int MODE>
+static cudaError_t launch_pk(const ConvParams &p, int total_tiles, int num_sms, size_t smem, cudaStream_t st)
+{
+    const int nchunks = p.Cout / p.NC;
+    const int items = total_tiles * nchunks;
+    const int grid = items < num_sms ? items : num_sms;
+    conv_umma_pk_kernel<MODE><<<grid, PK_THREADS, smem, st>>>(p, total_tiles, nchunks);
+    return cudaGetLastError();
+}
+
+// total_tiles counts 128-row tiles
+cudaError_t conv_umma_pk_launch(const ConvParams &p, int total_tiles, int num_sms, size_t smem, cudaStream_t st)
+{
+    switch (p.pro_mode) {
+        case PRO_F16:   return launch_pk<PRO_F16>(p, total_tiles, num_sms, smem, st);
+        case PRO_CVT:   return launch_pk<PRO_CVT>(p, total_tiles, num_sms, smem, st);
+        case PRO_LRELU: return launch_pk<PRO_LRELU>(p, total_tiles, num_sms, smem, st);
+        case PRO_NORM:  return launch_pk<PRO_NORM>(p, total_tiles, num_sms, smem, st);
+        case PRO_MEL:   return launch_pk<PRO_MEL>(p, total_tiles, num_sms, smem, st);
+        case PRO_SUM3:  return launch_pk<PRO_SUM3>(p, total_tiles, num_sms, smem, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
 template <int MODE, int MT>
 static cudaError_t launch_mode(const ConvParams &p, int total_tiles, size_t smem, cudaStream_t st)
 {
@@ -428,6 +706,7 @@ static cudaError_t init_mode()
 {
     cudaError_t e;
     const int kMax = 227 * 1024;
+    if ((e = cudaFuncSetAttribute(conv_umma_pk_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(conv_umma_kernel<MODE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax)) != cudaSuccess) return e;
     return cudaFuncSetAttribute(conv_umma_kernel<MODE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
 }

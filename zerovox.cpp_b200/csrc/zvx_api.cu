@@ -95,6 +95,7 @@ struct zvx_ctx {
     int fused_prefetch = 1;
     int fused_persistent = 1;
     int fused_flags = 0;
+    int conv_persistent = 1;
     int conv_mt2 = 0;   // two M-tiles per CTA: measured slower on B200 while the A producer is the limit (profiles/)
     std::vector<int> tile256_cfg;                 // per rate index: wincfg entry of the 256-row tiling
     int num_sms = 148;
@@ -113,7 +114,7 @@ struct zvx_ctx {
     float *v0 = nullptr, *U = nullptr, *CS = nullptr, *Y1 = nullptr, *VA = nullptr, *VB = nullptr, *T2 = nullptr, *wav = nullptr;
     int branch_sum_in_consumer = 1;               // fused stages: write the 3 branch outputs, the next kernel sums them
     int stage_is_split[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // set per run: stage i's output lives in CS/VA/VB (3 buffers)
-    __half *H16 = nullptr, *X16 = nullptr;       // X16: decoder conv operand (normalised, activated, fp16)
+    __half *H16 = nullptr, *X16 = nullptr, *R16 = nullptr;   // X16: decoder conv operand (normalised, activated, fp16); R16: raw input as fp16
     int dec_prepass = 1;
     int *d_seg = nullptr;                         // [B+1] frames prefix
     int *d_tiles = nullptr;                       // [nrates][B+1] tile prefixes
@@ -594,9 +595,10 @@ int reserve(zvx_ctx *ctx, int64_t frames, int batch)
         for (float **b : bufs) { dev_free(ctx, *b); *b = nullptr; }
         dev_free(ctx, ctx->H16); ctx->H16 = nullptr;
         dev_free(ctx, ctx->X16); ctx->X16 = nullptr;
+        dev_free(ctx, ctx->R16); ctx->R16 = nullptr;
         const int D = c.dim_in, BN = 2 * D, R = c.residual_dim;
         if (c.with_decoder) {
-            if (dev_alloc(ctx, &ctx->X16, F * (BN + R))) return 1;
+            if (dev_alloc(ctx, &ctx->X16, F * (BN + R)) || dev_alloc(ctx, &ctx->R16, F * (BN + R))) return 1;
             if (dev_alloc(ctx, &ctx->enc_in, F * D) || dev_alloc(ctx, &ctx->sc, F * BN) || dev_alloc(ctx, &ctx->h528, F * D) ||
                 dev_alloc(ctx, &ctx->e0, F * BN) || dev_alloc(ctx, &ctx->h1056, F * BN) || dev_alloc(ctx, &ctx->catA, F * (BN + R)) ||
                 dev_alloc(ctx, &ctx->catB, F * (BN + R)) || dev_alloc(ctx, &ctx->asr, F * R) || dev_alloc(ctx, &ctx->d1, F * D) ||
@@ -753,9 +755,18 @@ int run_conv(zvx_ctx *ctx, const ConvCall &cc)
     if (ctx->use_ref_kernels) {
         CK(ctx, conv_ref_launch(p, tiles, ctx->stream));
     } else {
-        const size_t smem = conv_umma_plan(p, p.mt == 2 ? 226 * 1024 : 100 * 1024);
-        if (smem > 227 * 1024) return fail(ctx, "conv needs %zu bytes of shared memory", smem);
-        CK(ctx, conv_umma_launch(p, tiles, smem, ctx->stream));
+        // persistent kernel whenever there are at least ~2 work items per SM, else one tile per CTA
+        // (measured per launch kind, profiles/: it wins on the MRF convs -- long K loops, residual-stream
+        // epilogue -- and loses on the short decoder / up-conv launches)
+        if (ctx->conv_persistent && cc.kind == ZVX_K_MRF_CONV && p.mt == 1 && (int64_t)tiles * (L.OC / L.NC) >= (int64_t)2 * ctx->num_sms) {
+            const size_t smem = conv_umma_pk_plan(p, 226 * 1024);
+            if (smem > 227 * 1024) return fail(ctx, "conv needs %zu bytes of shared memory", smem);
+            CK(ctx, conv_umma_pk_launch(p, tiles, ctx->num_sms, smem, ctx->stream));
+        } else {
+            const size_t smem = conv_umma_plan(p, p.mt == 2 ? 226 * 1024 : 100 * 1024);
+            if (smem > 227 * 1024) return fail(ctx, "conv needs %zu bytes of shared memory", smem);
+            CK(ctx, conv_umma_launch(p, tiles, smem, ctx->stream));
+        }
     }
     return prof_end(ctx);
 }
@@ -784,6 +795,22 @@ int run_norm_conv(zvx_ctx *ctx, ConvCall cc)
     return run_conv(ctx, cc);
 }
 
+// fp32 -> fp16 copy of a conv input that is used raw (1x1 shortcuts, asr_res, to_out); returns the
+// ConvCall rewritten to read it (PRO_F16).  `fresh` = false reuses the copy made by the previous call.
+int use_raw_f16(zvx_ctx *ctx, ConvCall &cc, bool fresh)
+{
+    if (!ctx->dec_prepass || ctx->use_ref_kernels || cc.pro_mode != PRO_CVT) return 0;
+    const int C = cc.L->IC;
+    if (fresh) {
+        ctx->launches++;
+        if (prof_begin(ctx, ZVX_K_NORM_AFFINE, 0, 0.0, 6.0 * (double)ctx->last_frames * C)) return 1;
+        CK(ctx, cvt_f16_launch(reinterpret_cast<const float *>(cc.x), cc.ldx, cc.x_ch_off, C, (size_t)ctx->last_frames, ctx->R16, ctx->stream));
+        if (prof_end(ctx)) return 1;
+    }
+    cc.x = ctx->R16; cc.ldx = C; cc.x_ch_off = 0; cc.pro_mode = PRO_F16;
+    return 0;
+}
+
 // ---------------------------------------------------------------- decoder schedule
 // enc_in [F][D] and style [B][S] are already on the device.
 int run_decoder(zvx_ctx *ctx, float *mel_out)
@@ -810,6 +837,7 @@ int run_decoder(zvx_ctx *ctx, float *mel_out)
         if (b.learned_sc) {
             ConvCall s; s.L = &b.conv1x1; s.x = x; s.ldx = ldx; s.pro_mode = PRO_CVT; s.use_bias = false;
             s.out32 = ctx->sc; s.ldo32 = b.cout;
+            if (use_raw_f16(ctx, s, true)) return 1;     // i == 0: x is enc_in; the copy is reused by asr_res below
             if (run_conv(ctx, s)) return 1;
             sc = ctx->sc; ldsc = b.cout;
         }
@@ -829,6 +857,7 @@ int run_decoder(zvx_ctx *ctx, float *mel_out)
     // ---- asr_res = IN_affine(conv1x1(enc_seq) + b)  (stylettsdec.cpp:382-396), into both concat buffers ----
     {
         ConvCall a; a.L = &ctx->asr0; a.x = ctx->enc_in; a.ldx = D; a.pro_mode = PRO_CVT; a.out32 = ctx->asr; a.ldo32 = R;
+        if (use_raw_f16(ctx, a, !ctx->enc[0].learned_sc)) return 1;   // enc_in was converted for encode.0's shortcut
         if (run_conv(ctx, a)) return 1;
         if (run_stats(ctx, ctx->asr, R, 0, R)) return 1;
         ctx->launches++;
@@ -856,6 +885,7 @@ int run_decoder(zvx_ctx *ctx, float *mel_out)
         if (b.learned_sc) {
             ConvCall s; s.L = &b.conv1x1; s.x = din[i]; s.ldx = dinl[i]; s.pro_mode = PRO_CVT; s.use_bias = false;
             s.out32 = ctx->sc; s.ldo32 = b.cout;
+            if (use_raw_f16(ctx, s, true)) return 1;
             if (run_conv(ctx, s)) return 1;
             sc = ctx->sc; ldsc = b.cout;
         }
@@ -1093,6 +1123,7 @@ int zvx_create(zvx_ctx **out, const zvx_config *cfg, const zvx_tensor_desc *weig
     if (const char *e = getenv("ZVX_DEC_PREPASS")) ctx->dec_prepass = atoi(e);
     if (const char *e = getenv("ZVX_BRANCH_SUM_IN_CONSUMER")) ctx->branch_sum_in_consumer = atoi(e);
     if (const char *e = getenv("ZVX_CONV_MT2")) ctx->conv_mt2 = atoi(e);
+    if (const char *e = getenv("ZVX_CONV_PERSISTENT")) ctx->conv_persistent = atoi(e);
     if (const char *e = getenv("ZVX_FUSED_UPCONV")) ctx->use_fused_upconv = atoi(e);
     ctx->num_sms = prop.multiProcessorCount;
     auto bail = [&](void) { g_create_error = ctx->err; zvx_destroy(ctx); return 1; };

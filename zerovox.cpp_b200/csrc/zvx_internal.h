@@ -15,6 +15,9 @@ namespace zvx {
 size_t      conv_umma_plan(ConvParams &p, size_t smem_budget);
 cudaError_t conv_umma_init();   // once per device: opt in to > 48 KB dynamic smem
 cudaError_t conv_umma_launch(const ConvParams &p, int total_tiles, size_t smem, cudaStream_t st);
+// persistent, fully warp-specialised variant (one CTA per SM, double-buffered accumulators)
+size_t      conv_umma_pk_plan(ConvParams &p, size_t smem_budget);
+cudaError_t conv_umma_pk_launch(const ConvParams &p, int total_tiles, int num_sms, size_t smem, cudaStream_t st);
 
 // conv_ref.cu (validation kernel: plain CUDA cores, same prologue/epilogue arithmetic) ---
 cudaError_t conv_ref_launch(const ConvParams &p, int total_tiles, cudaStream_t st);
@@ -53,6 +56,8 @@ cudaError_t norm_affine_launch(const float *x, int ldx, int C, const int *seg_st
 cudaError_t norm_act_f16_launch(const float *x, int ldx, int ch_off, int C, const int *seg_start, int B, int max_len,
                                 const float *mu, const float *rstd, const float *g, const float *b, int gb_stride, float slope,
                                 __half *y16, cudaStream_t st);
+
+cudaError_t cvt_f16_launch(const float *x, int ldx, int ch_off, int C, size_t rows, __half *y16, cudaStream_t st);
 
 // wav = tanh(conv_k(leaky_relu(x, slope)) + b), single output channel
 // w_host_kc: host copy of the weights as fp32 [K][C] (constant-bank fast path for C = 32, K = 7), may be null
