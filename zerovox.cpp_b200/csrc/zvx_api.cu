@@ -66,6 +66,9 @@ struct zvx_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     int64_t launches = 0;
+    zvx_ctx *lane = nullptr;             // second stream + workspace sharing this context's weights (zvx_synth_batch pipelining)
+    bool is_lane = false;
+    int e2e_chunks = 2;
     int use_ref_kernels = 0;
     int debug_stop = -1;
 
@@ -1054,6 +1057,41 @@ int ensure_pinned(zvx_ctx *ctx, float **buf, size_t *cap, size_t n)
 
 }  // namespace
 
+// A lane borrows the weights (device pointers) of its parent and owns only a stream, the utterance
+// tables and a workspace: zvx_synth_batch alternates sub-batches between the context and its lane so
+// that the H2D / D2H copies of one sub-batch run under the kernels of the other.
+int make_lane(zvx_ctx *parent)
+{
+    if (parent->lane) return 0;
+    zvx_ctx *l = new zvx_ctx(*parent);
+    l->is_lane = true;
+    l->lane = nullptr;
+    l->owned.clear();
+    l->stream = nullptr;
+    l->tables_event = nullptr;
+    l->tables_pending = false;
+    l->launches = 0;
+    l->prof = false;
+    l->ev_pool.clear();
+    l->ev_used = 0;
+    l->prof_entries.clear();
+    l->cap_frames = 0;
+    l->cap_batch = 0;
+    float **fp[] = {&l->enc_in, &l->sc, &l->h528, &l->e0, &l->h1056, &l->catA, &l->catB, &l->asr, &l->d1, &l->d2, &l->mel, &l->style,
+                    &l->mu, &l->rstd, &l->adain_gb, &l->v0, &l->U, &l->CS, &l->Y1, &l->VA, &l->VB, &l->T2, &l->wav, &l->pin_in, &l->pin_out};
+    for (float **q : fp) *q = nullptr;
+    l->H16 = l->X16 = l->R16 = nullptr;
+    l->d_seg = l->d_tiles = l->d_wins = l->d_err = l->pin_tables = nullptr;
+    l->pin_in_cap = l->pin_out_cap = 0;
+    parent->lane = l;
+    zvx_ctx *ctx = parent;   // error reporting goes to the parent
+    CK(ctx, cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking));
+    CK(ctx, cudaEventCreateWithFlags(&l->tables_event, cudaEventDisableTiming));
+    if (dev_alloc(l, &l->d_err, 1)) { ctx->err = l->err; return 1; }
+    CK(ctx, cudaMemset(l->d_err, 0, sizeof(int)));
+    return 0;
+}
+
 // ====================================================================== C ABI
 extern "C" {
 
@@ -1087,6 +1125,7 @@ void zvx_destroy(zvx_ctx *ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    if (ctx->lane) { zvx_destroy(ctx->lane); ctx->lane = nullptr; }
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (void *p : ctx->owned) cudaFree(p);
     if (ctx->pin_tables) cudaFreeHost(ctx->pin_tables);
@@ -1120,6 +1159,7 @@ int zvx_create(zvx_ctx **out, const zvx_config *cfg, const zvx_tensor_desc *weig
     if (const char *e = getenv("ZVX_FUSED_PREFETCH")) ctx->fused_prefetch = atoi(e);
     if (const char *e = getenv("ZVX_FUSED_PERSISTENT")) ctx->fused_persistent = atoi(e);
     if (const char *e = getenv("ZVX_FUSED_FLAGS")) ctx->fused_flags = atoi(e);
+    if (const char *e = getenv("ZVX_E2E_CHUNKS")) ctx->e2e_chunks = std::max(1, atoi(e));
     if (const char *e = getenv("ZVX_DEC_PREPASS")) ctx->dec_prepass = atoi(e);
     if (const char *e = getenv("ZVX_BRANCH_SUM_IN_CONSUMER")) ctx->branch_sum_in_consumer = atoi(e);
     if (const char *e = getenv("ZVX_CONV_MT2")) ctx->conv_mt2 = atoi(e);
@@ -1195,7 +1235,7 @@ int zvx_synchronize(zvx_ctx *ctx)
     return check_device_error(ctx);
 }
 
-int64_t zvx_kernel_launches(const zvx_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int64_t zvx_kernel_launches(const zvx_ctx *ctx) { return ctx ? ctx->launches + (ctx->lane ? ctx->lane->launches : 0) : 0; }
 
 int zvx_reserve(zvx_ctx *ctx, int64_t total_frames, int32_t max_batch)
 {
@@ -1271,32 +1311,80 @@ int zvx_vocode_batch_device(zvx_ctx *ctx, int32_t B, const float *d_mel, const i
     return sync ? check_device_error(ctx) : 0;
 }
 
+// one sub-batch [b0, b1) of zvx_synth_batch on context / lane `c`, everything asynchronous on c->stream
+static int synth_chunk(zvx_ctx *c, int b0, int b1, const float *const *enc_seq, const float *const *style, const int32_t *L,
+                       float *const *mel, float *const *wav)
+{
+    zvx_ctx *ctx = c;
+    const zvx_config &cfg = c->cfg;
+    const int n = b1 - b0;
+    if (set_batch(c, n, L + b0)) return 1;
+    for (int b = 0; b < n; ++b) {
+        CK(ctx, cudaMemcpyAsync(c->enc_in + (size_t)c->h_seg[b] * cfg.dim_in, enc_seq[b0 + b], sizeof(float) * (size_t)L[b0 + b] * cfg.dim_in,
+                                cudaMemcpyHostToDevice, c->stream));
+        CK(ctx, cudaMemcpyAsync(c->style + (size_t)b * cfg.style_dim, style[b0 + b], sizeof(float) * cfg.style_dim, cudaMemcpyHostToDevice,
+                                c->stream));
+    }
+    if (run_decoder(c, c->mel)) return 1;
+    if (run_vocoder(c, c->mel, c->wav)) return 1;
+    for (int b = 0; b < n; ++b) {
+        if (mel && mel[b0 + b])
+            CK(ctx, cudaMemcpyAsync(mel[b0 + b], c->mel + (size_t)c->h_seg[b] * cfg.num_mels, sizeof(float) * (size_t)L[b0 + b] * cfg.num_mels,
+                                    cudaMemcpyDeviceToHost, c->stream));
+        CK(ctx, cudaMemcpyAsync(wav[b0 + b], c->wav + (size_t)c->h_seg[b] * cfg.hop_size, sizeof(float) * (size_t)L[b0 + b] * cfg.hop_size,
+                                cudaMemcpyDeviceToHost, c->stream));
+    }
+    return 0;
+}
+
 int zvx_synth_batch(zvx_ctx *ctx, int32_t B, const float *const *enc_seq, const float *const *style, const int32_t *L,
                     float *const *mel, float *const *wav)
 {
     if (!ctx) return 1;
     if (!ctx->cfg.with_decoder || !ctx->cfg.with_vocoder) return fail(ctx, "context was built without decoder or vocoder");
     if (!enc_seq || !style || !L || !wav) return fail(ctx, "zvx_synth_batch: null argument");
+    if (B <= 0) return fail(ctx, "empty batch");
     CK(ctx, cudaSetDevice(ctx->device));
-    if (set_batch(ctx, B, L)) return 1;
-    const zvx_config &c = ctx->cfg;
-    const int64_t F = ctx->last_frames;
+    int64_t frames = 0;
     for (int b = 0; b < B; ++b) {
-        CK(ctx, cudaMemcpyAsync(ctx->enc_in + (size_t)ctx->h_seg[b] * c.dim_in, enc_seq[b], sizeof(float) * (size_t)L[b] * c.dim_in,
-                                cudaMemcpyHostToDevice, ctx->stream));
-        CK(ctx, cudaMemcpyAsync(ctx->style + (size_t)b * c.style_dim, style[b], sizeof(float) * c.style_dim, cudaMemcpyHostToDevice,
-                                ctx->stream));
+        if (L[b] <= 0) return fail(ctx, "utterance %d has non-positive length %d", b, L[b]);
+        frames += L[b];
     }
-    if (run_decoder(ctx, ctx->mel)) return 1;
-    if (run_vocoder(ctx, ctx->mel, ctx->wav)) return 1;
+    // Large batches are cut into a few sub-batches that alternate between this context and its lane
+    // (own stream + workspace, shared weights): the PCIe copies of one sub-batch overlap the kernels of
+    // the other.  Utterances are independent, so the result does not depend on the cut.
+    int nch = ctx->e2e_chunks;
+    if (ctx->prof || ctx->debug_stop >= 0 || B < 2 * nch || frames < 4096) nch = 1;
+    if (nch == 1) {
+        if (synth_chunk(ctx, 0, B, enc_seq, style, L, mel, wav)) return 1;
+        return check_device_error(ctx);
+    }
+    if (make_lane(ctx)) return 1;
+    ctx->lane->use_ref_kernels = ctx->use_ref_kernels;
+    ctx->lane->use_fused = ctx->use_fused;
+    // cut points with roughly equal frame counts
+    std::vector<int> cut(1, 0);
+    int64_t acc = 0;
     for (int b = 0; b < B; ++b) {
-        if (mel && mel[b])
-            CK(ctx, cudaMemcpyAsync(mel[b], ctx->mel + (size_t)ctx->h_seg[b] * c.num_mels, sizeof(float) * (size_t)L[b] * c.num_mels,
-                                    cudaMemcpyDeviceToHost, ctx->stream));
-        CK(ctx, cudaMemcpyAsync(wav[b], ctx->wav + (size_t)ctx->h_seg[b] * c.hop_size, sizeof(float) * (size_t)L[b] * c.hop_size,
-                                cudaMemcpyDeviceToHost, ctx->stream));
+        acc += L[b];
+        if ((int)cut.size() < nch && acc * nch >= frames * (int64_t)cut.size() && b + 1 < B) cut.push_back(b + 1);
     }
-    (void)F;
+    cut.push_back(B);
+    // size both workspaces once for the largest sub-batch (a growing reserve() would have to synchronise)
+    int64_t maxf = 0; int maxb = 0;
+    for (size_t q = 0; q + 1 < cut.size(); ++q) {
+        int64_t f = 0;
+        for (int b = cut[q]; b < cut[q + 1]; ++b) f += L[b];
+        maxf = std::max(maxf, f);
+        maxb = std::max(maxb, cut[q + 1] - cut[q]);
+    }
+    if (reserve(ctx, maxf, maxb)) return 1;
+    if (reserve(ctx->lane, maxf, maxb)) { ctx->err = ctx->lane->err; return 1; }
+    for (size_t q = 0; q + 1 < cut.size(); ++q) {
+        zvx_ctx *c = (q & 1) ? ctx->lane : ctx;
+        if (synth_chunk(c, cut[q], cut[q + 1], enc_seq, style, L, mel, wav)) { if (c != ctx) ctx->err = c->err; return 1; }
+    }
+    if (check_device_error(ctx->lane)) { ctx->err = ctx->lane->err; return 1; }
     return check_device_error(ctx);
 }
 
