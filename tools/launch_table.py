@@ -9,7 +9,7 @@ from zerovox_cpp_b200 import capi
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 gguf = zvx.synth.write_model(zvx.synth.default_model_path())
 ctx = capi.Context.from_gguf(gguf, device=0)
-lengths = zvx.synth.batch_lengths(B, seed=11)
+lengths = zvx.synth.batch_lengths(B, seed=11) if len(sys.argv) < 3 else __import__("numpy").full(B, int(sys.argv[2]), dtype="int32")
 F = int(lengths.sum())
 Larr = (ctypes.c_int32 * B)(*[int(x) for x in lengths])
 ctx.reserve(F, B)

@@ -572,7 +572,7 @@ int reserve(zvx_ctx *ctx, int64_t frames, int batch)
 {
     const zvx_config &c = ctx->cfg;
     if (batch > ctx->cap_batch) {
-        const int nb = std::max(batch, 64);
+        const int nb = std::max(std::max(batch, 64), 2 * ctx->cap_batch);   // grow geometrically: every growth reallocates
         const int nr = (int)std::max<size_t>(ctx->rates.size(), 1);
         const int nw = (int)std::max<size_t>(ctx->wincfg.size(), 1);
         dev_free(ctx, ctx->d_seg); dev_free(ctx, ctx->d_tiles); dev_free(ctx, ctx->d_wins); dev_free(ctx, ctx->mu); dev_free(ctx, ctx->rstd);
@@ -1319,21 +1319,34 @@ static int synth_chunk(zvx_ctx *c, int b0, int b1, const float *const *enc_seq, 
     const zvx_config &cfg = c->cfg;
     const int n = b1 - b0;
     if (set_batch(c, n, L + b0)) return 1;
-    for (int b = 0; b < n; ++b) {
-        CK(ctx, cudaMemcpyAsync(c->enc_in + (size_t)c->h_seg[b] * cfg.dim_in, enc_seq[b0 + b], sizeof(float) * (size_t)L[b0 + b] * cfg.dim_in,
+    // one copy per run of utterances whose host buffers are contiguous (the common packed layout)
+    for (int b = 0; b < n;) {
+        int e = b + 1;
+        while (e < n && enc_seq[b0 + e] == enc_seq[b0 + e - 1] + (size_t)L[b0 + e - 1] * cfg.dim_in) ++e;
+        CK(ctx, cudaMemcpyAsync(c->enc_in + (size_t)c->h_seg[b] * cfg.dim_in, enc_seq[b0 + b],
+                                sizeof(float) * (size_t)(c->h_seg[e] - c->h_seg[b]) * cfg.dim_in, cudaMemcpyHostToDevice, c->stream));
+        b = e;
+    }
+    for (int b = 0; b < n;) {
+        int e = b + 1;
+        while (e < n && style[b0 + e] == style[b0 + e - 1] + cfg.style_dim) ++e;
+        CK(ctx, cudaMemcpyAsync(c->style + (size_t)b * cfg.style_dim, style[b0 + b], sizeof(float) * (size_t)(e - b) * cfg.style_dim,
                                 cudaMemcpyHostToDevice, c->stream));
-        CK(ctx, cudaMemcpyAsync(c->style + (size_t)b * cfg.style_dim, style[b0 + b], sizeof(float) * cfg.style_dim, cudaMemcpyHostToDevice,
-                                c->stream));
+        b = e;
     }
     if (run_decoder(c, c->mel)) return 1;
     if (run_vocoder(c, c->mel, c->wav)) return 1;
-    for (int b = 0; b < n; ++b) {
+    for (int b = 0; b < n;) {
+        int e = b + 1;
+        while (e < n && wav[b0 + e] == wav[b0 + e - 1] + (size_t)L[b0 + e - 1] * cfg.hop_size) ++e;
+        CK(ctx, cudaMemcpyAsync(wav[b0 + b], c->wav + (size_t)c->h_seg[b] * cfg.hop_size,
+                                sizeof(float) * (size_t)(c->h_seg[e] - c->h_seg[b]) * cfg.hop_size, cudaMemcpyDeviceToHost, c->stream));
+        b = e;
+    }
+    for (int b = 0; b < n; ++b)
         if (mel && mel[b0 + b])
             CK(ctx, cudaMemcpyAsync(mel[b0 + b], c->mel + (size_t)c->h_seg[b] * cfg.num_mels, sizeof(float) * (size_t)L[b0 + b] * cfg.num_mels,
                                     cudaMemcpyDeviceToHost, c->stream));
-        CK(ctx, cudaMemcpyAsync(wav[b0 + b], c->wav + (size_t)c->h_seg[b] * cfg.hop_size, sizeof(float) * (size_t)L[b0 + b] * cfg.hop_size,
-                                cudaMemcpyDeviceToHost, c->stream));
-    }
     return 0;
 }
 
