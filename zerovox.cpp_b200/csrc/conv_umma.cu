@@ -199,70 +199,76 @@ __device__ __forceinline__ void produce_chunk(const ConvParams &p, const TileCoo
     }
 }
 
-// Drain one accumulator row (thread = output time step) from tensor memory and apply the fused
-// epilogue: bias, residual, branch sum, scale; fp32 and / or fp16(leaky-ReLU) outputs.
-__device__ __forceinline__ void epilogue_row(const ConvParams &p, uint32_t trow, bool valid, size_t orow, int nchunk, int NC)
+// Epilogue of one warp = 32 accumulator rows (time steps) x NC columns.  tcgen05.ld hands every
+// thread one ROW; writing rows from there costs 32 cache lines per warp instruction (measured:
+// the epilogue took 45 % of a CTA's lifetime on the decoder convs, profiles/r01_ncu_conv_*).  So the
+// warp transposes through a private shared-memory slab, 64 columns at a time: afterwards a half-warp
+// owns 256 contiguous bytes of one row and every global access (residual / branch-sum reads, fp32
+// and fp16 writes) is a full-line transaction.  Residual loads of 4 row pairs are issued before use.
+// Fused math, unchanged: ((acc + bias) + residual) + acc_in, times scale; fp16 copy with leaky-ReLU.
+constexpr int EPI_COLS   = 64;
+constexpr int SLAB_LD    = EPI_COLS + 4;               // floats; +4 keeps the row-wise 16-byte stores conflict-free
+constexpr int SLAB_BYTES = 32 * SLAB_LD * 4;
+
+__device__ __forceinline__ float4 f4_add(float4 a, float4 b)
 {
-    for (int col = 0; col < NC; col += 16) {
-        uint32_t r[16];
-        tmem_ld16(trow + (uint32_t)col, r);
-        if (!valid) continue;
-        const int oc = nchunk * NC + col;
-        float v[16];
+    return make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z), __fadd_rn(a.w, b.w));
+}
+
+__device__ __forceinline__ void epilogue_tile(const ConvParams &p, uint32_t trow, float *slab, int lane, int t_first, int seg_len,
+                                              size_t seg_row0, int nchunk, int NC)
+{
+    const int cl   = (lane & 15) * 4;       // this lane's 4 columns inside the 64-column pass
+    const int rsel = lane >> 4;             // which row of a row pair
+    for (int col0 = 0; col0 < NC; col0 += EPI_COLS) {
+        const int cw = min(EPI_COLS, NC - col0);
+        for (int cc = 0; cc < cw; cc += 16) {
+            uint32_t r[16];
+            tmem_ld16(trow + (uint32_t)(col0 + cc), r);
+            float4 *d = reinterpret_cast<float4 *>(slab + lane * SLAB_LD + cc);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-        if (p.bias) {
-            const float4 *b4 = reinterpret_cast<const float4 *>(p.bias + oc);
+            for (int q = 0; q < 4; ++q)
+                d[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+                                   __uint_as_float(r[4 * q + 3]));
+        }
+        __syncwarp();
+        if (cl < cw) {
+            const int oc = nchunk * NC + col0 + cl;
+            float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias) bias = __ldg(reinterpret_cast<const float4 *>(p.bias + oc));
+            for (int rb = 0; rb < 32; rb += 8) {
+                float4 rs[4], ai[4];
+                size_t orow[4];
+                bool ok[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float4 b = __ldg(b4 + q);
-                v[4 * q + 0] = __fadd_rn(v[4 * q + 0], b.x);
-                v[4 * q + 1] = __fadd_rn(v[4 * q + 1], b.y);
-                v[4 * q + 2] = __fadd_rn(v[4 * q + 2], b.z);
-                v[4 * q + 3] = __fadd_rn(v[4 * q + 3], b.w);
+                for (int q = 0; q < 4; ++q) {
+                    const int t = t_first + rb + 2 * q + rsel;
+                    ok[q]   = t < seg_len;
+                    orow[q] = (seg_row0 + (size_t)t) * (size_t)p.out_mul + p.out_add;
+                    rs[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    ai[q] = rs[q];
+                    if (ok[q] && p.res) rs[q] = *reinterpret_cast<const float4 *>(p.res + orow[q] * (size_t)p.ldres + p.res_ch_off + oc);
+                    if (ok[q] && p.acc_in) ai[q] = *reinterpret_cast<const float4 *>(p.acc_in + orow[q] * (size_t)p.ldo32 + p.o32_ch_off + oc);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (!ok[q]) continue;
+                    float4 v = *reinterpret_cast<const float4 *>(slab + (rb + 2 * q + rsel) * SLAB_LD + cl);
+                    if (p.bias) v = f4_add(v, bias);
+                    if (p.res) v = f4_add(v, rs[q]);
+                    if (p.acc_in) v = f4_add(ai[q], v);
+                    if (p.has_scale) v = make_float4(__fmul_rn(v.x, p.scale), __fmul_rn(v.y, p.scale), __fmul_rn(v.z, p.scale), __fmul_rn(v.w, p.scale));
+                    if (p.out32) *reinterpret_cast<float4 *>(p.out32 + orow[q] * (size_t)p.ldo32 + p.o32_ch_off + oc) = v;
+                    if (p.out16) {
+                        uint2 h;
+                        h.x = pack_half2(lrelu_f(v.x, p.out16_slope), lrelu_f(v.y, p.out16_slope));
+                        h.y = pack_half2(lrelu_f(v.z, p.out16_slope), lrelu_f(v.w, p.out16_slope));
+                        *reinterpret_cast<uint2 *>(p.out16 + orow[q] * (size_t)p.ldo16 + p.o16_ch_off + oc) = h;
+                    }
+                }
             }
         }
-        if (p.res) {
-            const float4 *r4 = reinterpret_cast<const float4 *>(p.res + orow * (size_t)p.ldres + p.res_ch_off + oc);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float4 b = r4[q];
-                v[4 * q + 0] = __fadd_rn(v[4 * q + 0], b.x);
-                v[4 * q + 1] = __fadd_rn(v[4 * q + 1], b.y);
-                v[4 * q + 2] = __fadd_rn(v[4 * q + 2], b.z);
-                v[4 * q + 3] = __fadd_rn(v[4 * q + 3], b.w);
-            }
-        }
-        if (p.acc_in) {
-            const float4 *r4 =
-                reinterpret_cast<const float4 *>(p.acc_in + orow * (size_t)p.ldo32 + p.o32_ch_off + oc);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float4 b = r4[q];
-                v[4 * q + 0] = __fadd_rn(b.x, v[4 * q + 0]);
-                v[4 * q + 1] = __fadd_rn(b.y, v[4 * q + 1]);
-                v[4 * q + 2] = __fadd_rn(b.z, v[4 * q + 2]);
-                v[4 * q + 3] = __fadd_rn(b.w, v[4 * q + 3]);
-            }
-        }
-        if (p.has_scale) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = __fmul_rn(v[i], p.scale);
-        }
-        if (p.out32) {
-            float4 *o4 = reinterpret_cast<float4 *>(p.out32 + orow * (size_t)p.ldo32 + p.o32_ch_off + oc);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) o4[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        }
-        if (p.out16) {
-            uint4 *o4 = reinterpret_cast<uint4 *>(p.out16 + orow * (size_t)p.ldo16 + p.o16_ch_off + oc);
-            uint32_t h[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                h[i] = pack_half2(lrelu_f(v[2 * i], p.out16_slope), lrelu_f(v[2 * i + 1], p.out16_slope));
-            o4[0] = make_uint4(h[0], h[1], h[2], h[3]);
-            o4[1] = make_uint4(h[4], h[5], h[6], h[7]);
-        }
+        __syncwarp();
     }
 }
 
@@ -331,82 +337,88 @@ __global__ void __launch_bounds__(128 * MT + 64) conv_umma_kernel(const ConvPara
     if (warp < MMA_WARP) {
         // =================== A producers ===================
         const int need_rows = ROWS_CTA + (ntaps - 1) * p.tap_step;
-        for (int c = 0; c < nkc; ++c) {
-            const int sa = c % p.a_stages;
-            const uint32_t ph = (uint32_t)(c / p.a_stages) & 1u;
-            mbar_wait(smem_u32(a_empty + sa), ph ^ 1u, p.err_flag);
-
-            produce_chunk<MODE, N_PRODUCERS, 8>(p, tc, c, smem + SMEM_HEADER + (size_t)sa * a_stage_bytes, lbo_a, need_rows, tid);
-            if (MODE == PRO_F16) {
-                cp_async_mbar_arrive_noinc(smem_u32(a_full + sa));
-            } else {
-                fence_proxy_async_smem();
-                mbar_arrive(smem_u32(a_full + sa));
+        {
+            int sa = 0;
+            uint32_t ph = 0;
+            for (int c = 0; c < nkc; ++c) {
+                mbar_wait(smem_u32(a_empty + sa), ph ^ 1u, p.err_flag);
+                produce_chunk<MODE, N_PRODUCERS, 8>(p, tc, c, smem + SMEM_HEADER + (size_t)sa * a_stage_bytes, lbo_a, need_rows, tid);
+                if (MODE == PRO_F16) {
+                    cp_async_mbar_arrive_noinc(smem_u32(a_full + sa));
+                } else {
+                    fence_proxy_async_smem();
+                    mbar_arrive(smem_u32(a_full + sa));
+                }
+                if (++sa == p.a_stages) { sa = 0; ph ^= 1u; }
             }
         }
 
         // =================== epilogue ===================
         mbar_wait(smem_u32(acc_full), 0u, p.err_flag);
         tc_fence_after_sync();
+        // every MMA has completed (acc_full), so the operand stages are dead: their memory is the slab
         const int  mt    = warp >> 2;                       // M-tile this warp drains
-        const int  t     = t0 + mt * TILE_M + (warp & 3) * 32 + lane;
-        const bool valid = t < seg_len;
-        const size_t orow = (seg_row0 + (size_t)t) * (size_t)p.out_mul + p.out_add;
         const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)mt * acc_stride;
-        epilogue_row(p, trow, valid, orow, nchunk, NC);
+        epilogue_tile(p, trow, reinterpret_cast<float *>(smem + SMEM_HEADER + (size_t)warp * SLAB_BYTES), lane,
+                      t0 + mt * TILE_M + (warp & 3) * 32, seg_len, seg_row0, nchunk, NC);
     } else if (warp == MMA_WARP) {
         // =================== MMA issuer (one elected lane of a converged warp) ===================
         const uint32_t leader = elect_one();
         const uint32_t idesc = make_idesc(NC);
-        int it = 0;
+        // descriptors advance by plain additions on the 14-bit start-address field (no carry out of
+        // it: shared memory is < 256 KB); stage indices / phases are counted, not divided
+        const uint64_t a_kstep = (uint64_t)((2u * lbo_a) >> 4), b_kstep = (uint64_t)((2u * lbo_b) >> 4);
+        const int a_stages = p.a_stages, b_stages = p.b_stages, tap_bytes = p.tap_step * 16;
+        int sa = 0, sb = 0;
+        uint32_t pha = 0, phb = 0, accum = 0;
         for (int c = 0; c < nkc; ++c) {
-            const int sa = c % p.a_stages;
-            const uint32_t pha = (uint32_t)(c / p.a_stages) & 1u;
-            const int kc = min(KCHUNK, Cin - c * KCHUNK);
+            const int ksteps = min(KCHUNK, Cin - c * KCHUNK) >> 4;
             mbar_wait(smem_u32(a_full + sa), pha, p.err_flag);
             if (MODE == PRO_F16) fence_proxy_async_smem();    // cp.async wrote through the generic proxy
             tc_fence_after_sync();
-            const uint32_t a_stage = a_base + sa * a_stage_bytes;
-            for (int a = 0; a < ntaps; ++a, ++it) {
-                const int sb = it % p.b_stages;
-                const uint32_t phb = (uint32_t)(it / p.b_stages) & 1u;
+            uint32_t a_tap = a_base + sa * a_stage_bytes;
+            for (int a = 0; a < ntaps; ++a, a_tap += tap_bytes) {
                 mbar_wait(smem_u32(b_full + sb), phb, p.err_flag);
                 tc_fence_after_sync();
                 if (leader) {
-                    const uint32_t b_stage = b_base + sb * b_stage_bytes;
-                    const uint32_t a_tap   = a_stage + (uint32_t)(a * p.tap_step) * 16u;
+                    const uint64_t bdesc0 = make_smem_desc(b_base + sb * b_stage_bytes, lbo_b, 128u);
 #pragma unroll
                     for (int mt = 0; mt < MT; ++mt) {
-                        for (int kk = 0; kk < (kc >> 4); ++kk) {
-                            const uint64_t adesc = make_smem_desc(a_tap + (uint32_t)mt * (TILE_M * 16u) + (uint32_t)kk * 2u * lbo_a, lbo_a, 128u);
-                            const uint64_t bdesc = make_smem_desc(b_stage + (uint32_t)kk * 2u * lbo_b, lbo_b, 128u);
-                            umma_f16(tmem_base + (uint32_t)mt * acc_stride, adesc, bdesc, idesc, (it | kk) ? 1u : 0u);
+                        uint64_t adesc = make_smem_desc(a_tap + (uint32_t)mt * (TILE_M * 16u), lbo_a, 128u);
+                        uint64_t bdesc = bdesc0;
+                        uint32_t acc = accum;
+                        for (int kk = 0; kk < ksteps; ++kk, adesc += a_kstep, bdesc += b_kstep) {
+                            umma_f16(tmem_base + (uint32_t)mt * acc_stride, adesc, bdesc, idesc, acc);
+                            acc = 1u;
                         }
                     }
                     umma_commit(smem_u32(b_empty + sb));
                 }
+                accum = 1u;
                 __syncwarp();
+                if (++sb == b_stages) { sb = 0; phb ^= 1u; }
             }
             if (leader) umma_commit(smem_u32(a_empty + sa));
             __syncwarp();
+            if (++sa == a_stages) { sa = 0; pha ^= 1u; }
         }
         if (leader) umma_commit(smem_u32(acc_full));
         __syncwarp();
     } else {
         // =================== weight (B operand) loader ===================
         if (lane == 0) {
-            const __half *wbase = p.w_packed + (size_t)nchunk * ((size_t)Cin * ntaps * NC);
-            int it = 0;
+            // the packed blocks of one N-chunk are consecutive in (K-chunk, tap) order
+            const uint8_t *src = reinterpret_cast<const uint8_t *>(p.w_packed + (size_t)nchunk * ((size_t)Cin * ntaps * NC));
+            const int b_stages = p.b_stages;
+            int sb = 0;
+            uint32_t phb = 0;
             for (int c = 0; c < nkc; ++c) {
-                const int kc = min(KCHUNK, Cin - c * KCHUNK);
-                const uint32_t bytes = (uint32_t)kc * NC * 2u;
-                for (int a = 0; a < ntaps; ++a, ++it) {
-                    const int sb = it % p.b_stages;
-                    const uint32_t phb = (uint32_t)(it / p.b_stages) & 1u;
+                const uint32_t bytes = (uint32_t)min(KCHUNK, Cin - c * KCHUNK) * NC * 2u;
+                for (int a = 0; a < ntaps; ++a, src += bytes) {
                     mbar_wait(smem_u32(b_empty + sb), phb ^ 1u, p.err_flag);
-                    const __half *src = wbase + ((size_t)c * KCHUNK * ntaps + (size_t)a * kc) * NC;
                     mbar_arrive_expect_tx(smem_u32(b_full + sb), bytes);
                     bulk_copy_g2s(b_base + sb * b_stage_bytes, src, bytes, smem_u32(b_full + sb));
+                    if (++sb == b_stages) { sb = 0; phb ^= 1u; }
                 }
             }
         }
@@ -500,12 +512,11 @@ __global__ void __launch_bounds__(PK_THREADS, 1) conv_umma_pk_kernel(const ConvP
     if (warp < 4) {
         // =================== A producers ===================
         const int need_rows = TILE_M + (ntaps - 1) * p.tap_step;
-        int ca = 0;
+        int sa = 0;
+        uint32_t ph = 0;
         for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
             const TileCoord tc = coord(w);
-            for (int c = 0; c < nkc; ++c, ++ca) {
-                const int sa = ca % p.a_stages;
-                const uint32_t ph = (uint32_t)(ca / p.a_stages) & 1u;
+            for (int c = 0; c < nkc; ++c) {
                 mbar_wait(smem_u32(a_empty + sa), ph ^ 1u, p.err_flag);
                 produce_chunk<MODE, 128, 8>(p, tc, c, smem + SMEM_HEADER + (size_t)sa * a_stage_bytes, lbo_a, need_rows, tid);
                 if (MODE == PRO_F16) {
@@ -514,21 +525,22 @@ __global__ void __launch_bounds__(PK_THREADS, 1) conv_umma_pk_kernel(const ConvP
                     fence_proxy_async_smem();
                     mbar_arrive(smem_u32(a_full + sa));
                 }
+                if (++sa == p.a_stages) { sa = 0; ph ^= 1u; }
             }
         }
     } else if (warp < 8) {
         // =================== epilogue ===================
+        // (runs under the next item's main loop, so its transpose slabs sit behind the operand stages)
+        float *slab = reinterpret_cast<float *>(smem + SMEM_HEADER + (size_t)p.a_stages * a_stage_bytes + (size_t)p.b_stages * b_stage_bytes +
+                                                (size_t)(warp & 3) * SLAB_BYTES);
         int n = 0;
         for (int w = blockIdx.x; w < total_items; w += gridDim.x, ++n) {
             const TileCoord tc = coord(w);
             const int buf = n & 1;
             mbar_wait(smem_u32(acc_full + buf), (uint32_t)(n >> 1) & 1u, p.err_flag);
             tc_fence_after_sync();
-            const int  t     = tc.t0 + (warp & 3) * 32 + lane;
-            const bool valid = t < tc.seg_len;
-            const size_t orow = (tc.seg_row0 + (size_t)t) * (size_t)p.out_mul + p.out_add;
             const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)buf * acc_stride;
-            epilogue_row(p, trow, valid, orow, tc.nchunk, NC);
+            epilogue_tile(p, trow, slab, lane, tc.t0 + (warp & 3) * 32, tc.seg_len, tc.seg_row0, tc.nchunk, NC);
             tc_fence_before_sync();
             mbar_arrive(smem_u32(acc_empty + buf));
         }
@@ -536,39 +548,41 @@ __global__ void __launch_bounds__(PK_THREADS, 1) conv_umma_pk_kernel(const ConvP
         // =================== MMA issuer ===================
         const uint32_t leader = elect_one();
         const uint32_t idesc = make_idesc(NC);
-        int it = 0, ca = 0, n = 0;
+        const uint64_t a_kstep = (uint64_t)((2u * lbo_a) >> 4), b_kstep = (uint64_t)((2u * lbo_b) >> 4);
+        const int a_stages = p.a_stages, b_stages = p.b_stages, tap_bytes = p.tap_step * 16;
+        int sa = 0, sb = 0, n = 0;
+        uint32_t pha = 0, phb = 0;
         for (int w = blockIdx.x; w < total_items; w += gridDim.x, ++n) {
             const int buf = n & 1;
             mbar_wait(smem_u32(acc_empty + buf), ((uint32_t)(n >> 1) & 1u) ^ 1u, p.err_flag);
             tc_fence_after_sync();
             const uint32_t dcol = tmem_base + (uint32_t)buf * acc_stride;
-            for (int c = 0; c < nkc; ++c, ++ca) {
-                const int sa = ca % p.a_stages;
-                const uint32_t pha = (uint32_t)(ca / p.a_stages) & 1u;
-                const int kc = min(KCHUNK, Cin - c * KCHUNK);
+            uint32_t accum = 0;
+            for (int c = 0; c < nkc; ++c) {
+                const int ksteps = min(KCHUNK, Cin - c * KCHUNK) >> 4;
                 mbar_wait(smem_u32(a_full + sa), pha, p.err_flag);
                 if (MODE == PRO_F16) fence_proxy_async_smem();    // cp.async wrote through the generic proxy
                 tc_fence_after_sync();
-                const uint32_t a_stage = a_base + sa * a_stage_bytes;
-                for (int a = 0; a < ntaps; ++a, ++it) {
-                    const int sb = it % p.b_stages;
-                    const uint32_t phb = (uint32_t)(it / p.b_stages) & 1u;
+                uint32_t a_tap = a_base + sa * a_stage_bytes;
+                for (int a = 0; a < ntaps; ++a, a_tap += tap_bytes) {
                     mbar_wait(smem_u32(b_full + sb), phb, p.err_flag);
                     tc_fence_after_sync();
                     if (leader) {
-                        const uint32_t b_stage = b_base + sb * b_stage_bytes;
-                        const uint32_t a_tap   = a_stage + (uint32_t)(a * p.tap_step) * 16u;
-                        for (int kk = 0; kk < (kc >> 4); ++kk) {
-                            const uint64_t adesc = make_smem_desc(a_tap + (uint32_t)kk * 2u * lbo_a, lbo_a, 128u);
-                            const uint64_t bdesc = make_smem_desc(b_stage + (uint32_t)kk * 2u * lbo_b, lbo_b, 128u);
-                            umma_f16(dcol, adesc, bdesc, idesc, (c | a | kk) ? 1u : 0u);
+                        uint64_t adesc = make_smem_desc(a_tap, lbo_a, 128u);
+                        uint64_t bdesc = make_smem_desc(b_base + sb * b_stage_bytes, lbo_b, 128u);
+                        for (int kk = 0; kk < ksteps; ++kk, adesc += a_kstep, bdesc += b_kstep) {
+                            umma_f16(dcol, adesc, bdesc, idesc, accum);
+                            accum = 1u;
                         }
                         umma_commit(smem_u32(b_empty + sb));
                     }
+                    accum = 1u;
                     __syncwarp();
+                    if (++sb == b_stages) { sb = 0; phb ^= 1u; }
                 }
                 if (leader) umma_commit(smem_u32(a_empty + sa));
                 __syncwarp();
+                if (++sa == a_stages) { sa = 0; pha ^= 1u; }
             }
             if (leader) umma_commit(smem_u32(acc_full + buf));
             __syncwarp();
@@ -576,20 +590,19 @@ __global__ void __launch_bounds__(PK_THREADS, 1) conv_umma_pk_kernel(const ConvP
     } else {
         // =================== weight (B operand) loader ===================
         if (lane == 0) {
-            int it = 0;
+            const int b_stages = p.b_stages;
+            int sb = 0;
+            uint32_t phb = 0;
             for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
                 const int nchunk = w % nchunks;
-                const __half *wbase = p.w_packed + (size_t)nchunk * ((size_t)Cin * ntaps * NC);
+                const uint8_t *src = reinterpret_cast<const uint8_t *>(p.w_packed + (size_t)nchunk * ((size_t)Cin * ntaps * NC));
                 for (int c = 0; c < nkc; ++c) {
-                    const int kc = min(KCHUNK, Cin - c * KCHUNK);
-                    const uint32_t bytes = (uint32_t)kc * NC * 2u;
-                    for (int a = 0; a < ntaps; ++a, ++it) {
-                        const int sb = it % p.b_stages;
-                        const uint32_t phb = (uint32_t)(it / p.b_stages) & 1u;
+                    const uint32_t bytes = (uint32_t)min(KCHUNK, Cin - c * KCHUNK) * NC * 2u;
+                    for (int a = 0; a < ntaps; ++a, src += bytes) {
                         mbar_wait(smem_u32(b_empty + sb), phb ^ 1u, p.err_flag);
-                        const __half *src = wbase + ((size_t)c * KCHUNK * ntaps + (size_t)a * kc) * NC;
                         mbar_arrive_expect_tx(smem_u32(b_full + sb), bytes);
                         bulk_copy_g2s(b_base + sb * b_stage_bytes, src, bytes, smem_u32(b_full + sb));
+                        if (++sb == b_stages) { sb = 0; phb ^= 1u; }
                     }
                 }
             }
@@ -646,7 +659,9 @@ size_t conv_umma_plan(ConvParams &p, size_t smem_budget)
     int cols = 32;
     while (cols < p.mt * ((p.NC + 31) & ~31)) cols <<= 1;
     p.tmem_cols = cols;
-    return SMEM_HEADER + as * a_stage + bs * b_stage;
+    // the epilogue reuses the stage memory for its transpose slabs (one per producer warp)
+    const size_t stages = as * a_stage + bs * b_stage, slabs = (size_t)4 * p.mt * SLAB_BYTES;
+    return SMEM_HEADER + (stages > slabs ? stages : slabs);
 }
 
 // smem plan of the persistent kernel: the whole SM for one CTA, weight ring as deep as it fits
@@ -659,6 +674,7 @@ size_t conv_umma_pk_plan(ConvParams &p, size_t smem_budget)
     const size_t a_stage = (size_t)(kc_max >> 3) * p.a_rows * 16;
     const size_t b_stage = (size_t)kc_max * p.NC * 2;
     int as = 3, bs = 2;
+    smem_budget -= 4 * SLAB_BYTES;      // epilogue transpose slabs behind the stages
     while (bs < MAX_B_STAGES && SMEM_HEADER + as * a_stage + (bs + 1) * b_stage <= smem_budget) ++bs;
     while (as < MAX_A_STAGES && SMEM_HEADER + (as + 1) * a_stage + bs * b_stage <= smem_budget) ++as;
     p.a_stages = as;
@@ -666,7 +682,7 @@ size_t conv_umma_pk_plan(ConvParams &p, size_t smem_budget)
     int cols = 32;
     while (cols < 2 * ((p.NC + 31) & ~31)) cols <<= 1;
     p.tmem_cols = cols;
-    return SMEM_HEADER + as * a_stage + bs * b_stage;
+    return SMEM_HEADER + as * a_stage + bs * b_stage + 4 * SLAB_BYTES;
 }
 
 template <int MODE>
