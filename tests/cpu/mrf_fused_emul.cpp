@@ -134,8 +134,9 @@ static int run(int k, int T, double min_eff)
         for (int l = 0; l < nl; ++l) {
             const Conv &cv = convs[2 * cp.p0 + l];
             wpk[l] = pack_weights(cv.raw.data(), CH, cv.k);
-            if (l & 1) { for (int i = 0; i < CH; ++i) cum[i] += cv.bias[i]; bias[l] = cum; }
-            else bias[l] = cv.bias;
+            // biases travel in the kernel's row order (row r <-> channel row_to_chan(r))
+            if (l & 1) { for (int i = 0; i < CH; ++i) cum[i] += cv.bias[i]; bias[l] = to_row_order(cum); }
+            else bias[l] = to_row_order(cv.bias);
             if (l + 1 < nl) tbl[l] = make_table(CH, NCOL, cv.d, convs[2 * cp.p0 + l + 1].d);
         }
         const std::vector<uint32_t> tbl0 = make_table(CH, NCOL, 1, convs[2 * cp.p0].d);
@@ -156,7 +157,7 @@ static int run(int k, int T, double min_eff)
                 for (int n = 0; n < NCOL; ++n) {
                     const int tau = S * n + s, t = tw + tau;
                     const bool ok = tau < Wp && t >= 0 && t < T;
-                    const float yv = ok ? cur[(size_t)t * CH + oc] : 0.f;
+                    const float yv = ok ? cur[(size_t)t * CH + row_to_chan(oc)] : 0.f;   // oc is a ROW index in here
                     Yacc[(size_t)m * NCOL + n] = yv;
                     const uint32_t e = tbl0[(size_t)s * NCOL + n];
                     // the stmatrix fast path of the kernel dumps beyond-window elements on the trash row:
@@ -209,7 +210,7 @@ static int run(int k, int T, double min_eff)
                             sts16(ob, tbl_unit(e), oc, (t >= 0 && t < T) ? lrelu(v, 0.1f) : 0.f);
                         } else {
                             const int tau = S * n + s, t = tw + tau;
-                            if (tau >= cp.halo && tau < cp.halo + cp.valid && t >= 0 && t < T) out[(size_t)t * CH + oc] = v;
+                            if (tau >= cp.halo && tau < cp.halo + cp.valid && t >= 0 && t < T) out[(size_t)t * CH + row_to_chan(oc)] = v;
                         }
                     }
                 }

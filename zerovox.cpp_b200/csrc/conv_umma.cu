@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(128 * MT + 64) conv_umma_kernel(const ConvPara
 
     // ---- which tile of which utterance ----
     const int tile    = blockIdx.x;
-    const int u       = find_segment(p.tile_start, p.B, tile);
+    const int u       = find_segment_warp(p.tile_start, p.B, tile);
     const int t0      = (tile - __ldg(p.tile_start + u)) * ROWS_CTA;
     const int seg_f0  = __ldg(p.seg_start + u);
     const int seg_len = (__ldg(p.seg_start + u + 1) - seg_f0) * p.rate_in;
@@ -480,7 +480,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) conv_umma_pk_kernel(const ConvP
         TileCoord tc;
         const int tile = w / nchunks;
         tc.nchunk  = w - tile * nchunks;
-        tc.u       = find_segment(p.tile_start, p.B, tile);
+        tc.u       = find_segment_warp(p.tile_start, p.B, tile);
         tc.t0      = (tile - __ldg(p.tile_start + tc.u)) * TILE_M;
         const int seg_f0 = __ldg(p.seg_start + tc.u);
         tc.seg_len  = (__ldg(p.seg_start + tc.u + 1) - seg_f0) * p.rate_in;

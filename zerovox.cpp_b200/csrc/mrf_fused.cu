@@ -26,6 +26,8 @@
 // K-major operand rows the next MMA reads; row addresses come from the scatter table.  Windows
 // that touch an utterance edge use a scalar path (tcgen05.ld.32x32b, one 2-byte store per
 // element) that also applies the per-layer zero masking (SURVEY.md H-d).
+#include <cstdio>
+
 #include "mrf_fused.cuh"
 #include "ptx_sm100.cuh"
 #include "zvx_common.cuh"
@@ -56,7 +58,7 @@ __device__ __forceinline__ void stmatrix_x4_trans(uint32_t addr, uint32_t a, uin
 }
 // 16 lanes x 64 columns; thread T gets for column group cg (8 columns): r[4cg+0/1] = (lane T/4,
 // columns 8cg + 2(T%4), +1), r[4cg+2/3] = (lane T/4 + 8, same columns)
-__device__ __forceinline__ void tmem_ld_16x256b_x8(uint32_t taddr, uint32_t (&r)[32])
+__device__ __forceinline__ void tmem_ld_16x256b_x8_nowait(uint32_t taddr, uint32_t (&r)[32])
 {
     asm volatile(
         "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
@@ -67,7 +69,12 @@ __device__ __forceinline__ void tmem_ld_16x256b_x8(uint32_t taddr, uint32_t (&r)
           "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld_16x256b_x8(uint32_t taddr, uint32_t (&r)[32])
+{
+    tmem_ld_16x256b_x8_nowait(taddr, r);
+    tmem_wait_ld();
 }
 __device__ __forceinline__ void tmem_st_16x256b_x8(uint32_t taddr, const uint32_t (&r)[32])
 {
@@ -82,6 +89,17 @@ __device__ __forceinline__ void tmem_st_16x256b_x8(uint32_t taddr, const uint32_
         : "memory");
 }
 
+// 16 lanes x 32 columns (column groups cg = 0..3), same per-thread layout as the x8 form
+__device__ __forceinline__ void tmem_st_16x256b_x4(uint32_t taddr, const uint32_t (&r)[16])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.16x256b.x4.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+
 template <int CH, int NCOL>
 struct FCfg {
     using G = mrf::Geo<CH, NCOL>;
@@ -90,7 +108,10 @@ struct FCfg {
     static constexpr int THREADS   = EPI + 64;
     static constexpr int CTAS      = NCOL == 128 ? 2 : 1;
     static constexpr int TBL_WORDS = G::S * NCOL;
-    static constexpr uint32_t OFF_TBL  = F_HEADER;
+    // utterance tables (seg_start, win_start: 1 + B entries each) are copied to shared memory when the
+    // batch is small enough; every window looks its utterance up in them
+    static constexpr int SEG_SMEM_MAX = 1024;
+    __host__ __device__ static constexpr uint32_t seg_bytes(int B) { return B + 1 <= SEG_SMEM_MAX ? (uint32_t)((2 * (B + 1) * 4 + 511) & ~511) : 0u; }
     // compact (16-bit row unit) copies of the scatter tables of all layers stay resident: tbl0 + one per
     // non-final layer
     __host__ __device__ static constexpr uint32_t tbl_bytes(int nlayers) { return (uint32_t)((nlayers * TBL_WORDS * 2 + 511) & ~511); }
@@ -114,8 +135,11 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
     uint64_t *acc_full  = bars + 2 * F_MAX_SLOTS;
     uint64_t *act_ready = bars + 2 * F_MAX_SLOTS + 1;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 256);
-    uint16_t *tbl_s     = reinterpret_cast<uint16_t *>(smem + C::OFF_TBL);     // [nlayers][S][NCOL] row units
-    const uint32_t OFF_BUF0 = C::OFF_TBL + C::tbl_bytes(p.nlayers);
+    const uint32_t OFF_TBL = F_HEADER + C::seg_bytes(p.B);
+    const int *seg_s    = reinterpret_cast<const int *>(smem + F_HEADER);      // [B + 1] seg_start, [B + 1] win_start
+    const bool seg_in_smem = C::seg_bytes(p.B) != 0;
+    uint16_t *tbl_s     = reinterpret_cast<uint16_t *>(smem + OFF_TBL);        // [nlayers][S][NCOL] row units
+    const uint32_t OFF_BUF0 = OFF_TBL + C::tbl_bytes(p.nlayers);
     const uint32_t OFF_BUF1 = OFF_BUF0 + G::BUF;
     const uint32_t OFF_RING = OFF_BUF1 + G::BUF;
 
@@ -132,10 +156,24 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
     struct Win { int T; size_t row0; int tw; bool interior; };
     auto window = [&](int win) {
         Win w;
-        const int u  = find_segment(p.win_start, p.B, win);
-        const int wi = win - __ldg(p.win_start + u);
-        const int f0 = __ldg(p.seg_start + u);
-        w.T    = (__ldg(p.seg_start + u + 1) - f0) * p.rate;
+        int wi, f0, f1;
+        if (seg_in_smem) {
+            const int *ws = seg_s + p.B + 1;
+            int lo = 0, hi = p.B - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (ws[mid] <= win) lo = mid; else hi = mid - 1;
+            }
+            wi = win - ws[lo];
+            f0 = seg_s[lo];
+            f1 = seg_s[lo + 1];
+        } else {
+            const int u = find_segment_warp(p.win_start, p.B, win);
+            wi = win - __ldg(p.win_start + u);
+            f0 = __ldg(p.seg_start + u);
+            f1 = __ldg(p.seg_start + u + 1);
+        }
+        w.T    = (f1 - f0) * p.rate;
         w.row0 = (size_t)f0 * p.rate;
         w.tw   = wi * p.valid - p.halo;                // time of window position 0 (may be < 0)
         w.interior = w.tw >= 0 && w.tw + G::WP <= w.T;
@@ -154,6 +192,13 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
             const int sg = i / NZ, z = i % NZ;
             const int row = z < mrf::GUARD ? z : mrf::GUARD + ROW_LO + (z - mrf::GUARD);
             *reinterpret_cast<uint4 *>(smem + OFF_BUF0 + (size_t)sg * LBO_B + (size_t)row * 16) = make_uint4(0u, 0u, 0u, 0u);
+        }
+    }
+    if (seg_in_smem) {
+        int *dst = reinterpret_cast<int *>(smem + F_HEADER);
+        for (int i = tid; i <= p.B; i += C::THREADS) {
+            dst[i] = __ldg(p.seg_start + i);
+            dst[p.B + 1 + i] = __ldg(p.win_start + i);
         }
     }
     for (int t = 0; t < nl; ++t) {
@@ -188,49 +233,79 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
         // ---- scalar-path coordinates: thread = accumulator row m ----
         const int m       = quarter * 32 + lane;
         const int s       = m / CH;
-        const int oc      = m % CH;
+        const int oc      = m % CH;                    // row inside the CH block (kernel row order)
+        const int gc      = mrf::row_to_chan(oc);      // the global channel it holds
         const uint32_t toff = (uint32_t)(oc >> 3) * LBO_B + (uint32_t)(oc & 7) * 2u;
         const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        // ---- fragment-path coordinates: per 16-lane half lh, rows rb + lane/4 and rb + lane/4 + 8 ----
+        // ---- fragment-path coordinates: per 16-lane half lh, rows rb + lane/4 and rb + lane/4 + 8;
+        //      over both halves a thread owns rows g, g+8, g+16, g+24 of its lane quarter = the four
+        //      adjacent global channels c4 .. c4+3 (mrf::row_to_chan) of shift sQ ----
         const int mi = lane >> 3, r8 = lane & 7;       // stmatrix: this thread addresses row r8 of matrix mi
+        const int sQ = (quarter * 32) / CH;
+        const int c4 = (quarter * 32) % CH + 4 * (lane >> 2);
 
+#ifdef ZVX_FUSED_PHASES
+        const bool dbg = (p.flags & 2) && blockIdx.x == 0 && warp == 0;
+        long long c_ld = 0, c_st = 0, c_l0 = 0;
+#else
+        constexpr bool dbg = false;
+#endif
         // y window -> tensor memory columns [ybase, ybase + NCOL) (fp32), lrelu(y) -> buffer 0 (fp16).
         // Uses table slot 1; does NOT arrive on act_ready.
         auto prologue = [&](const Win &w, uint32_t ybase) {
             if (w.interior && !(p.flags & 1)) {
+                // per 32-column half: 8 float4 loads per thread (its 4 channels x 8 columns), all in flight
+                // before the first use; a warp instruction covers 4 time steps x one 128-byte line
+                const float *yq = p.y_in + (w.row0 + (size_t)w.tw) * CH + c4;
 #pragma unroll 1
-                for (int lh = 0; lh < 2; ++lh) {
-                    const int rb  = quarter * 32 + lh * 16;
-                    const int sA  = rb / CH;
-                    const int ocA = rb % CH + (lane >> 2);
-                    const float *yA = p.y_in + (w.row0 + (size_t)w.tw) * CH + ocA;
-                    const uint16_t *tb = tbl_s + sA * NCOL + colw;
-                    uint32_t v[32];
+                for (int hc = 0; hc < 2; ++hc) {
+                    const int col0 = colw + 32 * hc;
+                    const uint16_t *tb = tbl_s + sQ * NCOL + col0;
+                    float4 f[8];
+#ifdef ZVX_FUSED_PHASES
+                    if (dbg) c_l0 = clock64();
+#endif
 #pragma unroll
-                    for (int cg = 0; cg < 8; ++cg) {
-                        const int n0 = colw + 8 * cg + 2 * (lane & 3);
-                        const int tau0 = S * n0 + sA, tau1 = tau0 + S;
-                        v[4 * cg + 0] = tau0 < G::WP ? __float_as_uint(__ldg(yA + (size_t)tau0 * CH)) : 0u;
-                        v[4 * cg + 1] = tau1 < G::WP ? __float_as_uint(__ldg(yA + (size_t)tau1 * CH)) : 0u;
-                        v[4 * cg + 2] = tau0 < G::WP ? __float_as_uint(__ldg(yA + (size_t)tau0 * CH + 8)) : 0u;
-                        v[4 * cg + 3] = tau1 < G::WP ? __float_as_uint(__ldg(yA + (size_t)tau1 * CH + 8)) : 0u;
+                    for (int i = 0; i < 8; ++i) {
+                        const int tau = S * (col0 + 8 * (i >> 1) + 2 * (lane & 3) + (i & 1)) + sQ;
+                        f[i] = tau < G::WP ? __ldg(reinterpret_cast<const float4 *>(yq + (size_t)tau * CH)) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
-                    tmem_st_16x256b_x8(tmem_base + ((uint32_t)rb << 16) + ybase + (uint32_t)colw, v);
-                    const uint32_t gbase = buf0 + (uint32_t)((rb % CH) >> 3) * LBO_B + (uint32_t)(mi & 1) * LBO_B;
+#ifdef ZVX_FUSED_PHASES
+                    if (dbg) {
+                        asm volatile("" ::"f"(f[0].x), "f"(f[1].x), "f"(f[2].x), "f"(f[3].x), "f"(f[4].x), "f"(f[5].x), "f"(f[6].x), "f"(f[7].x) : "memory");
+                        const long long c = clock64();
+                        c_ld += c - c_l0;
+                        c_l0 = c;
+                    }
+#endif
 #pragma unroll
-                    for (int pr = 0; pr < 4; ++pr) {
-                        uint32_t f[4];
+                    for (int lh = 0; lh < 2; ++lh) {
+                        const int rb = quarter * 32 + lh * 16;
+                        uint32_t v[16];
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const int i0 = 8 * pr + 2 * q;   // (cg = 2pr + q/2, row A/B = q & 1)
-                            f[q] = pack_h2(lrelu_max(__uint_as_float(v[i0]), p.in_slope), lrelu_max(__uint_as_float(v[i0 + 1]), p.in_slope));
+                        for (int cg = 0; cg < 4; ++cg) {
+                            v[4 * cg + 0] = __float_as_uint(lh ? f[2 * cg].z : f[2 * cg].x);
+                            v[4 * cg + 1] = __float_as_uint(lh ? f[2 * cg + 1].z : f[2 * cg + 1].x);
+                            v[4 * cg + 2] = __float_as_uint(lh ? f[2 * cg].w : f[2 * cg].y);
+                            v[4 * cg + 3] = __float_as_uint(lh ? f[2 * cg + 1].w : f[2 * cg + 1].y);
                         }
-                        const uint32_t e = tb[8 * (2 * pr + (mi >> 1)) + r8];
-                        stmatrix_x4_trans(gbase + e * 16u, f[0], f[1], f[2], f[3]);
+                        tmem_st_16x256b_x4(tmem_base + ((uint32_t)rb << 16) + ybase + (uint32_t)col0, v);
+                        const uint32_t gbase = buf0 + (uint32_t)((rb % CH) >> 3) * LBO_B + (uint32_t)(mi & 1) * LBO_B;
+#pragma unroll
+                        for (int pr = 0; pr < 2; ++pr) {
+                            uint32_t h[4];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const int i0 = 8 * pr + 2 * q;   // (cg = 2pr + q/2, row A/B = q & 1)
+                                h[q] = pack_h2(lrelu_max(__uint_as_float(v[i0]), p.in_slope), lrelu_max(__uint_as_float(v[i0 + 1]), p.in_slope));
+                            }
+                            const uint32_t e = tb[8 * (2 * pr + (mi >> 1)) + r8];
+                            stmatrix_x4_trans(gbase + e * 16u, h[0], h[1], h[2], h[3]);
+                        }
                     }
                 }
             } else {
-                const float *yin = p.y_in + w.row0 * CH + oc;
+                const float *yin = p.y_in + w.row0 * CH + gc;
                 const uint32_t *tb = p.tbl0 + s * NCOL;             // full entries (tau for the edge mask) from global
                 uint8_t *dst = smem + OFF_BUF0 + toff;
 #pragma unroll 1
@@ -254,24 +329,36 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
                     }
                 }
             }
+#ifdef ZVX_FUSED_PHASES
+            if (dbg) c_l0 = clock64();
+#endif
             tmem_wait_st();
             fence_proxy_async_smem();
+#ifdef ZVX_FUSED_PHASES
+            if (dbg) c_st += clock64() - c_l0;
+#endif
         };
         auto publish = [&]() {
             tc_fence_before_sync();
             mbar_arrive(smem_u32(act_ready));
         };
 
+        // -DZVX_FUSED_PHASES + flags bit 1: cycle counts per phase of CTA 0 / warp 0, printed at exit
+        long long c_pro = 0, c_wait = 0, c_drain = 0, c_final = 0, c_t0 = dbg ? clock64() : 0, c_a = 0;
         int iter = 0;
         int win = blockIdx.x;
+        Win wnext = {0, 0, 0, false};
         if (win < nwin) {
-            const Win w0 = window(win);
-            prologue(w0, ycol(0));
+            wnext = window(win);
+            prologue(wnext, ycol(0));
             publish();
         }
+#ifdef ZVX_FUSED_PHASES
+        const long long c_first = dbg ? clock64() - c_t0 : 0, c_ld_first = c_ld;
+#endif
 #pragma unroll 1
         for (; win < nwin; win += gridDim.x, ++iter) {
-            const Win w = window(win);
+            const Win w = wnext;
             const int tw = w.tw, T = w.T;
             const bool interior = w.interior;
             const bool has_next = win + (int)gridDim.x < nwin;
@@ -285,11 +372,15 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
                     // While the last conv of this window accumulates into y, bring in the NEXT window: its
                     // y goes to the (now idle) conv1 accumulator columns, lrelu(y) to buffer 0 (the last
                     // layer reads buffer 1; nlayers is even).  Published after this window's y is read.
-                    const Win wn = window(win + (int)gridDim.x);
-                    prologue(wn, hcol(iter));
+                    if (dbg) c_a = clock64();
+                    wnext = window(win + (int)gridDim.x);
+                    prologue(wnext, hcol(iter));
+                    if (dbg) c_pro += clock64() - c_a;
                 }
+                if (dbg) c_a = clock64();
                 mbar_wait(smem_u32(acc_full), gl & 1u, p.err_flag);
                 tc_fence_after_sync();
+                if (dbg) { const long long c_b = clock64(); c_wait += c_b - c_a; c_a = c_b; }
                 if (!last) {
                     const uint32_t obuf_off = (l & 1) ? OFF_BUF0 : OFF_BUF1;
                     const float slope = L.out_slope;
@@ -339,13 +430,41 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
                     }
                     fence_proxy_async_smem();
                     publish();
+                    if (dbg) c_drain += clock64() - c_a;
                 } else {
                     // final: y (+ running branch sum) (* 1/num_blocks) -> global fp32.  Both 32-column
                     // batches are pulled out of tensor memory first, then the next window is published
                     // (its first conv may overwrite these columns), then the global traffic follows.
+                    if (interior) {
+                        // fragment layout again: this thread's 4 adjacent channels x 16 columns leave as float4
+                        uint32_t r0[32], r1[32];
+                        tmem_ld_16x256b_x8_nowait(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc_col + (uint32_t)colw, r0);
+                        tmem_ld_16x256b_x8_nowait(tmem_base + ((uint32_t)(quarter * 32 + 16) << 16) + acc_col + (uint32_t)colw, r1);
+                        const int rq = (quarter * 32) % CH + (lane >> 2);
+                        const float4 b4 = make_float4(__ldg(L.bias + rq), __ldg(L.bias + rq + 8), __ldg(L.bias + rq + 16), __ldg(L.bias + rq + 24));
+                        tmem_wait_ld();
+                        if (has_next) publish();
+                        float *oq = p.out + (w.row0 + (size_t)tw) * CH + c4;
+                        const float *aq = p.acc_in ? p.acc_in + (w.row0 + (size_t)tw) * CH + c4 : nullptr;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int tau = S * (colw + 8 * (i >> 1) + 2 * (lane & 3) + (i & 1)) + sQ;
+                            if (tau >= p.halo && tau < p.halo + p.valid) {
+                                const int i0 = 4 * (i >> 1) + (i & 1);
+                                float4 v = make_float4(__fadd_rn(__uint_as_float(r0[i0]), b4.x), __fadd_rn(__uint_as_float(r0[i0 + 2]), b4.y),
+                                                       __fadd_rn(__uint_as_float(r1[i0]), b4.z), __fadd_rn(__uint_as_float(r1[i0 + 2]), b4.w));
+                                if (aq) {
+                                    const float4 a = *reinterpret_cast<const float4 *>(aq + (size_t)tau * CH);
+                                    v = make_float4(__fadd_rn(a.x, v.x), __fadd_rn(a.y, v.y), __fadd_rn(a.z, v.z), __fadd_rn(a.w, v.w));
+                                }
+                                if (p.has_scale) v = make_float4(__fmul_rn(v.x, p.scale), __fmul_rn(v.y, p.scale), __fmul_rn(v.z, p.scale), __fmul_rn(v.w, p.scale));
+                                *reinterpret_cast<float4 *>(oq + (size_t)tau * CH) = v;
+                            }
+                        }
+                    } else {
                     const float bias = __ldg(L.bias + oc);
-                    float *out = p.out + w.row0 * CH + oc;
-                    const float *ain = p.acc_in ? p.acc_in + w.row0 * CH + oc : nullptr;
+                    float *out = p.out + w.row0 * CH + gc;
+                    const float *ain = p.acc_in ? p.acc_in + w.row0 * CH + gc : nullptr;
                     uint32_t r0[32], r1[32];
                     tmem_ld32(tlane + acc_col + (uint32_t)colw, r0);
                     tmem_ld32(tlane + acc_col + (uint32_t)(colw + 32), r1);
@@ -378,13 +497,26 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
                             }
                         }
                     }
+                    }
+                    if (dbg) c_final += clock64() - c_a;
                 }
             }
         }
+#ifdef ZVX_FUSED_PHASES
+        if (dbg && lane == 0)
+            printf("mrf_fused CH=%d NCOL=%d k=%d nl=%d windows=%d: total %lld  prologue %lld  wait_mma %lld  drain %lld  final %lld  | prologue: loads %lld  wait_st+fence %lld  first prologue (tensor pipe idle) %lld of which loads %lld (cycles, CTA 0 warp 0)\n",
+                   CH, NCOL, p.L[0].k, nl, iter, clock64() - c_t0, c_pro, c_wait, c_drain, c_final, c_ld, c_st, c_first, c_ld_first);
+#endif
     } else if (warp == EPI_WARPS) {
         // =================== MMA issuer ===================
         const uint32_t leader = elect_one();
         const uint32_t idesc  = make_idesc_mn(128, NCOL);
+#ifdef ZVX_FUSED_PHASES
+        const bool dbg = (p.flags & 2) && blockIdx.x == 0;
+#else
+        constexpr bool dbg = false;
+#endif
+        long long c_act = 0, c_w = 0, c_a = 0, c_t0 = dbg ? clock64() : 0;
         int it = 0, iter = 0;
 #pragma unroll 1
         for (int win = blockIdx.x; win < nwin; win += gridDim.x, ++iter) {
@@ -396,14 +528,18 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
                 const uint32_t lbo_a = (uint32_t)mrf::tap_blocks(k, S) * CH * 16u;
                 const uint32_t ibuf  = (l & 1) ? buf1 : buf0;
                 const uint32_t dcol  = tmem_base + (L.accumulate ? ycol(iter) : hcol(iter));
+                if (dbg) c_a = clock64();
                 mbar_wait(smem_u32(act_ready), (uint32_t)(iter * nl + l) & 1u, p.err_flag);
                 tc_fence_after_sync();
+                if (dbg) c_act += clock64() - c_a;
 #pragma unroll 1
                 for (int c = 0; c < G::KSTEPS; ++c, ++it) {
                     const int slot = it % nslots;
                     const uint32_t ph = (uint32_t)(it / nslots) & 1u;
+                    if (dbg) c_a = clock64();
                     mbar_wait(smem_u32(w_full + slot), ph, p.err_flag);
                     tc_fence_after_sync();
+                    if (dbg) c_w += clock64() - c_a;
                     if (leader) {
                         const uint32_t a_slot = ring + (uint32_t)slot * slot_bytes;
                         const uint32_t b_c    = ibuf + (uint32_t)(2 * c) * LBO_B + (uint32_t)mrf::GUARD * 16u;
@@ -423,6 +559,8 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
                 __syncwarp();
             }
         }
+        if (dbg && lane == 0)
+            printf("mrf_fused MMA warp: total %lld  wait_activations %lld  wait_weights %lld (cycles, CTA 0)\n", clock64() - c_t0, c_act, c_w);
     } else {
         // =================== weight loader + L2 prefetcher ===================
         int it = 0;
@@ -476,7 +614,7 @@ cudaError_t launch_cfg(const mrf::Params &p, int total_windows, cudaStream_t st)
     using C = FCfg<CH, NCOL>;
     uint32_t slot = 0;
     for (int l = 0; l < p.nlayers; ++l) slot = max(slot, mrf::chunk_bytes(p.L[l].k, C::G::S, CH));
-    const size_t fixed = C::OFF_TBL + C::tbl_bytes(p.nlayers) + 2 * (size_t)C::G::BUF;
+    const size_t fixed = F_HEADER + C::seg_bytes(p.B) + C::tbl_bytes(p.nlayers) + 2 * (size_t)C::G::BUF;
     if (fixed + slot > C::SMEM_BUDGET) return cudaErrorInvalidConfiguration;
     int nslots = (int)((C::SMEM_BUDGET - fixed) / slot);
     if (nslots > F_MAX_SLOTS) nslots = F_MAX_SLOTS;

@@ -72,6 +72,16 @@ ZVX_HD int a_block(int k, int S, int j) { return k + S - 2 - j; }
 // bytes of one weight chunk = (layer, 16-channel K-step): two channel groups
 ZVX_HD uint32_t chunk_bytes(int k, int S, int CH) { return 2u * (uint32_t)tap_blocks(k, S) * CH * 16u; }
 
+// Channel order inside the kernel.  Accumulator row s*CH + r and K slot r of the activation rows
+// hold GLOBAL channel row_to_chan(r): inside every block of 32 channels, row 8 i + g <-> channel
+// 4 g + i.  A thread of the tcgen05.ld/st 16x256b fragment layout owns rows g, g+8 (first 16-lane
+// half) and g+16, g+24 (second half) of its lane quarter: with this order they are four adjacent
+// channels of [time][CH] global memory, so block input and output move as float4 and a warp
+// instruction touches whole 128-byte lines.  Weights (rows and K) and biases are packed in row order
+// by the host (mrf_fused_host.h); the layers in between never see the permutation.
+ZVX_HD int chan_to_row(int c) { return (c & ~31) | ((c & 3) << 3) | ((c >> 2) & 7); }
+ZVX_HD int row_to_chan(int r) { return (r & ~31) | ((r & 7) << 2) | ((r >> 3) & 3); }
+
 ZVX_HD int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
 // B operand of step j: sub-buffer and row offset (relative to data row 0)
@@ -119,8 +129,8 @@ struct Layer {
     int             d;          // dilation (layout of this layer's input and output positions)
     int             accumulate; // 0: conv1 -> H accumulator (fresh); 1: conv2 -> accumulates onto y
     float           out_slope;  // leaky-relu slope applied to (acc + bias) before the fp16 store
-    const uint16_t *w;          // packed fp16: [K-step][2 groups][tap block][oc][8]
-    const float    *bias;       // [CH]: conv1: its bias; conv2: cumulative sum of conv2 biases so far
+    const uint16_t *w;          // packed fp16: [K-step][2 groups][tap block][oc row][8 ic rows] (row order, see chan_to_row)
+    const float    *bias;       // [CH] in row order: conv1: its bias; conv2: cumulative sum of conv2 biases so far
     const uint32_t *tbl;        // [S][ncol] scatter into the next layer's buffer (unused for the last)
 };
 

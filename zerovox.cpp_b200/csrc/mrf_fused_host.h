@@ -15,8 +15,9 @@ namespace zvx {
 namespace mrf {
 
 // raw: (OC = CH, IC = CH, K = k) fp16, K fastest (ggml ne [K, IC, OC]).
-// packed: [K-step c][group g2 of 2][tap block tb][oc][8 channels]; tap block tb holds tap
-// t = (k - 1 + S - 1) - tb, zeros when t is outside [0, k).
+// packed: [K-step c][group g2 of 2][tap block tb][oc row][8 ic rows]; tap block tb holds tap
+// t = (k - 1 + S - 1) - tb, zeros when t is outside [0, k).  Output rows and K slots are in the
+// kernel's row order (row r <-> channel row_to_chan(r), mrf_fused.cuh).
 inline std::vector<uint16_t> pack_weights(const uint16_t *raw, int CH, int k)
 {
     const int S = 128 / CH, TB = tap_blocks(k, S);
@@ -28,9 +29,17 @@ inline std::vector<uint16_t> pack_weights(const uint16_t *raw, int CH, int k)
                 const int t = (k - 1 + S - 1) - tb;
                 for (int oc = 0; oc < CH; ++oc)
                     for (int e = 0; e < 8; ++e, ++o)
-                        if (t >= 0 && t < k) pk[o] = raw[((size_t)oc * CH + (c * 16 + g2 * 8 + e)) * k + t];
+                        if (t >= 0 && t < k) pk[o] = raw[((size_t)row_to_chan(oc) * CH + row_to_chan(c * 16 + g2 * 8 + e)) * k + t];
             }
     return pk;
+}
+
+// per-channel vector (bias) in the kernel's row order
+inline std::vector<float> to_row_order(const std::vector<float> &v)
+{
+    std::vector<float> r(v.size());
+    for (size_t i = 0; i < v.size(); ++i) r[i] = v[(size_t)row_to_chan((int)i)];
+    return r;
 }
 
 // Scatter table from a layer whose output positions are laid out for dilation d_cur into a

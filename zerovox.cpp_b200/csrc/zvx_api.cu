@@ -486,9 +486,9 @@ int build_fused(zvx_ctx *ctx, HostW &hw)
                     if (upload_vec(ctx, mrf::pack_weights(reinterpret_cast<const uint16_t *>(raw.data()), CH, k), &L.w)) return 1;
                     if (second) {
                         for (int q = 0; q < CH; ++q) cum[q] += bias[q];   // y_true = accumulator + sum of conv2 biases so far
-                        if (upload_vec(ctx, cum, &L.bias)) return 1;
+                        if (upload_vec(ctx, mrf::to_row_order(cum), &L.bias)) return 1;
                     } else {
-                        L.bias = ctx->mrf1[idx0 + p].bias;
+                        if (upload_vec(ctx, mrf::to_row_order(bias), &L.bias)) return 1;
                     }
                     L.tbl = nullptr;
                     if (l + 1 < fc.nlayers) {

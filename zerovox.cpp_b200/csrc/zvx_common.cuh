@@ -140,4 +140,26 @@ __device__ __forceinline__ int find_segment(const int *tile_start, int B, int ti
     return lo;
 }
 
+// Same search done by a whole (converged) warp with identical arguments: every round the 32 lanes
+// probe 32 evenly spaced entries and a ballot picks the sub-range, so a table of 1 + B entries costs
+// ceil(log32 B) dependent loads instead of log2 B.  (The tables are re-read by every tile / window;
+// between two uses the streaming traffic has evicted them from L1, so each dependent load is an L2
+// round trip -- measured as the top stall of the fused MRF prologue, profiles/r01_ncu_mrf_fused_ch32_k3_*.)
+__device__ __forceinline__ int find_segment_warp(const int *start, int B, int x)
+{
+    const int lane = threadIdx.x & 31;
+    int lo = 0, n = B;                                   // candidates [lo, lo + n); start[lo] <= x holds
+    while (n > 1) {
+        const int step = (n + 31) >> 5;
+        const int u = lo + lane * step;
+        const bool le = u < lo + n && __ldg(start + u) <= x;
+        const unsigned m = __ballot_sync(0xffffffffu, le) | 1u;
+        const int k = 31 - __clz(m);
+        const int end = lo + n;
+        lo += k * step;
+        n = min(step, end - lo);
+    }
+    return lo;
+}
+
 }  // namespace zvx
