@@ -14,7 +14,8 @@ import numpy as np
 from . import gguf_io
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libzvx.so")
+# ZVX_LIB: developer override used for A/B timing of two builds inside one GPU session (tools/ab_compare.py)
+LIB_PATH = os.environ.get("ZVX_LIB") or os.path.join(_HERE, "libzvx.so")
 
 ZVX_F32, ZVX_F16 = 0, 1
 

@@ -236,6 +236,38 @@ __global__ void __launch_bounds__(256) cvt_f16_kernel(const float *__restrict__ 
     }
 }
 
+// fp16( lrelu( ((a + b) + c) * scale ) ) of three [n] fp32 arrays: the MRF branch average of
+// hifigan.cpp:300-315 followed by the leaky_relu of :281, materialised once as the fp16 operand of an
+// up-conv whose output phases are separate launches (each of them would redo it otherwise).
+__global__ void __launch_bounds__(256) sum3_act_f16_kernel(const float4 *__restrict__ a, const float4 *__restrict__ b,
+                                                           const float4 *__restrict__ c, float scale, float slope, size_t n4,
+                                                           uint2 *__restrict__ y16)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 va = a[i], vb = b[i], vc = c[i];
+        const float v[4] = {__fmul_rn(__fadd_rn(__fadd_rn(va.x, vb.x), vc.x), scale), __fmul_rn(__fadd_rn(__fadd_rn(va.y, vb.y), vc.y), scale),
+                            __fmul_rn(__fadd_rn(__fadd_rn(va.z, vb.z), vc.z), scale), __fmul_rn(__fadd_rn(__fadd_rn(va.w, vb.w), vc.w), scale)};
+        const __half2 h01 = __floats2half2_rn(lrelu_f(v[0], slope), lrelu_f(v[1], slope));
+        const __half2 h23 = __floats2half2_rn(lrelu_f(v[2], slope), lrelu_f(v[3], slope));
+        uint2 h;
+        h.x = *reinterpret_cast<const uint32_t *>(&h01);
+        h.y = *reinterpret_cast<const uint32_t *>(&h23);
+        y16[i] = h;
+    }
+}
+
+cudaError_t sum3_act_f16_launch(const float *a, const float *b, const float *c, float scale, float slope, size_t n, __half *y16,
+                                cudaStream_t st)
+{
+    if (n % 4) return cudaErrorInvalidValue;
+    const size_t n4 = n / 4;
+    int blocks = (int)std::min<size_t>((n4 + 255) / 256, (size_t)148 * 8);
+    if (blocks < 1) blocks = 1;
+    sum3_act_f16_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4 *>(a), reinterpret_cast<const float4 *>(b),
+                                               reinterpret_cast<const float4 *>(c), scale, slope, n4, reinterpret_cast<uint2 *>(y16));
+    return cudaGetLastError();
+}
+
 cudaError_t cvt_f16_launch(const float *x, int ldx, int ch_off, int C, size_t rows, __half *y16, cudaStream_t st)
 {
     if (C % 8) return cudaErrorInvalidValue;

@@ -215,6 +215,38 @@ __device__ __forceinline__ float4 f4_add(float4 a, float4 b)
     return make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z), __fadd_rn(a.w, b.w));
 }
 
+// NQ row pairs starting at row rb of the warp's 32-row slab (this thread: row rb + 2 q + rsel, 4 columns)
+template <int NQ>
+__device__ __forceinline__ void epilogue_rows(const ConvParams &p, const float *slab, int rb, int rsel, int cl, int oc, float4 bias,
+                                              int t_first, size_t seg_row0, const float4 (&rs)[NQ], const float4 (&ai)[NQ], const bool (&ok)[NQ])
+{
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        if (!ok[q]) continue;
+        const int t = t_first + rb + 2 * q + rsel;
+        const size_t orow = (seg_row0 + (size_t)t) * (size_t)p.out_mul + p.out_add;
+        float4 v = *reinterpret_cast<const float4 *>(slab + (rb + 2 * q + rsel) * SLAB_LD + cl);
+        if (p.bias) v = f4_add(v, bias);
+        if (p.res) v = f4_add(v, rs[q]);
+        if (p.acc_in) v = f4_add(ai[q], v);
+        if (p.has_scale) v = make_float4(__fmul_rn(v.x, p.scale), __fmul_rn(v.y, p.scale), __fmul_rn(v.z, p.scale), __fmul_rn(v.w, p.scale));
+        if (p.out32) *reinterpret_cast<float4 *>(p.out32 + orow * (size_t)p.ldo32 + p.o32_ch_off + oc) = v;
+        if (p.out16) {
+            uint2 h;
+            h.x = pack_half2(lrelu_f(v.x, p.out16_slope), lrelu_f(v.y, p.out16_slope));
+            h.y = pack_half2(lrelu_f(v.z, p.out16_slope), lrelu_f(v.w, p.out16_slope));
+            *reinterpret_cast<uint2 *>(p.out16 + orow * (size_t)p.ldo16 + p.o16_ch_off + oc) = h;
+        }
+    }
+}
+
+// DEEP (launches with a residual input and no running branch sum): the residual rows of a whole
+// 64-column pass (16 float4 per thread) are requested BEFORE the pass's accumulator columns are pulled
+// out of tensor memory and transposed, so their L2 / HBM latency is covered by that work instead of
+// being paid once per 8 rows (conv2-type launches were bound by exactly this: 4 warps x 4 loads in
+// flight, profiles/r01_launch_table_*).  It costs registers and code size, which the launches without a
+// residual (more co-resident CTAs, nothing to wait for) do not want: they keep the short loop.
+template <bool DEEP>
 __device__ __forceinline__ void epilogue_tile(const ConvParams &p, uint32_t trow, float *slab, int lane, int t_first, int seg_len,
                                               size_t seg_row0, int nchunk, int NC)
 {
@@ -222,6 +254,21 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams &p, uint32_t trow
     const int rsel = lane >> 4;             // which row of a row pair
     for (int col0 = 0; col0 < NC; col0 += EPI_COLS) {
         const int cw = min(EPI_COLS, NC - col0);
+        const int oc = nchunk * NC + col0 + cl;
+        float4 rsd[DEEP ? 16 : 1];
+        bool okd[DEEP ? 16 : 1];
+        if (DEEP) {
+#pragma unroll
+            for (int q = 0; q < (DEEP ? 16 : 1); ++q) {
+                const int t = t_first + 2 * q + rsel;
+                okd[q] = cl < cw && t < seg_len;
+                rsd[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (okd[q]) {
+                    const size_t orow = (seg_row0 + (size_t)t) * (size_t)p.out_mul + p.out_add;
+                    rsd[q] = *reinterpret_cast<const float4 *>(p.res + orow * (size_t)p.ldres + p.res_ch_off + oc);
+                }
+            }
+        }
         for (int cc = 0; cc < cw; cc += 16) {
             uint32_t r[16];
             tmem_ld16(trow + (uint32_t)(col0 + cc), r);
@@ -233,38 +280,28 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams &p, uint32_t trow
         }
         __syncwarp();
         if (cl < cw) {
-            const int oc = nchunk * NC + col0 + cl;
             float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
             if (p.bias) bias = __ldg(reinterpret_cast<const float4 *>(p.bias + oc));
-            for (int rb = 0; rb < 32; rb += 8) {
-                float4 rs[4], ai[4];
-                size_t orow[4];
-                bool ok[4];
+            if (DEEP) {
+                float4 aid[DEEP ? 16 : 1];      // (never read: DEEP launches have no acc_in)
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int t = t_first + rb + 2 * q + rsel;
-                    ok[q]   = t < seg_len;
-                    orow[q] = (seg_row0 + (size_t)t) * (size_t)p.out_mul + p.out_add;
-                    rs[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    ai[q] = rs[q];
-                    if (ok[q] && p.res) rs[q] = *reinterpret_cast<const float4 *>(p.res + orow[q] * (size_t)p.ldres + p.res_ch_off + oc);
-                    if (ok[q] && p.acc_in) ai[q] = *reinterpret_cast<const float4 *>(p.acc_in + orow[q] * (size_t)p.ldo32 + p.o32_ch_off + oc);
-                }
+                for (int q = 0; q < (DEEP ? 16 : 1); ++q) aid[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                epilogue_rows<DEEP ? 16 : 1>(p, slab, 0, rsel, cl, oc, bias, t_first, seg_row0, rsd, aid, okd);
+            } else {
+                for (int rb = 0; rb < 32; rb += 8) {
+                    float4 rs[4], ai[4];
+                    bool ok[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    if (!ok[q]) continue;
-                    float4 v = *reinterpret_cast<const float4 *>(slab + (rb + 2 * q + rsel) * SLAB_LD + cl);
-                    if (p.bias) v = f4_add(v, bias);
-                    if (p.res) v = f4_add(v, rs[q]);
-                    if (p.acc_in) v = f4_add(ai[q], v);
-                    if (p.has_scale) v = make_float4(__fmul_rn(v.x, p.scale), __fmul_rn(v.y, p.scale), __fmul_rn(v.z, p.scale), __fmul_rn(v.w, p.scale));
-                    if (p.out32) *reinterpret_cast<float4 *>(p.out32 + orow[q] * (size_t)p.ldo32 + p.o32_ch_off + oc) = v;
-                    if (p.out16) {
-                        uint2 h;
-                        h.x = pack_half2(lrelu_f(v.x, p.out16_slope), lrelu_f(v.y, p.out16_slope));
-                        h.y = pack_half2(lrelu_f(v.z, p.out16_slope), lrelu_f(v.w, p.out16_slope));
-                        *reinterpret_cast<uint2 *>(p.out16 + orow[q] * (size_t)p.ldo16 + p.o16_ch_off + oc) = h;
+                    for (int q = 0; q < 4; ++q) {
+                        const int t = t_first + rb + 2 * q + rsel;
+                        ok[q] = t < seg_len;
+                        const size_t orow = (seg_row0 + (size_t)t) * (size_t)p.out_mul + p.out_add;
+                        rs[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        ai[q] = rs[q];
+                        if (ok[q] && p.res) rs[q] = *reinterpret_cast<const float4 *>(p.res + orow * (size_t)p.ldres + p.res_ch_off + oc);
+                        if (ok[q] && p.acc_in) ai[q] = *reinterpret_cast<const float4 *>(p.acc_in + orow * (size_t)p.ldo32 + p.o32_ch_off + oc);
                     }
+                    epilogue_rows<4>(p, slab, rb, rsel, cl, oc, bias, t_first, seg_row0, rs, ai, ok);
                 }
             }
         }
@@ -273,7 +310,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams &p, uint32_t trow
 }
 
 // ------------------------------------------------------------------ the kernel
-template <int MODE, int MT>
+template <int MODE, int MT, bool DEEP>
 __global__ void __launch_bounds__(128 * MT + 64) conv_umma_kernel(const ConvParams p)
 {
     constexpr int N_PRODUCERS = 128 * MT;
@@ -359,7 +396,7 @@ __global__ void __launch_bounds__(128 * MT + 64) conv_umma_kernel(const ConvPara
         // every MMA has completed (acc_full), so the operand stages are dead: their memory is the slab
         const int  mt    = warp >> 2;                       // M-tile this warp drains
         const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)mt * acc_stride;
-        epilogue_tile(p, trow, reinterpret_cast<float *>(smem + SMEM_HEADER + (size_t)warp * SLAB_BYTES), lane,
+        epilogue_tile<DEEP>(p, trow, reinterpret_cast<float *>(smem + SMEM_HEADER + (size_t)warp * SLAB_BYTES), lane,
                       t0 + mt * TILE_M + (warp & 3) * 32, seg_len, seg_row0, nchunk, NC);
     } else if (warp == MMA_WARP) {
         // =================== MMA issuer (one elected lane of a converged warp) ===================
@@ -444,7 +481,7 @@ __global__ void __launch_bounds__(128 * MT + 64) conv_umma_kernel(const ConvPara
 // whole epilogue.)
 constexpr int PK_THREADS = 320;
 
-template <int MODE>
+template <int MODE, bool DEEP>
 __global__ void __launch_bounds__(PK_THREADS, 1) conv_umma_pk_kernel(const ConvParams p, const int total_tiles, const int nchunks)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -540,7 +577,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) conv_umma_pk_kernel(const ConvP
             mbar_wait(smem_u32(acc_full + buf), (uint32_t)(n >> 1) & 1u, p.err_flag);
             tc_fence_after_sync();
             const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)buf * acc_stride;
-            epilogue_tile(p, trow, slab, lane, tc.t0 + (warp & 3) * 32, tc.seg_len, tc.seg_row0, tc.nchunk, NC);
+            epilogue_tile<DEEP>(p, trow, slab, lane, tc.t0 + (warp & 3) * 32, tc.seg_len, tc.seg_row0, tc.nchunk, NC);
             tc_fence_before_sync();
             mbar_arrive(smem_u32(acc_empty + buf));
         }
@@ -691,7 +728,8 @@ static cudaError_t launch_pk(const ConvParams &p, int total_tiles, int num_sms, 
     const int nchunks = p.Cout / p.NC;
     const int items = total_tiles * nchunks;
     const int grid = items < num_sms ? items : num_sms;
-    conv_umma_pk_kernel<MODE><<<grid, PK_THREADS, smem, st>>>(p, total_tiles, nchunks);
+    if (p.res && !p.acc_in) conv_umma_pk_kernel<MODE, true><<<grid, PK_THREADS, smem, st>>>(p, total_tiles, nchunks);
+    else conv_umma_pk_kernel<MODE, false><<<grid, PK_THREADS, smem, st>>>(p, total_tiles, nchunks);
     return cudaGetLastError();
 }
 
@@ -713,7 +751,8 @@ template <int MODE, int MT>
 static cudaError_t launch_mode(const ConvParams &p, int total_tiles, size_t smem, cudaStream_t st)
 {
     dim3 grid(total_tiles, p.Cout / p.NC, 1);
-    conv_umma_kernel<MODE, MT><<<grid, 128 * MT + 64, smem, st>>>(p);
+    if (p.res && !p.acc_in) conv_umma_kernel<MODE, MT, true><<<grid, 128 * MT + 64, smem, st>>>(p);
+    else conv_umma_kernel<MODE, MT, false><<<grid, 128 * MT + 64, smem, st>>>(p);
     return cudaGetLastError();
 }
 
@@ -722,9 +761,12 @@ static cudaError_t init_mode()
 {
     cudaError_t e;
     const int kMax = 227 * 1024;
-    if ((e = cudaFuncSetAttribute(conv_umma_pk_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(conv_umma_kernel<MODE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax)) != cudaSuccess) return e;
-    return cudaFuncSetAttribute(conv_umma_kernel<MODE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
+    if ((e = cudaFuncSetAttribute(conv_umma_pk_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(conv_umma_pk_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(conv_umma_kernel<MODE, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(conv_umma_kernel<MODE, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(conv_umma_kernel<MODE, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax)) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(conv_umma_kernel<MODE, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
 }
 
 cudaError_t conv_umma_init()

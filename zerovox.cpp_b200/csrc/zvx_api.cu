@@ -932,19 +932,31 @@ int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out)
             if (vin2) { u.pro_mode = PRO_SUM3; u.x2 = vin2; u.x3 = vin3; u.sum_scale = third; }
             u.flops = 2.0 * (double)ctx->last_frames * ctx->rates[i] * s * ch * cin * (ctx->up[i].K / s);
             if (run_conv(ctx, u)) return 1;
-        } else
-        for (int phi = 0; phi < s; ++phi) {
-            ConvCall u; u.kind = ZVX_K_UPCONV; u.stage = i; u.L = &ctx->up[i]; u.variant = phi; u.x = vin; u.ldx = cin; u.rate_idx = i;
-            u.pro_mode = PRO_LRELU; u.pro_slope = 0.1f; u.out32 = ctx->U; u.ldo32 = ch; u.out_mul = s;
-            if (vin2) { u.pro_mode = PRO_SUM3; u.x2 = vin2; u.x3 = vin3; u.sum_scale = third; }
-            if (run_conv(ctx, u)) return 1;
+        } else {
+            const bool pre = vin2 && !ctx->use_ref_kernels;
+            if (pre) {
+                // one pass makes the fp16 operand lrelu(mean of the 3 branches) for all s phase launches
+                const size_t n = (size_t)ctx->last_frames * ctx->rates[i] * cin;
+                ctx->launches++;
+                if (prof_begin(ctx, ZVX_K_NORM_AFFINE, i, 0.0, 14.0 * (double)n)) return 1;
+                CK(ctx, sum3_act_f16_launch(vin, vin2, vin3, third, 0.1f, n, ctx->H16, ctx->stream));
+                if (prof_end(ctx)) return 1;
+            }
+            for (int phi = 0; phi < s; ++phi) {
+                ConvCall u; u.kind = ZVX_K_UPCONV; u.stage = i; u.L = &ctx->up[i]; u.variant = phi; u.x = vin; u.ldx = cin; u.rate_idx = i;
+                u.pro_mode = PRO_LRELU; u.pro_slope = 0.1f; u.out32 = ctx->U; u.ldo32 = ch; u.out_mul = s;
+                if (pre) { u.x = ctx->H16; u.pro_mode = PRO_F16; }
+                else if (vin2) { u.pro_mode = PRO_SUM3; u.x2 = vin2; u.x3 = vin3; u.sum_scale = third; }
+                if (run_conv(ctx, u)) return 1;
+            }
         }
         // MRF: three residual blocks on U, averaged (hifigan.cpp:300-315, :97-183).  When all three run as
         // fused chains, each writes its own output buffer and the branch sum / average is applied by the
         // consumer (next up-conv or the output conv, PRO_SUM3): the fused kernel's final phase is then pure
         // stores instead of a read-modify-write of the running sum.
-        bool split = ctx->branch_sum_in_consumer && ctx->use_fused && !ctx->use_ref_kernels && nb == 3;
-        for (int j = 0; j < nb; ++j) split = split && ctx->fused[(size_t)i * nb + j].CH != 0;
+        // The per-conv path (stage 0, 256 channels) does the same: block j keeps its residual stream in
+        // branch buffer j, so no conv epilogue reads a running sum.
+        const bool split = ctx->branch_sum_in_consumer && !ctx->use_ref_kernels && nb == 3;
         float *branch_out[3] = {ctx->CS, ctx->VA, ctx->VB};
         for (int j = 0; j < nb; ++j) {
             const FusedBlock &fb = ctx->fused[(size_t)i * nb + j];
@@ -993,7 +1005,7 @@ int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out)
                 }
                 continue;
             }
-            float *Y = (j == 0) ? ctx->CS : ctx->Y1;
+            float *Y = split ? branch_out[j] : (j == 0) ? ctx->CS : ctx->Y1;
             for (int d = 0; d < nd; ++d) {
                 const size_t idx = ((size_t)i * nb + j) * nd + d;
                 const float *yin = d == 0 ? ctx->U : Y;
@@ -1004,7 +1016,7 @@ int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out)
                 ConvCall c2; c2.kind = ZVX_K_MRF_CONV; c2.stage = i; c2.L = &ctx->mrf2[idx]; c2.x = ctx->H16; c2.ldx = ch; c2.rate_idx = i + 1; c2.pro_mode = PRO_F16;
                 c2.res = yin; c2.ldres = ch;
                 const bool last = d == nd - 1;
-                if (last && j > 0) {
+                if (last && j > 0 && !split) {
                     c2.acc_in = ctx->CS;                       // cs = cs + y_j
                     if (j == nb - 1) { c2.scale = third; c2.out32 = vout[i & 1]; }   // c = cs / num_blocks
                     else c2.out32 = ctx->CS;
