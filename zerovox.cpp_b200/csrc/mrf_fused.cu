@@ -133,7 +133,8 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
     uint64_t *w_full    = bars;                        // [F_MAX_SLOTS]
     uint64_t *w_empty   = bars + F_MAX_SLOTS;          // [F_MAX_SLOTS]
     uint64_t *acc_full  = bars + 2 * F_MAX_SLOTS;
-    uint64_t *act_ready = bars + 2 * F_MAX_SLOTS + 1;
+    uint64_t *act_ready = bars + 2 * F_MAX_SLOTS + 1;   // a layer's whole input is in shared memory
+    uint64_t *act_half  = bars + 2 * F_MAX_SLOTS + 2;   // ... its even 16-channel K-steps are (see the MMA issuer)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 256);
     const uint32_t OFF_TBL = F_HEADER + C::seg_bytes(p.B);
     const int *seg_s    = reinterpret_cast<const int *>(smem + F_HEADER);      // [B + 1] seg_start, [B + 1] win_start
@@ -212,6 +213,7 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
         }
         mbar_init(smem_u32(acc_full), 1);
         mbar_init(smem_u32(act_ready), C::EPI);
+        mbar_init(smem_u32(act_half), C::EPI);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == EPI_WARPS) tmem_alloc(smem_u32(tmem_slot), 2u * NCOL);
@@ -338,7 +340,16 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
             if (dbg) c_st += clock64() - c_l0;
 #endif
         };
-        auto publish = [&]() {
+        auto publish_half = [&]() {
+            tc_fence_before_sync();
+            mbar_arrive(smem_u32(act_half));
+        };
+        auto publish = [&]() {       // both barriers: everything this thread had to write is written
+            tc_fence_before_sync();
+            mbar_arrive(smem_u32(act_half));
+            mbar_arrive(smem_u32(act_ready));
+        };
+        auto publish_rest = [&]() {  // after publish_half
             tc_fence_before_sync();
             mbar_arrive(smem_u32(act_ready));
         };
@@ -408,7 +419,15 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
                                 const uint32_t e = tb[8 * (2 * pr + (mi >> 1)) + r8];
                                 stmatrix_x4_trans(gbase + e * 16u, f[0], f[1], f[2], f[3]);
                             }
+                            if (lh == 0) {
+                                // rows [rb, rb + 16) of every lane quarter = the even K-steps of the next layer's
+                                // operand: its MMAs over those start while the odd half is still being drained
+                                fence_proxy_async_smem();
+                                publish_half();
+                            }
                         }
+                        fence_proxy_async_smem();
+                        publish_rest();
                     } else {
                         const float bias = __ldg(L.bias + oc);
                         const uint32_t *tb = L.tbl + s * NCOL;              // full entries from global
@@ -427,9 +446,9 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
                                 if (e & mrf::TBL_VALID) *reinterpret_cast<__half *>(dst + mrf::tbl_byte(e)) = __float2half_rn(v);
                             }
                         }
+                        fence_proxy_async_smem();
+                        publish();
                     }
-                    fence_proxy_async_smem();
-                    publish();
                     if (dbg) c_drain += clock64() - c_a;
                 } else {
                     // final: y (+ running branch sum) (* 1/num_blocks) -> global fp32.  Both 32-column
@@ -528,12 +547,17 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
                 const uint32_t lbo_a = (uint32_t)mrf::tap_blocks(k, S) * CH * 16u;
                 const uint32_t ibuf  = (l & 1) ? buf1 : buf0;
                 const uint32_t dcol  = tmem_base + (L.accumulate ? ycol(iter) : hcol(iter));
-                if (dbg) c_a = clock64();
-                mbar_wait(smem_u32(act_ready), (uint32_t)(iter * nl + l) & 1u, p.err_flag);
-                tc_fence_after_sync();
-                if (dbg) c_act += clock64() - c_a;
+                // K-steps in the order even, then odd: the epilogue warps publish the even ones (first 16-lane
+                // half of every lane quarter) before they drain the odd ones
 #pragma unroll 1
-                for (int c = 0; c < G::KSTEPS; ++c, ++it) {
+                for (int ci = 0; ci < G::KSTEPS; ++ci, ++it) {
+                    const int c = ci < G::KSTEPS / 2 ? 2 * ci : 2 * (ci - G::KSTEPS / 2) + 1;
+                    if (ci == 0 || ci == G::KSTEPS / 2) {
+                        if (dbg) c_a = clock64();
+                        mbar_wait(smem_u32(ci == 0 ? act_half : act_ready), (uint32_t)(iter * nl + l) & 1u, p.err_flag);
+                        tc_fence_after_sync();
+                        if (dbg) c_act += clock64() - c_a;
+                    }
                     const int slot = it % nslots;
                     const uint32_t ph = (uint32_t)(it / nslots) & 1u;
                     if (dbg) c_a = clock64();
@@ -549,7 +573,7 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
                             mrf::b_step(k, S, j, q, ro);
                             const uint64_t adesc = make_smem_desc(a_slot + (uint32_t)mrf::a_block(k, S, j) * (CH * 16u), lbo_a, 128u);
                             const uint64_t bdesc = make_smem_desc(b_c + (uint32_t)q * G::SUB + (uint32_t)(ro * 16), LBO_B, 128u);
-                            umma_f16(dcol, adesc, bdesc, idesc, (L.accumulate || c > 0 || j > 0) ? 1u : 0u);
+                            umma_f16(dcol, adesc, bdesc, idesc, (L.accumulate || ci > 0 || j > 0) ? 1u : 0u);
                         }
                         umma_commit(smem_u32(w_empty + slot));
                     }
@@ -586,7 +610,8 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
                 for (int l = 0; l < nl; ++l) {
                     const mrf::Layer &L = p.L[l];
                     const uint32_t bytes = mrf::chunk_bytes(L.k, S, CH);
-                    for (int c = 0; c < G::KSTEPS; ++c, ++it) {
+                    for (int ci = 0; ci < G::KSTEPS; ++ci, ++it) {
+                        const int c = ci < G::KSTEPS / 2 ? 2 * ci : 2 * (ci - G::KSTEPS / 2) + 1;   // the issuer's order
                         const int slot = it % nslots;
                         const uint32_t ph = (uint32_t)(it / nslots) & 1u;
                         mbar_wait(smem_u32(w_empty + slot), ph ^ 1u, p.err_flag);
