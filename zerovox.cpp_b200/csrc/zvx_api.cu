@@ -99,6 +99,7 @@ struct zvx_ctx {
     int fused_persistent = 1;
     int fused_flags = 0;
     int conv_persistent = 1;
+    int conv_smem_kb = 100;   // shared-memory budget of a one-tile conv CTA (two CTAs per SM)
     int conv_mt2 = 0;   // two M-tiles per CTA: measured slower on B200 while the A producer is the limit (profiles/)
     std::vector<int> tile256_cfg;                 // per rate index: wincfg entry of the 256-row tiling
     int num_sms = 148;
@@ -766,7 +767,7 @@ int run_conv(zvx_ctx *ctx, const ConvCall &cc)
             if (smem > 227 * 1024) return fail(ctx, "conv needs %zu bytes of shared memory", smem);
             CK(ctx, conv_umma_pk_launch(p, tiles, ctx->num_sms, smem, ctx->stream));
         } else {
-            const size_t smem = conv_umma_plan(p, p.mt == 2 ? 226 * 1024 : 100 * 1024);
+            const size_t smem = conv_umma_plan(p, p.mt == 2 ? 226 * 1024 : (size_t)ctx->conv_smem_kb * 1024);
             if (smem > 227 * 1024) return fail(ctx, "conv needs %zu bytes of shared memory", smem);
             CK(ctx, conv_umma_launch(p, tiles, smem, ctx->stream));
         }
@@ -1175,6 +1176,7 @@ int zvx_create(zvx_ctx **out, const zvx_config *cfg, const zvx_tensor_desc *weig
     if (const char *e = getenv("ZVX_DEC_PREPASS")) ctx->dec_prepass = atoi(e);
     if (const char *e = getenv("ZVX_BRANCH_SUM_IN_CONSUMER")) ctx->branch_sum_in_consumer = atoi(e);
     if (const char *e = getenv("ZVX_CONV_MT2")) ctx->conv_mt2 = atoi(e);
+    if (const char *e = getenv("ZVX_CONV_SMEM_KB")) ctx->conv_smem_kb = atoi(e);
     if (const char *e = getenv("ZVX_CONV_PERSISTENT")) ctx->conv_persistent = atoi(e);
     if (const char *e = getenv("ZVX_FUSED_UPCONV")) ctx->use_fused_upconv = atoi(e);
     ctx->num_sms = prop.multiProcessorCount;
