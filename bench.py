@@ -274,6 +274,22 @@ def main():
     e2e_value = total_audio * args.steps / t_e2e
     checksum = float(h_wav[:: 997].double().abs().sum())
 
+    # same, with the reference's write_wav_file conversion (float -> PCM_16, zerovox.cpp:357-371) done by the output
+    # conv on the GPU: zvx_synth_batch_pcm16, half the device -> host bytes (extra key, the headline stays `e2e`)
+    h_pcm = torch.empty(F * ctx.hop, dtype=torch.int16).pin_memory()
+    pp = (vp * B)(*[h_pcm.data_ptr() + int(offs[b]) * ctx.hop * 2 for b in range(B)])
+    for _ in range(max(1, args.warmup)):
+        ctx.synth_batch_pcm16_ptrs(B, pe, ps, Larr, pp)
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.synth_batch_pcm16_ptrs(B, pe, ps, Larr, pp)
+    t_pcm = max_over_ranks(time.perf_counter() - t0)
+    e2e_pcm = {"value": total_audio * args.steps / t_pcm, "unit": UNIT,
+               "h2d_bytes_per_step": int(F * ctx.dim_in * 4 + B * ctx.style_dim * 4), "d2h_bytes_per_step": int(F * ctx.hop * 2),
+               "pcm_checksum": int(h_pcm[:: 997].long().abs().sum())}
+
     # ---------------- roofline of the dominant kernel ----------------
     peak_tf, peak_gbs, peak_src = measured_peaks()
     by = {}
@@ -315,6 +331,7 @@ def main():
            "clocks": clk, "gpu_launches": launches,
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(F * ctx.dim_in * 4 + B * ctx.style_dim * 4),
                    "d2h_bytes_per_step": int(F * ctx.hop * 4), "wav_checksum": checksum},
+           "e2e_pcm16": e2e_pcm,
            "roofline": roofline, "kernel_breakdown": breakdown,
            "audio_s_per_step_per_gpu": audio_s}
 

@@ -85,6 +85,24 @@ int zvx_vocode(zvx_ctx *ctx, const float *mel, int32_t L, float *wav);
 int zvx_synth_batch(zvx_ctx *ctx, int32_t B, const float *const *enc_seq, const float *const *style,
                     const int32_t *L, float *const *mel, float *const *wav);
 
+/* Output stage: the waveform leaves the GPU as signed 16-bit PCM.
+ * Replaces, for the batch, the float -> short conversion libsndfile performs inside
+ * sf_write_float() when ZeroVOXModel::write_wav_file writes its SF_FORMAT_PCM_16 file
+ * (/root/reference/src/zerovox.cpp:357-371; libsndfile src/pcm.c f2s_array, default
+ * normalisation, clipping off: lrintf(x * 0x7FFF)).  The conversion is fused into the output
+ * conv's tanh epilogue, so the device -> host copy is half the size of zvx_synth_batch's.
+ * pcm[b] receives L[b]*hop_size samples; other arguments as zvx_synth_batch. */
+int zvx_synth_batch_pcm16(zvx_ctx *ctx, int32_t B, const float *const *enc_seq, const float *const *style,
+                          const int32_t *L, float *const *mel, int16_t *const *pcm);
+
+/* HiFiGAN::eval (hifigan.cpp:358-377) + the same conversion: mel [L][num_mels] -> pcm [L*hop_size]. */
+int zvx_vocode_pcm16(zvx_ctx *ctx, const float *mel, int32_t L, int16_t *pcm);
+
+/* Replaces sf_open / sf_write / sf_close of ZeroVOXModel::write_wav_file (zerovox.cpp:354-384) for
+ * its one format, mono SF_FORMAT_WAV | SF_FORMAT_PCM_16: a canonical 44-byte RIFF header followed by
+ * little-endian samples.  Host only (no ctx, no GPU).  Returns 0 on success. */
+int zvx_write_wav_pcm16(const char *path, const int16_t *pcm, int64_t n_samples, int32_t sample_rate);
+
 /* Batched HiFiGAN::eval (hifigan.cpp:358-377) for B independent mels; HOST pointers. */
 int zvx_vocode_batch(zvx_ctx *ctx, int32_t B, const float *const *mel, const int32_t *L, float *const *wav);
 

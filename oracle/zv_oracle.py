@@ -197,3 +197,26 @@ def snr_db(ref: np.ndarray, test: np.ndarray) -> float:
     if den == 0.0:
         return float("inf")
     return float(10.0 * np.log10(float((ref * ref).sum()) / den))
+
+
+# ---------------------------------------------------------------------------------------------
+# Output stage.  The reference hands its float waveform to libsndfile
+# (/root/reference/src/zerovox.cpp:354-371: SF_FORMAT_WAV | SF_FORMAT_PCM_16, sf_write_float).
+# libsndfile is an UNVENDORED, UNPINNED system dependency of the reference (CMakeLists.txt:7-8,
+# find_package(SndFile)) and is absent from this image, so its published algorithm is restated:
+# src/pcm.c f2s_array -- with the defaults SFC_SET_NORM_FLOAT = SF_TRUE and SFC_SET_CLIPPING =
+# SF_FALSE a float sample becomes lrintf(x * 0x7FFF) (round half to even in the default rounding
+# mode); src/wav.c writes, for plain PCM, "RIFF" <36 + data bytes> "WAVE" "fmt " <16> {format 1,
+# channels, rate, rate * block align, block align, 16 bits} "data" <bytes> and little-endian samples.
+# Pinned by tests/test_oracle_cpu.py against Python's own `wave` module and a hand-written vector.
+def pcm16(wav):
+    return np.rint(np.asarray(wav, np.float32) * np.float32(32767.0)).astype(np.int16)
+
+
+def wav_file_bytes(pcm, sample_rate):
+    import struct
+    pcm = np.asarray(pcm, np.int16)
+    data = pcm.astype("<i2").tobytes()
+    hdr = b"RIFF" + struct.pack("<I", 36 + len(data)) + b"WAVE" + b"fmt " + struct.pack("<IHHIIHH", 16, 1, 1, sample_rate,
+                                                                                         2 * sample_rate, 2, 16)
+    return hdr + b"data" + struct.pack("<I", len(data)) + data

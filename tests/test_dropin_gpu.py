@@ -31,6 +31,12 @@ def test_reference_load_sequence_with_b200_classes(zvx, gguf_path, tmp_path):
     wav = np.fromfile(tmp_path / "out.wav.f32", np.float32)
     assert zv_oracle.snr_db(g["mel"], mel) >= 55.0
     assert zv_oracle.snr_db(g["wav"], wav) >= 60.0 and np.abs(wav - g["wav"]).max() <= 1e-3
+    # write_wav_file stage (zerovox.cpp:337-391): PCM_16 WAV of the same waveform, libsndfile's conversion
+    import wave
+    with wave.open(str(tmp_path / "out.wav")) as w:
+        assert (w.getnchannels(), w.getsampwidth(), w.getframerate(), w.getnframes()) == (1, 2, 24000, L * 300)
+        pcm = np.frombuffer(w.readframes(w.getnframes()), "<i2")
+    assert np.array_equal(pcm, zv_oracle.pcm16(wav))
 
 
 def test_missing_tensor_throws_like_checked_get_tensor(zvx, tmp_path):

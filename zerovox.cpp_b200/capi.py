@@ -55,6 +55,7 @@ EXPORTS = [
     "zvx_synth_batch", "zvx_synth_batch_device", "zvx_vocode_batch_device", "zvx_stream", "zvx_synchronize",
     "zvx_kernel_launches", "zvx_reserve", "zvx_set_debug_kernels", "zvx_test_conv", "zvx_debug_fetch",
     "zvx_set_debug_stop", "zvx_profile_begin", "zvx_profile_end", "zvx_set_fused_mrf", "zvx_vocode_batch", "zvx_vocode_chunked",
+    "zvx_synth_batch_pcm16", "zvx_vocode_pcm16", "zvx_write_wav_pcm16",
 ]
 
 _lib = None
@@ -86,6 +87,12 @@ def load_library() -> C.CDLL:
     lib.zvx_synth_batch.restype = i32
     lib.zvx_vocode_batch.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(i32), C.POINTER(vp)]
     lib.zvx_vocode_batch.restype = i32
+    lib.zvx_synth_batch_pcm16.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(i32), C.POINTER(vp), C.POINTER(vp)]
+    lib.zvx_synth_batch_pcm16.restype = i32
+    lib.zvx_vocode_pcm16.argtypes = [vp, vp, i32, vp]
+    lib.zvx_vocode_pcm16.restype = i32
+    lib.zvx_write_wav_pcm16.argtypes = [C.c_char_p, vp, i64, i32]
+    lib.zvx_write_wav_pcm16.restype = i32
     lib.zvx_vocode_chunked.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp]
     lib.zvx_vocode_chunked.restype = i32
     lib.zvx_synth_batch_device.argtypes = [vp, i32, vp, vp, C.POINTER(i32), vp, vp, i32]
@@ -116,6 +123,13 @@ def load_library() -> C.CDLL:
     lib.zvx_profile_end.restype = i64
     _lib = lib
     return lib
+
+
+def write_wav_pcm16(path: str, pcm: np.ndarray, sample_rate: int) -> None:
+    """zvx_write_wav_pcm16: mono 16-bit RIFF/WAVE file (host only)."""
+    pcm = np.ascontiguousarray(pcm, np.int16)
+    if load_library().zvx_write_wav_pcm16(os.fsencode(path), pcm.ctypes.data, pcm.size, int(sample_rate)) != 0:
+        raise ZvxError(f"cannot write {path}")
 
 
 class ZvxError(RuntimeError):
@@ -235,6 +249,29 @@ class Context:
         pw = (vp * B)(*[w.ctypes.data for w in wavs])
         self._check(self.lib.zvx_synth_batch(self.h, B, pe, ps, Ls, pm, pw))
         return mels, wavs
+
+    def synth_batch_pcm16(self, enc_list: Sequence[np.ndarray], style_list: Sequence[np.ndarray]):
+        """Like synth_batch, but the waveforms come back as int16 PCM (zvx_synth_batch_pcm16)."""
+        B = len(enc_list)
+        encs = [np.ascontiguousarray(e, np.float32) for e in enc_list]
+        stys = [np.ascontiguousarray(s, np.float32) for s in style_list]
+        Ls = (C.c_int32 * B)(*[e.shape[0] for e in encs])
+        pcms = [np.empty(e.shape[0] * self.hop, np.int16) for e in encs]
+        vp = C.c_void_p
+        pe = (vp * B)(*[e.ctypes.data for e in encs])
+        ps = (vp * B)(*[s.ctypes.data for s in stys])
+        pp = (vp * B)(*[w.ctypes.data for w in pcms])
+        self._check(self.lib.zvx_synth_batch_pcm16(self.h, B, pe, ps, Ls, None, pp))
+        return pcms
+
+    def synth_batch_pcm16_ptrs(self, B: int, enc_ptrs, style_ptrs, lengths, pcm_ptrs):
+        self._check(self.lib.zvx_synth_batch_pcm16(self.h, B, enc_ptrs, style_ptrs, lengths, None, pcm_ptrs))
+
+    def vocode_pcm16(self, mel: np.ndarray) -> np.ndarray:
+        mel = np.ascontiguousarray(mel, np.float32)
+        pcm = np.empty(mel.shape[0] * self.hop, np.int16)
+        self._check(self.lib.zvx_vocode_pcm16(self.h, mel.ctypes.data, mel.shape[0], pcm.ctypes.data))
+        return pcm
 
     def synth_batch_ptrs(self, B: int, enc_ptrs, style_ptrs, lengths, mel_ptrs, wav_ptrs):
         """Raw-pointer form (host pointers as ints) for bench.py: no numpy allocation in the timed region."""

@@ -295,6 +295,16 @@ cudaError_t norm_act_f16_launch(const float *x, int ldx, int ch_off, int C, cons
 // on the CUDA cores.  A block stages (128 + K - 1) activated, fp16-rounded rows in shared
 // memory (row stride C+1 floats: conflict-free), one thread per output sample.
 // ---------------------------------------------------------------------------------
+// One output sample: float (what HiFiGAN::eval returns, hifigan.cpp:374-376) and / or signed 16-bit PCM, i.e. the
+// conversion libsndfile applies inside sf_write_float() for SF_FORMAT_PCM_16 (the reference's write_wav_file,
+// zerovox.cpp:357-371; libsndfile src/pcm.c f2s_array with the default SFC_SET_NORM_FLOAT = true and clipping
+// off: lrintf(x * 0x7FFF), round-half-even).  |tanh| <= 1, so the product is always in range.
+__device__ __forceinline__ void store_sample(float v, size_t i, float *__restrict__ wav, int16_t *__restrict__ pcm)
+{
+    if (wav) wav[i] = v;
+    if (pcm) pcm[i] = (int16_t)__float2int_rn(__fmul_rn(v, 32767.0f));
+}
+
 constexpr int OC_MAX_C = 64;
 constexpr int OC_MAX_K = 16;
 
@@ -304,7 +314,7 @@ __global__ void __launch_bounds__(128) out_conv_kernel(const float *__restrict__
                                                        const __half *__restrict__ w_raw, const float *__restrict__ bias,
                                                        float slope, const int *__restrict__ seg_start,
                                                        const int *__restrict__ tile_start, int B, int rate,
-                                                       float *__restrict__ wav)
+                                                       float *__restrict__ wav, int16_t *__restrict__ pcm)
 {
     extern __shared__ float sm[];
     float *ws   = sm;                           // [K][C]
@@ -341,7 +351,7 @@ __global__ void __launch_bounds__(128) out_conv_kernel(const float *__restrict__
         const float *wk = ws + k * C;
         for (int c = 0; c < C; ++c) acc = fmaf(row[c], wk[c], acc);
     }
-    wav[row0 + t] = tanhf(__fadd_rn(acc, __ldg(bias)));
+    store_sample(tanhf(__fadd_rn(acc, __ldg(bias))), row0 + t, wav, pcm);
 }
 
 // The shipped shape (32 channels, 7 taps): the 224 weights travel as a kernel parameter, i.e. in the
@@ -353,7 +363,7 @@ __global__ void __launch_bounds__(128) out_conv_32x7_kernel(const float *__restr
                                                             const float *__restrict__ x3, float sum_scale, const OutConvW W, float slope,
                                                             const int *__restrict__ seg_start,
                                                             const int *__restrict__ tile_start, int B, int rate,
-                                                            float *__restrict__ wav)
+                                                            float *__restrict__ wav, int16_t *__restrict__ pcm)
 {
     constexpr int C = 32, K = 7, ROWS = 128 + K - 1, LD = C + 1;
     __shared__ float tile[ROWS * LD];
@@ -398,23 +408,23 @@ __global__ void __launch_bounds__(128) out_conv_32x7_kernel(const float *__restr
             acc1 = fmaf(row[k * LD + c + 1], W.w[k * C + c + 1], acc1);
         }
     }
-    wav[row0 + t] = tanhf(__fadd_rn(__fadd_rn(acc0, acc1), W.bias));
+    store_sample(tanhf(__fadd_rn(__fadd_rn(acc0, acc1), W.bias)), row0 + t, wav, pcm);
 }
 
 cudaError_t out_conv_launch(const float *x, const float *x2, const float *x3, float sum_scale, int C, int K, const __half *w_raw, const float *bias, const float *w_host_kc,
                             float bias_host, float slope, const int *seg_start, const int *tile_start, int B, int rate,
-                            int total_tiles, float *wav, cudaStream_t st)
+                            int total_tiles, float *wav, int16_t *pcm, cudaStream_t st)
 {
     if (C == 32 && K == 7 && w_host_kc) {
         OutConvW W;
         for (int i = 0; i < 7 * 32; ++i) W.w[i] = w_host_kc[i];
         W.bias = bias_host;
-        out_conv_32x7_kernel<<<total_tiles, 128, 0, st>>>(x, x2, x3, sum_scale, W, slope, seg_start, tile_start, B, rate, wav);
+        out_conv_32x7_kernel<<<total_tiles, 128, 0, st>>>(x, x2, x3, sum_scale, W, slope, seg_start, tile_start, B, rate, wav, pcm);
         return cudaGetLastError();
     }
     if (C > OC_MAX_C || K > OC_MAX_K) return cudaErrorInvalidValue;
     const size_t smem = (OC_MAX_K * OC_MAX_C + (128 + OC_MAX_K) * (OC_MAX_C + 1)) * sizeof(float);
-    out_conv_kernel<<<total_tiles, 128, smem, st>>>(x, x2, x3, sum_scale, C, K, w_raw, bias, slope, seg_start, tile_start, B, rate, wav);
+    out_conv_kernel<<<total_tiles, 128, smem, st>>>(x, x2, x3, sum_scale, C, K, w_raw, bias, slope, seg_start, tile_start, B, rate, wav, pcm);
     return cudaGetLastError();
 }
 

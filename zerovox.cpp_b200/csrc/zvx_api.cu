@@ -907,7 +907,7 @@ int run_decoder(zvx_ctx *ctx, float *mel_out)
 }
 
 // ---------------------------------------------------------------- vocoder schedule
-int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out)
+int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out, int16_t *pcm_out = nullptr)
 {
     const zvx_config &c = ctx->cfg;
     const int nb = c.num_resblocks, nd = c.num_resblock_dilations;
@@ -1044,7 +1044,7 @@ int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out)
     CK(ctx, out_conv_launch(vin, vin2, vin3, third, ctx->chans[last], ctx->output_conv.K, ctx->output_conv.raw, ctx->output_conv.bias,
                             ctx->out_w_kc.empty() ? nullptr : ctx->out_w_kc.data(), ctx->out_b_host, 0.01f,
                             ctx->d_seg, ctx->d_tiles + (size_t)last * (ctx->cap_batch + 1), ctx->last_B, ctx->rates[last],
-                            ctx->total_tiles[last], wav_out, ctx->stream));
+                            ctx->total_tiles[last], wav_out, pcm_out, ctx->stream));
     return prof_end(ctx);
 }
 
@@ -1326,8 +1326,9 @@ int zvx_vocode_batch_device(zvx_ctx *ctx, int32_t B, const float *d_mel, const i
 }
 
 // one sub-batch [b0, b1) of zvx_synth_batch on context / lane `c`, everything asynchronous on c->stream
+// (wav: float samples; or pcm: 16-bit samples converted by the output conv itself, staged in the same device buffer)
 static int synth_chunk(zvx_ctx *c, int b0, int b1, const float *const *enc_seq, const float *const *style, const int32_t *L,
-                       float *const *mel, float *const *wav)
+                       float *const *mel, float *const *wav, int16_t *const *pcm = nullptr)
 {
     zvx_ctx *ctx = c;
     const zvx_config &cfg = c->cfg;
@@ -1349,6 +1350,17 @@ static int synth_chunk(zvx_ctx *c, int b0, int b1, const float *const *enc_seq, 
         b = e;
     }
     if (run_decoder(c, c->mel)) return 1;
+    if (pcm) {
+        int16_t *d_pcm = reinterpret_cast<int16_t *>(c->wav);
+        if (run_vocoder(c, c->mel, nullptr, d_pcm)) return 1;
+        for (int b = 0; b < n;) {
+            int e = b + 1;
+            while (e < n && pcm[b0 + e] == pcm[b0 + e - 1] + (size_t)L[b0 + e - 1] * cfg.hop_size) ++e;
+            CK(ctx, cudaMemcpyAsync(pcm[b0 + b], d_pcm + (size_t)c->h_seg[b] * cfg.hop_size,
+                                    sizeof(int16_t) * (size_t)(c->h_seg[e] - c->h_seg[b]) * cfg.hop_size, cudaMemcpyDeviceToHost, c->stream));
+            b = e;
+        }
+    } else {
     if (run_vocoder(c, c->mel, c->wav)) return 1;
     for (int b = 0; b < n;) {
         int e = b + 1;
@@ -1357,6 +1369,7 @@ static int synth_chunk(zvx_ctx *c, int b0, int b1, const float *const *enc_seq, 
                                 sizeof(float) * (size_t)(c->h_seg[e] - c->h_seg[b]) * cfg.hop_size, cudaMemcpyDeviceToHost, c->stream));
         b = e;
     }
+    }
     for (int b = 0; b < n; ++b)
         if (mel && mel[b0 + b])
             CK(ctx, cudaMemcpyAsync(mel[b0 + b], c->mel + (size_t)c->h_seg[b] * cfg.num_mels, sizeof(float) * (size_t)L[b0 + b] * cfg.num_mels,
@@ -1364,12 +1377,12 @@ static int synth_chunk(zvx_ctx *c, int b0, int b1, const float *const *enc_seq, 
     return 0;
 }
 
-int zvx_synth_batch(zvx_ctx *ctx, int32_t B, const float *const *enc_seq, const float *const *style, const int32_t *L,
-                    float *const *mel, float *const *wav)
+static int synth_batch_impl(zvx_ctx *ctx, int32_t B, const float *const *enc_seq, const float *const *style, const int32_t *L,
+                            float *const *mel, float *const *wav, int16_t *const *pcm)
 {
     if (!ctx) return 1;
     if (!ctx->cfg.with_decoder || !ctx->cfg.with_vocoder) return fail(ctx, "context was built without decoder or vocoder");
-    if (!enc_seq || !style || !L || !wav) return fail(ctx, "zvx_synth_batch: null argument");
+    if (!enc_seq || !style || !L || (!wav && !pcm)) return fail(ctx, "zvx_synth_batch: null argument");
     if (B <= 0) return fail(ctx, "empty batch");
     CK(ctx, cudaSetDevice(ctx->device));
     int64_t frames = 0;
@@ -1383,7 +1396,7 @@ int zvx_synth_batch(zvx_ctx *ctx, int32_t B, const float *const *enc_seq, const 
     int nch = ctx->e2e_chunks;
     if (ctx->prof || ctx->debug_stop >= 0 || B < 2 * nch || frames < 4096) nch = 1;
     if (nch == 1) {
-        if (synth_chunk(ctx, 0, B, enc_seq, style, L, mel, wav)) return 1;
+        if (synth_chunk(ctx, 0, B, enc_seq, style, L, mel, wav, pcm)) return 1;
         return check_device_error(ctx);
     }
     if (make_lane(ctx)) return 1;
@@ -1409,10 +1422,70 @@ int zvx_synth_batch(zvx_ctx *ctx, int32_t B, const float *const *enc_seq, const 
     if (reserve(ctx->lane, maxf, maxb)) { ctx->err = ctx->lane->err; return 1; }
     for (size_t q = 0; q + 1 < cut.size(); ++q) {
         zvx_ctx *c = (q & 1) ? ctx->lane : ctx;
-        if (synth_chunk(c, cut[q], cut[q + 1], enc_seq, style, L, mel, wav)) { if (c != ctx) ctx->err = c->err; return 1; }
+        if (synth_chunk(c, cut[q], cut[q + 1], enc_seq, style, L, mel, wav, pcm)) { if (c != ctx) ctx->err = c->err; return 1; }
     }
     if (check_device_error(ctx->lane)) { ctx->err = ctx->lane->err; return 1; }
     return check_device_error(ctx);
+}
+
+int zvx_synth_batch(zvx_ctx *ctx, int32_t B, const float *const *enc_seq, const float *const *style, const int32_t *L,
+                    float *const *mel, float *const *wav)
+{
+    if (ctx && !wav) return fail(ctx, "zvx_synth_batch: null argument");
+    return synth_batch_impl(ctx, B, enc_seq, style, L, mel, wav, nullptr);
+}
+
+int zvx_synth_batch_pcm16(zvx_ctx *ctx, int32_t B, const float *const *enc_seq, const float *const *style, const int32_t *L,
+                          float *const *mel, int16_t *const *pcm)
+{
+    if (ctx && !pcm) return fail(ctx, "zvx_synth_batch_pcm16: null argument");
+    return synth_batch_impl(ctx, B, enc_seq, style, L, mel, nullptr, pcm);
+}
+
+int zvx_vocode_pcm16(zvx_ctx *ctx, const float *mel, int32_t L, int16_t *pcm)
+{
+    if (!ctx) return 1;
+    if (!ctx->cfg.with_vocoder) return fail(ctx, "context was built without the vocoder");
+    if (!mel || !pcm) return fail(ctx, "zvx_vocode_pcm16: null argument");
+    const zvx_config &c = ctx->cfg;
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (set_batch(ctx, 1, &L)) return 1;
+    CK(ctx, cudaMemcpyAsync(ctx->mel, mel, sizeof(float) * (size_t)L * c.num_mels, cudaMemcpyHostToDevice, ctx->stream));
+    int16_t *d_pcm = reinterpret_cast<int16_t *>(ctx->wav);
+    if (run_vocoder(ctx, ctx->mel, nullptr, d_pcm)) return 1;
+    CK(ctx, cudaMemcpyAsync(pcm, d_pcm, sizeof(int16_t) * (size_t)L * c.hop_size, cudaMemcpyDeviceToHost, ctx->stream));
+    return check_device_error(ctx);
+}
+
+// Minimal RIFF/WAVE writer, mono 16-bit PCM: what sf_open(SFM_WRITE, SF_FORMAT_WAV | SF_FORMAT_PCM_16) +
+// sf_write + sf_close produce for the reference's write_wav_file (zerovox.cpp:354-384): "RIFF" size "WAVE",
+// "fmt " 16 {1, 1, rate, 2 rate, 2, 16}, "data" 2 n, little-endian samples.  Host only, no CUDA involved.
+int zvx_write_wav_pcm16(const char *path, const int16_t *pcm, int64_t n_samples, int32_t sample_rate)
+{
+    if (!path || (!pcm && n_samples > 0) || n_samples < 0 || sample_rate <= 0) return 1;
+    if (n_samples > (int64_t)0x7FFFFFD0 / 2) return 1;      // RIFF sizes are 32-bit
+    FILE *f = fopen(path, "wb");
+    if (!f) return 1;
+    auto u32 = [](uint8_t *p, uint32_t v) { p[0] = v & 255; p[1] = (v >> 8) & 255; p[2] = (v >> 16) & 255; p[3] = (v >> 24) & 255; };
+    auto u16 = [](uint8_t *p, uint32_t v) { p[0] = v & 255; p[1] = (v >> 8) & 255; };
+    const uint32_t data_bytes = (uint32_t)(2 * n_samples);
+    uint8_t h[44];
+    memcpy(h, "RIFF", 4); u32(h + 4, 36u + data_bytes); memcpy(h + 8, "WAVE", 4);
+    memcpy(h + 12, "fmt ", 4); u32(h + 16, 16u); u16(h + 20, 1u); u16(h + 22, 1u);
+    u32(h + 24, (uint32_t)sample_rate); u32(h + 28, 2u * (uint32_t)sample_rate); u16(h + 32, 2u); u16(h + 34, 16u);
+    memcpy(h + 36, "data", 4); u32(h + 40, data_bytes);
+    bool ok = fwrite(h, 1, sizeof h, f) == sizeof h;
+    // samples are written little-endian whatever the host order
+    std::vector<uint8_t> buf;
+    const int64_t CH = 1 << 16;
+    for (int64_t i = 0; ok && i < n_samples; i += CH) {
+        const int64_t m = std::min<int64_t>(CH, n_samples - i);
+        buf.resize((size_t)(2 * m));
+        for (int64_t j = 0; j < m; ++j) u16(buf.data() + 2 * j, (uint16_t)pcm[i + j]);
+        ok = fwrite(buf.data(), 1, buf.size(), f) == buf.size();
+    }
+    ok = (fclose(f) == 0) && ok;
+    return ok ? 0 : 1;
 }
 
 int zvx_decode(zvx_ctx *ctx, const float *enc_seq, const float *style, int32_t L, float *mel)

@@ -66,6 +66,6 @@ cudaError_t cvt_f16_launch(const float *x, int ldx, int ch_off, int C, size_t ro
 // x2 / x3 non-null: input = ((x + x2) + x3) * sum_scale (MRF branch average applied by the consumer)
 cudaError_t out_conv_launch(const float *x, const float *x2, const float *x3, float sum_scale, int C, int K, const __half *w_raw, const float *bias, const float *w_host_kc,
                             float bias_host, float slope, const int *seg_start, const int *tile_start, int B, int rate,
-                            int total_tiles, float *wav, cudaStream_t st);
+                            int total_tiles, float *wav, int16_t *pcm, cudaStream_t st);
 
 }  // namespace zvx

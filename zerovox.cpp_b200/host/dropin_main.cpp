@@ -84,6 +84,10 @@ int main(int argc, char **argv)
     try {
         decoder.eval(enc.data(), sty.data(), mel.data());     // zerovox.cpp:330
         meldec.eval(mel.data(), wav.data());                  // zerovox.cpp:334
+        // zerovox.cpp:337-391 (write_wav_file): PCM_16 conversion on the GPU, RIFF file without libsndfile
+        std::vector<int16_t> pcm((size_t)L * hop);
+        meldec.eval_pcm16(mel.data(), pcm.data(), (uint32_t)L);
+        if (!ZeroVOX::write_wav_file_pcm16(std::string(argv[5]) + ".wav", pcm.data(), pcm.size(), 24000)) return 1;
     } catch (const std::exception &e) {
         fprintf(stderr, "error: %s\n", e.what());
         return 1;

@@ -189,4 +189,22 @@ namespace ZeroVOX
         if (!zvx) init();
         if (zvx_vocode(zvx, mel, (int32_t)n_frames, wav) != 0) raise(zvx, "HiFiGAN::eval");
     }
+
+    void HiFiGAN::eval_pcm16(const float *mel, int16_t *pcm, uint32_t n_frames)
+    {
+        if (n_frames == 0 || n_frames > max_seq_len) throw std::runtime_error("HiFiGAN::eval_pcm16: n_frames out of range");
+        if (!zvx) init();
+        if (zvx_vocode_pcm16(zvx, mel, (int32_t)n_frames, pcm) != 0) raise(zvx, "HiFiGAN::eval_pcm16");
+    }
+
+    // ZeroVOXModel::write_wav_file (zerovox.cpp:337-391) without libsndfile: same file format (mono WAV,
+    // PCM_16), same return convention (false + message on stderr when the file cannot be written).
+    bool write_wav_file_pcm16(const std::string &fname, const int16_t *pcm, size_t n_samples, uint32_t sample_rate)
+    {
+        if (zvx_write_wav_pcm16(fname.c_str(), pcm, (int64_t)n_samples, (int32_t)sample_rate) != 0) {
+            fprintf(stderr, "Error writing %s\n", fname.c_str());
+            return false;
+        }
+        return true;
+    }
 }

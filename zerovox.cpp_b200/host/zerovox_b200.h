@@ -81,6 +81,11 @@ namespace ZeroVOX
             // B200 extension: any number of frames <= max_seq_len
             void eval(const float *mel, float *wav, uint32_t n_frames);
 
+            // B200 extension: the waveform as signed 16-bit PCM, converted in the output
+            // conv's epilogue exactly as libsndfile converts it inside ZeroVOXModel::write_wav_file
+            // (zerovox.cpp:357-371): half the device -> host bytes of eval()
+            void eval_pcm16(const float *mel, int16_t *pcm, uint32_t n_frames);
+
         private:
 
             void init();
@@ -93,4 +98,8 @@ namespace ZeroVOX
             int           device;
             zvx_ctx      *zvx;
     };
+
+    // ZeroVOXModel::write_wav_file (zerovox.cpp:337-391) for samples that are already PCM_16: mono
+    // RIFF/WAVE, no libsndfile.  Returns false (and reports on stderr) when the file cannot be written.
+    bool write_wav_file_pcm16(const std::string &fname, const int16_t *pcm, size_t n_samples, uint32_t sample_rate);
 }
