@@ -179,6 +179,9 @@ def main():
 
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # NCCL writes its banner ("NCCL version ...") and debug lines to stdout by default; stdout carries exactly
+        # one JSON line here, so send them to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
