@@ -293,6 +293,37 @@ def main():
                "h2d_bytes_per_step": int(F * ctx.dim_in * 4 + B * ctx.style_dim * 4), "d2h_bytes_per_step": int(F * ctx.hop * 2),
                "pcm_checksum": int(h_pcm[:: 997].long().abs().sum())}
 
+    # same workload entered one stage earlier: phoneme-rate features + log-durations through
+    # zvx_synth_batch_regulated (7 frames per phoneme, the last one shorter, so that every utterance expands to the
+    # same number of frames as above), PCM_16 out.  Extra key; this entry point does not pipeline copies yet.
+    import math
+    FPP = 7
+    Pn = [(int(L) + FPP - 1) // FPP for L in lengths]
+    poffs = np.concatenate([[0], np.cumsum(Pn)]).astype(np.int64)
+    h_feat = torch.randn(int(poffs[-1]), ctx.dim_in).pin_memory()
+    h_ld = torch.empty(int(poffs[-1]), dtype=torch.float32).pin_memory()
+    for b in range(B):
+        h_ld[int(poffs[b]):int(poffs[b + 1])] = math.log(FPP + 1.0)
+        last = int(lengths[b]) - FPP * (Pn[b] - 1)
+        h_ld[int(poffs[b + 1]) - 1] = math.log(last + 1.0)
+    pf = (vp * B)(*[h_feat.data_ptr() + int(poffs[b]) * ctx.dim_in * 4 for b in range(B)])
+    pl = (vp * B)(*[h_ld.data_ptr() + int(poffs[b]) * 4 for b in range(B)])
+    Parr = (ctypes.c_int32 * B)(*Pn)
+    maxL = int(max(lengths))
+    for b in range(B):
+        assert capi.regulated_frames(h_ld[int(poffs[b]):int(poffs[b + 1])].numpy(), maxL) == int(lengths[b])
+    for _ in range(max(1, args.warmup)):
+        ctx.synth_batch_regulated_ptrs(B, pf, pl, Parr, ps, maxL, False, None, pp)
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.synth_batch_regulated_ptrs(B, pf, pl, Parr, ps, maxL, False, None, pp)
+    t_reg = max_over_ranks(time.perf_counter() - t0)
+    e2e_reg = {"value": total_audio * args.steps / t_reg, "unit": UNIT,
+               "h2d_bytes_per_step": int(poffs[-1]) * (ctx.dim_in * 4 + 4 + 8) + B * ctx.style_dim * 4, "d2h_bytes_per_step": int(F * ctx.hop * 2),
+               "phonemes_per_step": int(poffs[-1]), "pcm_checksum": int(h_pcm[:: 997].long().abs().sum())}
+
     # ---------------- roofline of the dominant kernel ----------------
     peak_tf, peak_gbs, peak_src = measured_peaks()
     by = {}
@@ -334,7 +365,7 @@ def main():
            "clocks": clk, "gpu_launches": launches,
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(F * ctx.dim_in * 4 + B * ctx.style_dim * 4),
                    "d2h_bytes_per_step": int(F * ctx.hop * 4), "wav_checksum": checksum},
-           "e2e_pcm16": e2e_pcm,
+           "e2e_pcm16": e2e_pcm, "e2e_regulated_pcm16": e2e_reg,
            "roofline": roofline, "kernel_breakdown": breakdown,
            "audio_s_per_step_per_gpu": audio_s}
 

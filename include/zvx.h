@@ -103,6 +103,28 @@ int zvx_vocode_pcm16(zvx_ctx *ctx, const float *mel, int32_t L, int16_t *pcm);
  * little-endian samples.  Host only (no ctx, no GPU).  Returns 0 on success. */
 int zvx_write_wav_pcm16(const char *path, const int16_t *pcm, int64_t n_samples, int32_t sample_rate);
 
+/* Length regulator in front of the hot path.  Replaces the host loop at
+ * the end of FS2Encoder::eval (/root/reference/src/fs2encoder.cpp:611-654: every phoneme's feature row is
+ * repeated round(exp(log_duration) - 1) times into a zeroed [max_seq_len][emb] matrix; the number of valid
+ * frames is returned and then ignored by ZeroVOXModel::eval, zerovox.cpp:326-334) and the host -> device copy
+ * of that expanded matrix: features travel at PHONEME rate and are expanded on the GPU.
+ *   features[b] [P[b]][dim_in], log_dur[b] [P[b]]  (the `features` / `log_duration_prediction` graph outputs),
+ *   style[b] [style_dim]; HOST pointers.
+ *   Durations are rounded on the host with the reference's own expression
+ *   (float dur = exp(d) - 1.0; (int32_t)(dur + 0.5)), capped at max_seq_len frames per utterance.
+ *   pad_to_max != 0: reference behaviour -- every utterance is synthesised as max_seq_len frames with a
+ *   zero tail (InstanceNorm statistics span the tail); outputs hold max_seq_len frames.
+ *   pad_to_max == 0: only the valid frames are synthesised (f1); outputs hold frames_out[b] frames --
+ *   size them with zvx_regulated_frames first.
+ *   frames_out (may be NULL) receives the valid-frame counts, i.e. FS2Encoder::eval's return value.
+ *   Exactly one of wav / pcm (see zvx_synth_batch_pcm16) is non-NULL; mel as in zvx_synth_batch. */
+int zvx_synth_batch_regulated(zvx_ctx *ctx, int32_t B, const float *const *features, const float *const *log_dur,
+                              const int32_t *P, const float *const *style, int32_t max_seq_len, int32_t pad_to_max,
+                              int32_t *frames_out, float *const *mel, float *const *wav, int16_t *const *pcm);
+
+/* The valid-frame count FS2Encoder::eval returns for one utterance (fs2encoder.cpp:621-654); host only. */
+int32_t zvx_regulated_frames(const float *log_dur, int32_t P, int32_t max_seq_len);
+
 /* Batched HiFiGAN::eval (hifigan.cpp:358-377) for B independent mels; HOST pointers. */
 int zvx_vocode_batch(zvx_ctx *ctx, int32_t B, const float *const *mel, const int32_t *L, float *const *wav);
 

@@ -220,3 +220,30 @@ def wav_file_bytes(pcm, sample_rate):
     hdr = b"RIFF" + struct.pack("<I", 36 + len(data)) + b"WAVE" + b"fmt " + struct.pack("<IHHIIHH", 16, 1, 1, sample_rate,
                                                                                          2 * sample_rate, 2, 16)
     return hdr + b"data" + struct.pack("<I", len(data)) + data
+
+
+# ---------------------------------------------------------------------------------------------
+# Length regulator: restatement of the host loop at the end of
+# FS2Encoder::eval, /root/reference/src/fs2encoder.cpp:611-654.  PARITY UNPINNED for this function: the
+# loop is not callable on its own (it sits behind the FastSpeech2 graph, whose weights are not in the
+# repository) and the reference has no test vector for it; tests/test_regulator_*.py therefore check the
+# library against THIS restatement only, plus hand-computed cases.
+def length_regulate(features, log_dur, max_seq_len):
+    """-> (x [max_seq_len][emb] with zero tail, number of valid frames)"""
+    import math
+    features = np.asarray(features, np.float32)
+    x = np.zeros((max_seq_len, features.shape[1]), np.float32)           # :614 memset
+    xoff = 0
+    for i in range(features.shape[0]):
+        dur = np.float32(math.exp(float(np.float32(log_dur[i]))) - 1.0)   # :623 float dur = exp(dur_data[i]) - 1.0
+        rounded = int(float(dur) + 0.5)                                   # :624 (int32_t)(dur + 0.5): truncation
+        if rounded < 0:
+            continue                                                      # :625-626
+        for _ in range(rounded):                                          # :631-637
+            x[xoff] = features[i]
+            xoff += 1
+            if xoff >= max_seq_len:
+                break
+        if xoff >= max_seq_len:                                           # :638-639
+            break
+    return x, xoff

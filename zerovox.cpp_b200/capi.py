@@ -55,7 +55,7 @@ EXPORTS = [
     "zvx_synth_batch", "zvx_synth_batch_device", "zvx_vocode_batch_device", "zvx_stream", "zvx_synchronize",
     "zvx_kernel_launches", "zvx_reserve", "zvx_set_debug_kernels", "zvx_test_conv", "zvx_debug_fetch",
     "zvx_set_debug_stop", "zvx_profile_begin", "zvx_profile_end", "zvx_set_fused_mrf", "zvx_vocode_batch", "zvx_vocode_chunked",
-    "zvx_synth_batch_pcm16", "zvx_vocode_pcm16", "zvx_write_wav_pcm16",
+    "zvx_synth_batch_pcm16", "zvx_vocode_pcm16", "zvx_write_wav_pcm16", "zvx_synth_batch_regulated", "zvx_regulated_frames",
 ]
 
 _lib = None
@@ -93,6 +93,11 @@ def load_library() -> C.CDLL:
     lib.zvx_vocode_pcm16.restype = i32
     lib.zvx_write_wav_pcm16.argtypes = [C.c_char_p, vp, i64, i32]
     lib.zvx_write_wav_pcm16.restype = i32
+    lib.zvx_synth_batch_regulated.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(i32), C.POINTER(vp), i32, i32,
+                                              C.POINTER(i32), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    lib.zvx_synth_batch_regulated.restype = i32
+    lib.zvx_regulated_frames.argtypes = [vp, i32, i32]
+    lib.zvx_regulated_frames.restype = i32
     lib.zvx_vocode_chunked.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp]
     lib.zvx_vocode_chunked.restype = i32
     lib.zvx_synth_batch_device.argtypes = [vp, i32, vp, vp, C.POINTER(i32), vp, vp, i32]
@@ -123,6 +128,12 @@ def load_library() -> C.CDLL:
     lib.zvx_profile_end.restype = i64
     _lib = lib
     return lib
+
+
+def regulated_frames(log_dur: np.ndarray, max_seq_len: int) -> int:
+    """zvx_regulated_frames: the valid-frame count FS2Encoder::eval returns (host only)."""
+    d = np.ascontiguousarray(log_dur, np.float32)
+    return int(load_library().zvx_regulated_frames(d.ctypes.data, d.size, int(max_seq_len)))
 
 
 def write_wav_pcm16(path: str, pcm: np.ndarray, sample_rate: int) -> None:
@@ -272,6 +283,30 @@ class Context:
         pcm = np.empty(mel.shape[0] * self.hop, np.int16)
         self._check(self.lib.zvx_vocode_pcm16(self.h, mel.ctypes.data, mel.shape[0], pcm.ctypes.data))
         return pcm
+
+    def synth_batch_regulated(self, feats: Sequence[np.ndarray], log_durs: Sequence[np.ndarray], style_list: Sequence[np.ndarray],
+                              max_seq_len: int, pad_to_max: bool, pcm16: bool = False):
+        """zvx_synth_batch_regulated: phoneme-rate features + log-durations -> (valid frame counts, waveforms)."""
+        B = len(feats)
+        fs = [np.ascontiguousarray(f, np.float32) for f in feats]
+        ds = [np.ascontiguousarray(d, np.float32) for d in log_durs]
+        stys = [np.ascontiguousarray(s, np.float32) for s in style_list]
+        Ps = (C.c_int32 * B)(*[f.shape[0] for f in fs])
+        frames = [max_seq_len if pad_to_max else regulated_frames(d, max_seq_len) for d in ds]
+        outs = [np.empty(n * self.hop, np.int16 if pcm16 else np.float32) for n in frames]
+        vp = C.c_void_p
+        pf = (vp * B)(*[f.ctypes.data for f in fs])
+        pd = (vp * B)(*[d.ctypes.data for d in ds])
+        ps = (vp * B)(*[s.ctypes.data for s in stys])
+        po = (vp * B)(*[o.ctypes.data for o in outs])
+        valid = (C.c_int32 * B)()
+        self._check(self.lib.zvx_synth_batch_regulated(self.h, B, pf, pd, Ps, ps, int(max_seq_len), int(pad_to_max), valid, None,
+                                                       None if pcm16 else po, po if pcm16 else None))
+        return list(valid), outs
+
+    def synth_batch_regulated_ptrs(self, B: int, feat_ptrs, logdur_ptrs, P, style_ptrs, max_seq_len: int, pad_to_max: bool, wav_ptrs, pcm_ptrs):
+        self._check(self.lib.zvx_synth_batch_regulated(self.h, B, feat_ptrs, logdur_ptrs, P, style_ptrs, int(max_seq_len), int(pad_to_max),
+                                                       None, None, wav_ptrs, pcm_ptrs))
 
     def synth_batch_ptrs(self, B: int, enc_ptrs, style_ptrs, lengths, mel_ptrs, wav_ptrs):
         """Raw-pointer form (host pointers as ints) for bench.py: no numpy allocation in the timed region."""

@@ -268,6 +268,29 @@ cudaError_t sum3_act_f16_launch(const float *a, const float *b, const float *c, 
     return cudaGetLastError();
 }
 
+// Length regulator (the host loop at the end of FS2Encoder::eval, /root/reference/src/fs2encoder.cpp:611-641):
+// the feature row of phoneme i is repeated tab[i].y times, starting at packed frame tab[i].x.  One CTA per
+// phoneme: the row is read once, every copy is a run of full-line float4 stores.  Index work only -- the
+// durations are rounded on the host with the reference's own libm call (zvx_api.cu).
+__global__ void __launch_bounds__(128) length_regulate_kernel(const float4 *__restrict__ feat, const int2 *__restrict__ tab, int D4,
+                                                              float4 *__restrict__ out)
+{
+    const int i = blockIdx.x;
+    const int2 t = tab[i];
+    for (int c = threadIdx.x; c < D4; c += 128) {
+        const float4 v = feat[(size_t)i * D4 + c];
+        for (int r = 0; r < t.y; ++r) out[(size_t)(t.x + r) * D4 + c] = v;
+    }
+}
+
+cudaError_t length_regulate_launch(const float *feat, const int2 *tab, int n_phonemes, int D, float *out, cudaStream_t st)
+{
+    if (D % 4) return cudaErrorInvalidValue;
+    if (n_phonemes <= 0) return cudaSuccess;
+    length_regulate_kernel<<<n_phonemes, 128, 0, st>>>(reinterpret_cast<const float4 *>(feat), tab, D / 4, reinterpret_cast<float4 *>(out));
+    return cudaGetLastError();
+}
+
 cudaError_t cvt_f16_launch(const float *x, int ldx, int ch_off, int C, size_t rows, __half *y16, cudaStream_t st)
 {
     if (C % 8) return cudaErrorInvalidValue;

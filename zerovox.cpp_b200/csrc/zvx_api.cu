@@ -99,6 +99,7 @@ struct zvx_ctx {
     int fused_persistent = 1;
     int fused_flags = 0;
     int conv_persistent = 1;
+    float *feat = nullptr; int2 *feat_tab = nullptr; size_t feat_cap = 0, feat_tab_cap = 0;   // length regulator staging
     int conv_smem_kb = 100;   // shared-memory budget of a one-tile conv CTA (two CTAs per SM)
     int conv_mt2 = 0;   // two M-tiles per CTA: measured slower on B200 while the A producer is the limit (profiles/)
     std::vector<int> tile256_cfg;                 // per rate index: wincfg entry of the 256-row tiling
@@ -1486,6 +1487,111 @@ int zvx_write_wav_pcm16(const char *path, const int16_t *pcm, int64_t n_samples,
     }
     ok = (fclose(f) == 0) && ok;
     return ok ? 0 : 1;
+}
+
+// ---------------------------------------------------------------- length regulator (SURVEY.md 8f, f2 + f1)
+// Duration of one phoneme exactly as FS2Encoder::eval rounds it (fs2encoder.cpp:623-627):
+//   float dur = exp(dur_data[i]) - 1.0;  int32_t duration_runded = (int32_t)(dur + 0.5);  negative -> skipped
+// (exp in double on the float argument, the difference narrowed to float, + 0.5 in double, truncation).
+static inline int32_t regulated_duration(float log_dur, int32_t cap)
+{
+    const float dur = (float)(exp((double)log_dur) - 1.0);
+    const double d = (double)dur + 0.5;
+    if (!(d >= 0.0)) return 0;                       // negative (or NaN): the reference's `continue`
+    if (d >= (double)cap) return cap;                // cannot contribute more than the frames that are left
+    return (int32_t)d;
+}
+
+int32_t zvx_regulated_frames(const float *log_dur, int32_t P, int32_t max_seq_len)
+{
+    if (!log_dur || P < 0 || max_seq_len <= 0) return -1;
+    int64_t x = 0;
+    for (int32_t i = 0; i < P && x < max_seq_len; ++i) x += regulated_duration(log_dur[i], (int32_t)(max_seq_len - x));
+    return (int32_t)std::min<int64_t>(x, max_seq_len);
+}
+
+int zvx_synth_batch_regulated(zvx_ctx *ctx, int32_t B, const float *const *features, const float *const *log_dur, const int32_t *P,
+                              const float *const *style, int32_t max_seq_len, int32_t pad_to_max, int32_t *frames_out,
+                              float *const *mel, float *const *wav, int16_t *const *pcm)
+{
+    if (!ctx) return 1;
+    if (!ctx->cfg.with_decoder || !ctx->cfg.with_vocoder) return fail(ctx, "context was built without decoder or vocoder");
+    if (!features || !log_dur || !P || !style || (!wav == !pcm)) return fail(ctx, "zvx_synth_batch_regulated: null argument (exactly one of wav / pcm)");
+    if (B <= 0) return fail(ctx, "empty batch");
+    if (max_seq_len <= 0) return fail(ctx, "zvx_synth_batch_regulated: max_seq_len must be positive");
+    const zvx_config &cfg = ctx->cfg;
+    CK(ctx, cudaSetDevice(ctx->device));
+    // host: durations -> valid frames per utterance, {first packed frame, count} per phoneme
+    std::vector<int32_t> L(B), valid(B);
+    std::vector<int2> tab;
+    int64_t np = 0, frame0 = 0;
+    for (int b = 0; b < B; ++b) {
+        if (P[b] <= 0 || !features[b] || !log_dur[b] || !style[b]) return fail(ctx, "utterance %d: no phonemes / null pointer", b);
+        np += P[b];
+    }
+    tab.reserve((size_t)np);
+    for (int b = 0; b < B; ++b) {
+        int64_t x = 0;
+        for (int32_t i = 0; i < P[b]; ++i) {
+            const int32_t d = x < max_seq_len ? regulated_duration(log_dur[b][i], (int32_t)(max_seq_len - x)) : 0;
+            tab.push_back(make_int2((int)(frame0 + x), d));
+            x += d;
+        }
+        valid[b] = (int32_t)x;
+        if (frames_out) frames_out[b] = valid[b];
+        L[b] = pad_to_max ? max_seq_len : valid[b];
+        if (L[b] <= 0) return fail(ctx, "utterance %d: all durations are zero", b);
+        frame0 += L[b];
+    }
+    if (set_batch(ctx, B, L.data())) return 1;
+    // staging buffers (grown geometrically; growing synchronises, steady state does not)
+    const size_t need_f = (size_t)np * cfg.dim_in;
+    if (need_f > ctx->feat_cap) {
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+        const size_t cap = std::max(need_f, ctx->feat_cap * 2);
+        dev_free(ctx, ctx->feat); ctx->feat = nullptr; ctx->feat_cap = 0;
+        if (dev_alloc(ctx, &ctx->feat, cap)) return 1;
+        ctx->feat_cap = cap;
+    }
+    if ((size_t)np > ctx->feat_tab_cap) {
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+        const size_t cap = std::max((size_t)np, std::max(ctx->feat_tab_cap * 2, (size_t)1024));
+        dev_free(ctx, ctx->feat_tab); ctx->feat_tab = nullptr; ctx->feat_tab_cap = 0;
+        if (dev_alloc(ctx, &ctx->feat_tab, cap)) return 1;
+        ctx->feat_tab_cap = cap;
+    }
+    // H2D at PHONEME rate: [sum P][dim_in] instead of [sum L][dim_in] (one copy per run of contiguous host buffers)
+    size_t off = 0;
+    for (int b = 0; b < B;) {
+        int e = b + 1;
+        size_t rows = (size_t)P[b];
+        while (e < B && features[e] == features[e - 1] + (size_t)P[e - 1] * cfg.dim_in) rows += (size_t)P[e++];
+        CK(ctx, cudaMemcpyAsync(ctx->feat + off * cfg.dim_in, features[b], sizeof(float) * rows * cfg.dim_in, cudaMemcpyHostToDevice, ctx->stream));
+        off += rows;
+        b = e;
+    }
+    CK(ctx, cudaMemcpyAsync(ctx->feat_tab, tab.data(), sizeof(int2) * (size_t)np, cudaMemcpyHostToDevice, ctx->stream));
+    for (int b = 0; b < B; ++b)
+        CK(ctx, cudaMemcpyAsync(ctx->style + (size_t)b * cfg.style_dim, style[b], sizeof(float) * cfg.style_dim, cudaMemcpyHostToDevice, ctx->stream));
+    // the reference clears the whole [max_seq_len][emb] buffer first (fs2encoder.cpp:614): zero tail of every utterance
+    if (pad_to_max) CK(ctx, cudaMemsetAsync(ctx->enc_in, 0, sizeof(float) * (size_t)frame0 * cfg.dim_in, ctx->stream));
+    ctx->launches++;
+    if (prof_begin(ctx, ZVX_K_NORM_AFFINE, 0, 0.0, 4.0 * ((double)np + (double)frame0) * cfg.dim_in)) return 1;
+    CK(ctx, length_regulate_launch(ctx->feat, ctx->feat_tab, (int)np, cfg.dim_in, ctx->enc_in, ctx->stream));
+    if (prof_end(ctx)) return 1;
+    // (`tab` outlives its asynchronous copy: this function ends with a stream synchronisation)
+    if (run_decoder(ctx, ctx->mel)) return 1;
+    int16_t *d_pcm = reinterpret_cast<int16_t *>(ctx->wav);
+    if (run_vocoder(ctx, ctx->mel, pcm ? nullptr : ctx->wav, pcm ? d_pcm : nullptr)) return 1;
+    for (int b = 0; b < B; ++b) {
+        const size_t s0 = (size_t)ctx->h_seg[b] * cfg.hop_size, n = (size_t)L[b] * cfg.hop_size;
+        if (pcm) CK(ctx, cudaMemcpyAsync(pcm[b], d_pcm + s0, sizeof(int16_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+        else     CK(ctx, cudaMemcpyAsync(wav[b], ctx->wav + s0, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+        if (mel && mel[b])
+            CK(ctx, cudaMemcpyAsync(mel[b], ctx->mel + (size_t)ctx->h_seg[b] * cfg.num_mels, sizeof(float) * (size_t)L[b] * cfg.num_mels,
+                                    cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    return check_device_error(ctx);
 }
 
 int zvx_decode(zvx_ctx *ctx, const float *enc_seq, const float *style, int32_t L, float *mel)

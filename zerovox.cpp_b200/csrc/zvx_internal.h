@@ -59,6 +59,7 @@ cudaError_t norm_act_f16_launch(const float *x, int ldx, int ch_off, int C, cons
 
 cudaError_t sum3_act_f16_launch(const float *a, const float *b, const float *c, float scale, float slope, size_t n, __half *y16,
                                 cudaStream_t st);
+cudaError_t length_regulate_launch(const float *feat, const int2 *tab, int n_phonemes, int D, float *out, cudaStream_t st);
 cudaError_t cvt_f16_launch(const float *x, int ldx, int ch_off, int C, size_t rows, __half *y16, cudaStream_t st);
 
 // wav = tanh(conv_k(leaky_relu(x, slope)) + b), single output channel
