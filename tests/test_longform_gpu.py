@@ -27,6 +27,25 @@ def test_chunked_vocoding_equals_whole_sequence(ctx, zvx):
         ctx.vocode_chunked(mel, 256, 8)
 
 
+def test_chunk_callbacks_stream_in_order_with_final_data(ctx, zvx):
+    """Chunks go through the vocoder in groups (1, 2, 4, 8, ... per pass) but are reported one by one, in order,
+    each exactly once, and their samples are final when the callback runs."""
+    L = 2600
+    enc, sty = zvx.synth.make_inputs(L, seed=9)
+    mel = ctx.decode(enc, sty)
+    whole = ctx.vocode(mel)
+    seen = []
+
+    def on_chunk(first, n, wav):
+        assert np.array_equal(wav[first:first + n], whole[first:first + n])
+        seen.append((first, n))
+
+    got = ctx.vocode_chunked(mel, 200, 20, on_chunk=on_chunk)
+    assert np.array_equal(got, whole)
+    assert [f for f, _ in seen] == [i * 200 * 300 for i in range(13)]
+    assert sum(n for _, n in seen) == L * 300 and seen[-1][1] == 200 * 300
+
+
 def test_sixty_second_utterance_matches_live_reference(ctx, zvx, gguf_path):
     import refrun
     if not refrun.available():

@@ -227,12 +227,17 @@ class Context:
         self._check(self.lib.zvx_vocode(self.h, _ptr(mel), L, _ptr(wav)))
         return wav
 
-    def vocode_chunked(self, mel: np.ndarray, chunk_frames: int = 256, halo_frames: int = 20) -> np.ndarray:
-        """Long-form vocoding in overlapping mel chunks (configs[2]); equals vocode(mel)."""
+    def vocode_chunked(self, mel: np.ndarray, chunk_frames: int = 256, halo_frames: int = 20, on_chunk=None) -> np.ndarray:
+        """Long-form vocoding in overlapping mel chunks (configs[2]); equals vocode(mel).
+        on_chunk(first_sample, n_samples, wav) is called as soon as those samples are final."""
         mel = np.ascontiguousarray(mel, np.float32)
         L = mel.shape[0]
         wav = np.empty(L * self.hop, np.float32)
-        self._check(self.lib.zvx_vocode_chunked(self.h, _ptr(mel), L, chunk_frames, halo_frames, _ptr(wav), None, None))
+        cb = None
+        if on_chunk is not None:
+            cb = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_int64)(lambda user, first, n: on_chunk(int(first), int(n), wav))
+        self._check(self.lib.zvx_vocode_chunked(self.h, _ptr(mel), L, chunk_frames, halo_frames, _ptr(wav),
+                                                C.cast(cb, C.c_void_p) if cb else None, None))
         return wav
 
     def vocode_batch(self, mel_list: Sequence[np.ndarray]):

@@ -100,6 +100,7 @@ struct zvx_ctx {
     int fused_flags = 0;
     int conv_persistent = 1;
     float *feat = nullptr; int2 *feat_tab = nullptr; size_t feat_cap = 0, feat_tab_cap = 0;   // length regulator staging
+    int chunk_group_max = 8;   // zvx_vocode_chunked: at most this many chunks per vocoder pass
     int conv_smem_kb = 100;   // shared-memory budget of a one-tile conv CTA (two CTAs per SM)
     int conv_mt2 = 0;   // two M-tiles per CTA: measured slower on B200 while the A producer is the limit (profiles/)
     std::vector<int> tile256_cfg;                 // per rate index: wincfg entry of the 256-row tiling
@@ -1178,6 +1179,7 @@ int zvx_create(zvx_ctx **out, const zvx_config *cfg, const zvx_tensor_desc *weig
     if (const char *e = getenv("ZVX_BRANCH_SUM_IN_CONSUMER")) ctx->branch_sum_in_consumer = atoi(e);
     if (const char *e = getenv("ZVX_CONV_MT2")) ctx->conv_mt2 = atoi(e);
     if (const char *e = getenv("ZVX_CONV_SMEM_KB")) ctx->conv_smem_kb = atoi(e);
+    if (const char *e = getenv("ZVX_CHUNK_GROUP_MAX")) ctx->chunk_group_max = std::max(1, atoi(e));
     if (const char *e = getenv("ZVX_CONV_PERSISTENT")) ctx->conv_persistent = atoi(e);
     if (const char *e = getenv("ZVX_FUSED_UPCONV")) ctx->use_fused_upconv = atoi(e);
     ctx->num_sms = prop.multiProcessorCount;
@@ -1657,17 +1659,31 @@ int zvx_vocode_chunked(zvx_ctx *ctx, const float *mel, int32_t L, int32_t chunk_
     if (chunk_frames <= 0 || halo_frames < 20) return fail(ctx, "zvx_vocode_chunked: chunk_frames must be > 0 and halo_frames >= 20 (receptive field 19.5 frames)");
     CK(ctx, cudaSetDevice(ctx->device));
     const zvx_config &c = ctx->cfg;
-    for (int32_t a = 0; a < L; a += chunk_frames) {
-        const int32_t b = std::min(L, a + chunk_frames);
-        const int32_t lo = std::max(0, a - halo_frames), hi = std::min(L, b + halo_frames);
-        const int32_t n = hi - lo;
-        if (set_batch(ctx, 1, &n)) return 1;
-        CK(ctx, cudaMemcpyAsync(ctx->mel, mel + (size_t)lo * c.num_mels, sizeof(float) * (size_t)n * c.num_mels, cudaMemcpyHostToDevice, ctx->stream));
+    // Chunks are independent once they carry their halo, so several of them go through the vocoder as ONE batch
+    // (one pass over ~100 launches instead of one pass per chunk).  The group size ramps 1, 2, 4, 8, 8, ...: the
+    // first samples leave after a single chunk's worth of work, the rest of a long utterance runs at batch throughput.
+    const int32_t nchunks = (L + chunk_frames - 1) / chunk_frames;
+    int32_t group = 1;
+    for (int32_t c0 = 0; c0 < nchunks; c0 += group, group = std::min(2 * group, ctx->chunk_group_max)) {
+        const int32_t g = std::min(group, nchunks - c0);
+        std::vector<int32_t> n(g), lo(g), a(g), b(g);
+        for (int32_t i = 0; i < g; ++i) {
+            a[i] = (c0 + i) * chunk_frames;
+            b[i] = std::min(L, a[i] + chunk_frames);
+            lo[i] = std::max(0, a[i] - halo_frames);
+            n[i] = std::min(L, b[i] + halo_frames) - lo[i];
+        }
+        if (set_batch(ctx, g, n.data())) return 1;
+        for (int32_t i = 0; i < g; ++i)
+            CK(ctx, cudaMemcpyAsync(ctx->mel + (size_t)ctx->h_seg[i] * c.num_mels, mel + (size_t)lo[i] * c.num_mels,
+                                    sizeof(float) * (size_t)n[i] * c.num_mels, cudaMemcpyHostToDevice, ctx->stream));
         if (run_vocoder(ctx, ctx->mel, ctx->wav)) return 1;
-        CK(ctx, cudaMemcpyAsync(wav + (size_t)a * c.hop_size, ctx->wav + (size_t)(a - lo) * c.hop_size, sizeof(float) * (size_t)(b - a) * c.hop_size,
-                                cudaMemcpyDeviceToHost, ctx->stream));
+        for (int32_t i = 0; i < g; ++i)
+            CK(ctx, cudaMemcpyAsync(wav + (size_t)a[i] * c.hop_size, ctx->wav + (size_t)(ctx->h_seg[i] + a[i] - lo[i]) * c.hop_size,
+                                    sizeof(float) * (size_t)(b[i] - a[i]) * c.hop_size, cudaMemcpyDeviceToHost, ctx->stream));
         if (check_device_error(ctx)) return 1;
-        if (on_chunk) on_chunk(user, (int64_t)a * c.hop_size, (int64_t)(b - a) * c.hop_size);
+        if (on_chunk)
+            for (int32_t i = 0; i < g; ++i) on_chunk(user, (int64_t)a[i] * c.hop_size, (int64_t)(b[i] - a[i]) * c.hop_size);
     }
     return 0;
 }
