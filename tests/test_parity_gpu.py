@@ -87,6 +87,22 @@ def test_batched_varlen_equals_single_utterance_bit_exact(ctx, zvx):
     assert np.array_equal(m, mels[0]) and np.array_equal(ctx.vocode(m), wavs[0])
 
 
+def test_batch_of_more_than_1023_utterances(ctx, zvx):
+    """Maximum-size batches: above 1023 utterances the fused MRF kernel no longer keeps the utterance tables in
+    shared memory (warp-cooperative search in global memory) and the segment search of the conv kernels needs two
+    probe rounds.  Must equal the same utterances synthesised in small batches, bit for bit."""
+    rng = np.random.default_rng(77)
+    B = 1100
+    Ls = rng.integers(2, 5, B)                 # < 4096 frames in total: zvx_synth_batch keeps it as ONE batch
+    assert int(Ls.sum()) < 4096
+    base = [zvx.synth.make_inputs(int(L), seed=200 + int(L)) for L in range(2, 5)]
+    ins = [base[int(L) - 2] for L in Ls]
+    _, wavs = ctx.synth_batch([e for e, _ in ins], [s for _, s in ins], want_mel=False)
+    _, ref = ctx.synth_batch([e for e, _ in base], [s for _, s in base], want_mel=False)
+    for L, w in zip(Ls, wavs):
+        assert np.array_equal(w, ref[int(L) - 2])
+
+
 def test_live_reference_on_unseen_length(ctx, zvx, gguf_path):
     """Run the compiled reference on the GPU box's host for a length without a committed fixture."""
     import refrun
