@@ -87,6 +87,24 @@ def test_batched_varlen_equals_single_utterance_bit_exact(ctx, zvx):
     assert np.array_equal(m, mels[0]) and np.array_equal(ctx.vocode(m), wavs[0])
 
 
+def test_graph_replay_of_single_utterance_calls(ctx, zvx):
+    """zvx_decode / zvx_vocode / zvx_vocode_pcm16 capture their ~100 launches into a CUDA graph per length and replay
+    it afterwards: replays with new inputs, interleaved lengths and an intervening large batch (workspace growth drops
+    the graphs) must equal the batch path, which launches kernel by kernel."""
+    cases = [(57, 1), (91, 2), (57, 3), (91, 4), (57, 5)]
+    for rnd in range(2):
+        for L, seed in cases:
+            enc, sty = zvx.synth.make_inputs(L, seed=300 + seed)
+            mels, wavs = ctx.synth_batch([enc], [sty])
+            mel = ctx.decode(enc, sty)
+            assert np.array_equal(mel, mels[0])
+            assert np.array_equal(ctx.vocode(mel), wavs[0])
+            assert np.array_equal(ctx.vocode_pcm16(mel), zv_oracle.pcm16(wavs[0]))
+        if rnd == 0:        # grow the workspace beyond anything used so far
+            big = [zvx.synth.make_inputs(2100, seed=400 + i) for i in range(5)]
+            ctx.synth_batch([e for e, _ in big], [s for _, s in big], want_mel=False)
+
+
 def test_batch_of_more_than_1023_utterances(ctx, zvx):
     """Maximum-size batches: above 1023 utterances the fused MRF kernel no longer keeps the utterance tables in
     shared memory (warp-cooperative search in global memory) and the segment search of the conv kernels needs two

@@ -100,6 +100,11 @@ struct zvx_ctx {
     int fused_flags = 0;
     int conv_persistent = 1;
     float *feat = nullptr; int2 *feat_tab = nullptr; size_t feat_cap = 0, feat_tab_cap = 0;   // length regulator staging
+    // single-utterance calls (the reference-facing eval() path: ~100 small launches) are replayed from CUDA graphs,
+    // one per (stage, length, switches); dropped whenever a workspace buffer they point into is reallocated
+    struct GraphEntry { int kind, L, flags; cudaGraphExec_t exec; int64_t launches; };
+    std::vector<GraphEntry> graphs;
+    int use_graphs = 1;
     int chunk_group_max = 8;   // zvx_vocode_chunked: at most this many chunks per vocoder pass
     int conv_smem_kb = 100;   // shared-memory budget of a one-tile conv CTA (two CTAs per SM)
     int conv_mt2 = 0;   // two M-tiles per CTA: measured slower on B200 while the A producer is the limit (profiles/)
@@ -571,8 +576,15 @@ int64_t max_stage_elems(const zvx_ctx *ctx)
     return m;
 }
 
+void drop_graphs(zvx_ctx *ctx)
+{
+    for (auto &g : ctx->graphs) cudaGraphExecDestroy(g.exec);
+    ctx->graphs.clear();
+}
+
 int reserve(zvx_ctx *ctx, int64_t frames, int batch)
 {
+    if (batch > ctx->cap_batch || frames > ctx->cap_frames) drop_graphs(ctx);
     const zvx_config &c = ctx->cfg;
     if (batch > ctx->cap_batch) {
         const int nb = std::max(std::max(batch, 64), 2 * ctx->cap_batch);   // grow geometrically: every growth reallocates
@@ -1059,6 +1071,39 @@ int check_device_error(zvx_ctx *ctx)
     return 0;
 }
 
+// Run `body` (kernel launches on ctx->stream only, no synchronisation) for a single utterance of L frames: the
+// first time it is captured into a CUDA graph, afterwards the graph is replayed (one launch instead of ~100).
+template <class F>
+int run_graphed(zvx_ctx *ctx, int kind, int L, F body)
+{
+    if (!ctx->use_graphs || ctx->prof || ctx->debug_stop >= 0 || ctx->use_ref_kernels) return body();
+    const int flags = ctx->use_fused;
+    for (auto &g : ctx->graphs)
+        if (g.kind == kind && g.L == L && g.flags == flags) {
+            CK(ctx, cudaGraphLaunch(g.exec, ctx->stream));
+            ctx->launches += g.launches;
+            return 0;
+        }
+    const int64_t l0 = ctx->launches;
+    CK(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = body();
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+    if (rc || e != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        if (!rc) return fail(ctx, "CUDA graph capture failed: %s", cudaGetErrorString(e));
+        return 1;
+    }
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t ei = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ei != cudaSuccess) return fail(ctx, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ei));
+    if (ctx->graphs.size() >= 16) { cudaGraphExecDestroy(ctx->graphs.front().exec); ctx->graphs.erase(ctx->graphs.begin()); }
+    ctx->graphs.push_back({kind, L, flags, exec, ctx->launches - l0});
+    CK(ctx, cudaGraphLaunch(exec, ctx->stream));
+    return 0;
+}
+
 int ensure_pinned(zvx_ctx *ctx, float **buf, size_t *cap, size_t n)
 {
     if (n <= *cap) return 0;
@@ -1098,6 +1143,8 @@ int make_lane(zvx_ctx *parent)
     l->H16 = l->X16 = l->R16 = nullptr;
     l->d_seg = l->d_tiles = l->d_wins = l->d_err = l->pin_tables = nullptr;
     l->pin_in_cap = l->pin_out_cap = 0;
+    l->graphs.clear();           // the copies of the parent's graph handles are not the lane's to destroy
+    l->feat = nullptr; l->feat_tab = nullptr; l->feat_cap = l->feat_tab_cap = 0;
     parent->lane = l;
     zvx_ctx *ctx = parent;   // error reporting goes to the parent
     CK(ctx, cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking));
@@ -1142,6 +1189,7 @@ void zvx_destroy(zvx_ctx *ctx)
     cudaSetDevice(ctx->device);
     if (ctx->lane) { zvx_destroy(ctx->lane); ctx->lane = nullptr; }
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    drop_graphs(ctx);
     for (void *p : ctx->owned) cudaFree(p);
     if (ctx->pin_tables) cudaFreeHost(ctx->pin_tables);
     if (ctx->pin_in) cudaFreeHost(ctx->pin_in);
@@ -1179,6 +1227,7 @@ int zvx_create(zvx_ctx **out, const zvx_config *cfg, const zvx_tensor_desc *weig
     if (const char *e = getenv("ZVX_BRANCH_SUM_IN_CONSUMER")) ctx->branch_sum_in_consumer = atoi(e);
     if (const char *e = getenv("ZVX_CONV_MT2")) ctx->conv_mt2 = atoi(e);
     if (const char *e = getenv("ZVX_CONV_SMEM_KB")) ctx->conv_smem_kb = atoi(e);
+    if (const char *e = getenv("ZVX_GRAPHS")) ctx->use_graphs = atoi(e);
     if (const char *e = getenv("ZVX_CHUNK_GROUP_MAX")) ctx->chunk_group_max = std::max(1, atoi(e));
     if (const char *e = getenv("ZVX_CONV_PERSISTENT")) ctx->conv_persistent = atoi(e);
     if (const char *e = getenv("ZVX_FUSED_UPCONV")) ctx->use_fused_upconv = atoi(e);
@@ -1455,7 +1504,7 @@ int zvx_vocode_pcm16(zvx_ctx *ctx, const float *mel, int32_t L, int16_t *pcm)
     if (set_batch(ctx, 1, &L)) return 1;
     CK(ctx, cudaMemcpyAsync(ctx->mel, mel, sizeof(float) * (size_t)L * c.num_mels, cudaMemcpyHostToDevice, ctx->stream));
     int16_t *d_pcm = reinterpret_cast<int16_t *>(ctx->wav);
-    if (run_vocoder(ctx, ctx->mel, nullptr, d_pcm)) return 1;
+    if (run_graphed(ctx, 2, L, [&]() { return run_vocoder(ctx, ctx->mel, nullptr, d_pcm); })) return 1;
     CK(ctx, cudaMemcpyAsync(pcm, d_pcm, sizeof(int16_t) * (size_t)L * c.hop_size, cudaMemcpyDeviceToHost, ctx->stream));
     return check_device_error(ctx);
 }
@@ -1606,7 +1655,7 @@ int zvx_decode(zvx_ctx *ctx, const float *enc_seq, const float *style, int32_t L
     const zvx_config &c = ctx->cfg;
     CK(ctx, cudaMemcpyAsync(ctx->enc_in, enc_seq, sizeof(float) * (size_t)L * c.dim_in, cudaMemcpyHostToDevice, ctx->stream));
     CK(ctx, cudaMemcpyAsync(ctx->style, style, sizeof(float) * c.style_dim, cudaMemcpyHostToDevice, ctx->stream));
-    if (run_decoder(ctx, ctx->mel)) return 1;
+    if (run_graphed(ctx, 0, L, [&]() { return run_decoder(ctx, ctx->mel); })) return 1;
     CK(ctx, cudaMemcpyAsync(mel, ctx->mel, sizeof(float) * (size_t)L * c.num_mels, cudaMemcpyDeviceToHost, ctx->stream));
     return check_device_error(ctx);
 }
@@ -1620,7 +1669,7 @@ int zvx_vocode(zvx_ctx *ctx, const float *mel, int32_t L, float *wav)
     if (set_batch(ctx, 1, &L)) return 1;
     const zvx_config &c = ctx->cfg;
     CK(ctx, cudaMemcpyAsync(ctx->mel, mel, sizeof(float) * (size_t)L * c.num_mels, cudaMemcpyHostToDevice, ctx->stream));
-    if (run_vocoder(ctx, ctx->mel, ctx->wav)) return 1;
+    if (run_graphed(ctx, 1, L, [&]() { return run_vocoder(ctx, ctx->mel, ctx->wav); })) return 1;
     if (ctx->debug_stop < 0)
         CK(ctx, cudaMemcpyAsync(wav, ctx->wav, sizeof(float) * (size_t)L * c.hop_size, cudaMemcpyDeviceToHost, ctx->stream));
     return check_device_error(ctx);
