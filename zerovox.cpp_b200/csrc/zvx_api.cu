@@ -102,6 +102,14 @@ struct zvx_ctx {
     float *feat = nullptr; int2 *feat_tab = nullptr; size_t feat_cap = 0, feat_tab_cap = 0;   // length regulator staging
     // single-utterance calls (the reference-facing eval() path: ~100 small launches) are replayed from CUDA graphs,
     // one per (stage, length, switches); dropped whenever a workspace buffer they point into is reallocated
+    // small jobs (a single short utterance leaves most launches under-filled): the three independent residual blocks of
+    // an MRF stage run on three streams -- inside a graph capture that becomes three parallel branches of the graph
+    int fork_branches = 1;
+    int64_t fork_max_frames = 2048;
+    cudaStream_t fork_stream[2] = {nullptr, nullptr};
+    cudaEvent_t fork_ev = nullptr, join_ev[2] = {nullptr, nullptr};
+    float *fkY1[2] = {nullptr, nullptr}, *fkT2[2] = {nullptr, nullptr};
+    __half *fkH16[2] = {nullptr, nullptr};
     struct GraphEntry { int kind, L, flags; cudaGraphExec_t exec; int64_t launches; };
     std::vector<GraphEntry> graphs;
     int use_graphs = 1;
@@ -637,6 +645,8 @@ int reserve(zvx_ctx *ctx, int64_t frames, int batch)
     return 0;
 }
 
+int ensure_fork(zvx_ctx *ctx);
+
 // upload utterance segmentation: frames prefix + per-rate 128-row tile prefixes
 int set_batch(zvx_ctx *ctx, int B, const int32_t *L, bool reserve_workspace = true)
 {
@@ -681,6 +691,7 @@ int set_batch(zvx_ctx *ctx, int B, const int32_t *L, bool reserve_workspace = tr
     }
     CK(ctx, cudaEventRecord(ctx->tables_event, ctx->stream));
     ctx->tables_pending = true;
+    if (ctx->fork_branches && ctx->cfg.with_vocoder && frames <= ctx->fork_max_frames && ensure_fork(ctx)) return 1;
     ctx->last_B = B;
     ctx->last_frames = frames;
     ctx->last_max_len = 0;
@@ -921,6 +932,21 @@ int run_decoder(zvx_ctx *ctx, float *mel_out)
 }
 
 // ---------------------------------------------------------------- vocoder schedule
+// streams, events and the per-branch temporaries of the forked MRF stages (allocated once, for fork_max_frames)
+int ensure_fork(zvx_ctx *ctx)
+{
+    if (ctx->fork_stream[0]) return 0;
+    const int64_t n = ctx->fork_max_frames * max_stage_elems(ctx);
+    for (int j = 0; j < 2; ++j) {
+        if (dev_alloc(ctx, &ctx->fkY1[j], (size_t)n) || dev_alloc(ctx, &ctx->fkT2[j], (size_t)n) || dev_alloc(ctx, &ctx->fkH16[j], (size_t)n)) return 1;
+        CK(ctx, cudaEventCreateWithFlags(&ctx->join_ev[j], cudaEventDisableTiming));
+    }
+    CK(ctx, cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
+    CK(ctx, cudaStreamCreateWithFlags(&ctx->fork_stream[1], cudaStreamNonBlocking));
+    CK(ctx, cudaStreamCreateWithFlags(&ctx->fork_stream[0], cudaStreamNonBlocking));
+    return 0;
+}
+
 int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out, int16_t *pcm_out = nullptr)
 {
     const zvx_config &c = ctx->cfg;
@@ -935,6 +961,8 @@ int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out, int16_t *pcm_
     const float *vin = ctx->v0, *vin2 = nullptr, *vin3 = nullptr;   // vin2/vin3: stage output still split in 3 branches
     float *vout[2] = {ctx->VA, ctx->VB};
     const float third = (float)(1.0 / (float)nb);
+    const bool fork_ok = ctx->fork_branches && ctx->fork_stream[0] && !ctx->prof && ctx->debug_stop < 0 && !ctx->use_ref_kernels &&
+                         ctx->last_frames <= ctx->fork_max_frames;
     for (int i = 0; i < 8; ++i) ctx->stage_is_split[i] = 0;
     for (int i = 0; i < c.num_upsamples; ++i) {
         if (ctx->debug_stop >= 0 && i >= ctx->debug_stop) return 0;
@@ -973,11 +1001,30 @@ int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out, int16_t *pcm_
         // branch buffer j, so no conv epilogue reads a running sum.
         const bool split = ctx->branch_sum_in_consumer && !ctx->use_ref_kernels && nb == 3;
         float *branch_out[3] = {ctx->CS, ctx->VA, ctx->VB};
+        // small job: blocks 1 and 2 go to their own streams (own temporaries), joined before the consumer
+        const bool fork = split && fork_ok;
+        cudaStream_t main_stream = ctx->stream;
+        if (fork) CK(ctx, cudaEventRecord(ctx->fork_ev, main_stream));
         for (int j = 0; j < nb; ++j) {
             const FusedBlock &fb = ctx->fused[(size_t)i * nb + j];
+            struct StreamSwap {          // launches of this block go to ctx->stream: point it at the branch's stream
+                zvx_ctx *c; cudaStream_t saved;
+                ~StreamSwap() { c->stream = saved; }
+            } swap_back = {ctx, main_stream};
+            float *bY1 = ctx->Y1, *bT2 = ctx->T2;
+            __half *bH16 = ctx->H16;
+            if (fork && j > 0) {
+                ctx->stream = ctx->fork_stream[j - 1];
+                CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->fork_ev, 0));
+                bY1 = ctx->fkY1[j - 1]; bT2 = ctx->fkT2[j - 1]; bH16 = ctx->fkH16[j - 1];
+            }
+            struct Join {                // ... and the main stream waits for it at the end of the iteration
+                zvx_ctx *c; cudaStream_t main; cudaEvent_t ev; bool on;
+                ~Join() { if (on) { cudaEventRecord(ev, c->stream); cudaStreamWaitEvent(main, ev, 0); } }
+            } join = {ctx, main_stream, (fork && j > 0) ? ctx->join_ev[j - 1] : nullptr, fork && j > 0};
             if (ctx->use_fused && !ctx->use_ref_kernels && fb.CH) {
                 // whole residual block (or chains of its conv pairs) on chip: mrf_fused.cu
-                float *tmp[2] = {ctx->Y1, split ? ctx->T2 : vout[(i + 1) & 1]};   // (the stage-input buffer is free after the up-conv)
+                float *tmp[2] = {bY1, split ? bT2 : vout[(i + 1) & 1]};   // (the stage-input buffer is free after the up-conv)
                 const float *yin = ctx->U;
                 for (size_t q = 0; q < fb.chains.size(); ++q) {
                     const FusedChain &fc = fb.chains[q];
@@ -1020,15 +1067,15 @@ int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out, int16_t *pcm_
                 }
                 continue;
             }
-            float *Y = split ? branch_out[j] : (j == 0) ? ctx->CS : ctx->Y1;
+            float *Y = split ? branch_out[j] : (j == 0) ? ctx->CS : bY1;
             for (int d = 0; d < nd; ++d) {
                 const size_t idx = ((size_t)i * nb + j) * nd + d;
                 const float *yin = d == 0 ? ctx->U : Y;
                 ConvCall c1; c1.kind = ZVX_K_MRF_CONV; c1.stage = i; c1.L = &ctx->mrf1[idx]; c1.x = yin; c1.ldx = ch; c1.rate_idx = i + 1;
                 c1.pro_mode = PRO_LRELU; c1.pro_slope = 0.1f;
-                c1.out16 = ctx->H16; c1.ldo16 = ch; c1.out16_slope = 0.1f;
+                c1.out16 = bH16; c1.ldo16 = ch; c1.out16_slope = 0.1f;
                 if (run_conv(ctx, c1)) return 1;
-                ConvCall c2; c2.kind = ZVX_K_MRF_CONV; c2.stage = i; c2.L = &ctx->mrf2[idx]; c2.x = ctx->H16; c2.ldx = ch; c2.rate_idx = i + 1; c2.pro_mode = PRO_F16;
+                ConvCall c2; c2.kind = ZVX_K_MRF_CONV; c2.stage = i; c2.L = &ctx->mrf2[idx]; c2.x = bH16; c2.ldx = ch; c2.rate_idx = i + 1; c2.pro_mode = PRO_F16;
                 c2.res = yin; c2.ldres = ch;
                 const bool last = d == nd - 1;
                 if (last && j > 0 && !split) {
@@ -1144,6 +1191,8 @@ int make_lane(zvx_ctx *parent)
     l->d_seg = l->d_tiles = l->d_wins = l->d_err = l->pin_tables = nullptr;
     l->pin_in_cap = l->pin_out_cap = 0;
     l->graphs.clear();           // the copies of the parent's graph handles are not the lane's to destroy
+    for (int j = 0; j < 2; ++j) { l->fork_stream[j] = nullptr; l->join_ev[j] = nullptr; l->fkY1[j] = l->fkT2[j] = nullptr; l->fkH16[j] = nullptr; }
+    l->fork_ev = nullptr;
     l->feat = nullptr; l->feat_tab = nullptr; l->feat_cap = l->feat_tab_cap = 0;
     parent->lane = l;
     zvx_ctx *ctx = parent;   // error reporting goes to the parent
@@ -1190,6 +1239,11 @@ void zvx_destroy(zvx_ctx *ctx)
     if (ctx->lane) { zvx_destroy(ctx->lane); ctx->lane = nullptr; }
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     drop_graphs(ctx);
+    for (int j = 0; j < 2; ++j) {
+        if (ctx->fork_stream[j]) cudaStreamDestroy(ctx->fork_stream[j]);
+        if (ctx->join_ev[j]) cudaEventDestroy(ctx->join_ev[j]);
+    }
+    if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
     for (void *p : ctx->owned) cudaFree(p);
     if (ctx->pin_tables) cudaFreeHost(ctx->pin_tables);
     if (ctx->pin_in) cudaFreeHost(ctx->pin_in);
@@ -1228,6 +1282,7 @@ int zvx_create(zvx_ctx **out, const zvx_config *cfg, const zvx_tensor_desc *weig
     if (const char *e = getenv("ZVX_CONV_MT2")) ctx->conv_mt2 = atoi(e);
     if (const char *e = getenv("ZVX_CONV_SMEM_KB")) ctx->conv_smem_kb = atoi(e);
     if (const char *e = getenv("ZVX_GRAPHS")) ctx->use_graphs = atoi(e);
+    if (const char *e = getenv("ZVX_FORK_BRANCHES")) ctx->fork_branches = atoi(e);
     if (const char *e = getenv("ZVX_CHUNK_GROUP_MAX")) ctx->chunk_group_max = std::max(1, atoi(e));
     if (const char *e = getenv("ZVX_CONV_PERSISTENT")) ctx->conv_persistent = atoi(e);
     if (const char *e = getenv("ZVX_FUSED_UPCONV")) ctx->use_fused_upconv = atoi(e);
