@@ -102,10 +102,10 @@ struct zvx_ctx {
     float *feat = nullptr; int2 *feat_tab = nullptr; size_t feat_cap = 0, feat_tab_cap = 0;   // length regulator staging
     // single-utterance calls (the reference-facing eval() path: ~100 small launches) are replayed from CUDA graphs,
     // one per (stage, length, switches); dropped whenever a workspace buffer they point into is reallocated
-    // small jobs (a single short utterance leaves most launches under-filled): the three independent residual blocks of
-    // an MRF stage run on three streams -- inside a graph capture that becomes three parallel branches of the graph
+    // the three independent residual blocks of an MRF stage run on three streams (inside a graph capture: three parallel
+    // branches of the graph): a single short utterance leaves most launches under-filled, and for large batches the tail
+    // of one block's persistent kernel overlaps the start of the next
     int fork_branches = 1;
-    int64_t fork_max_frames = 2048;
     cudaStream_t fork_stream[2] = {nullptr, nullptr};
     cudaEvent_t fork_ev = nullptr, join_ev[2] = {nullptr, nullptr};
     float *fkY1[2] = {nullptr, nullptr}, *fkT2[2] = {nullptr, nullptr};
@@ -620,6 +620,10 @@ int reserve(zvx_ctx *ctx, int64_t frames, int batch)
                           &ctx->d1, &ctx->d2, &ctx->mel, &ctx->v0, &ctx->U, &ctx->CS, &ctx->Y1, &ctx->VA, &ctx->VB, &ctx->T2, &ctx->wav};
         for (float **b : bufs) { dev_free(ctx, *b); *b = nullptr; }
         dev_free(ctx, ctx->H16); ctx->H16 = nullptr;
+        for (int j = 0; j < 2; ++j) {
+            dev_free(ctx, ctx->fkY1[j]); dev_free(ctx, ctx->fkT2[j]); dev_free(ctx, ctx->fkH16[j]);
+            ctx->fkY1[j] = ctx->fkT2[j] = nullptr; ctx->fkH16[j] = nullptr;
+        }
         dev_free(ctx, ctx->X16); ctx->X16 = nullptr;
         dev_free(ctx, ctx->R16); ctx->R16 = nullptr;
         const int D = c.dim_in, BN = 2 * D, R = c.residual_dim;
@@ -639,6 +643,10 @@ int reserve(zvx_ctx *ctx, int64_t frames, int batch)
                 dev_alloc(ctx, &ctx->T2, F * S) ||
                 dev_alloc(ctx, &ctx->H16, F * S) || dev_alloc(ctx, &ctx->wav, F * c.hop_size))
                 return 1;
+            // per-branch temporaries of the forked MRF stages (run_vocoder): + 2 x (2 fp32 + 1 fp16) stage buffers
+            if (ctx->fork_branches)
+                for (int j = 0; j < 2; ++j)
+                    if (dev_alloc(ctx, &ctx->fkY1[j], F * S) || dev_alloc(ctx, &ctx->fkT2[j], F * S) || dev_alloc(ctx, &ctx->fkH16[j], F * S)) return 1;
         }
         ctx->cap_frames = F;
     }
@@ -691,7 +699,7 @@ int set_batch(zvx_ctx *ctx, int B, const int32_t *L, bool reserve_workspace = tr
     }
     CK(ctx, cudaEventRecord(ctx->tables_event, ctx->stream));
     ctx->tables_pending = true;
-    if (ctx->fork_branches && ctx->cfg.with_vocoder && frames <= ctx->fork_max_frames && ensure_fork(ctx)) return 1;
+    if (ctx->fork_branches && ctx->cfg.with_vocoder && ensure_fork(ctx)) return 1;
     ctx->last_B = B;
     ctx->last_frames = frames;
     ctx->last_max_len = 0;
@@ -932,15 +940,11 @@ int run_decoder(zvx_ctx *ctx, float *mel_out)
 }
 
 // ---------------------------------------------------------------- vocoder schedule
-// streams, events and the per-branch temporaries of the forked MRF stages (allocated once, for fork_max_frames)
+// streams and events of the forked MRF stages (their per-branch temporaries are part of the workspace, reserve())
 int ensure_fork(zvx_ctx *ctx)
 {
     if (ctx->fork_stream[0]) return 0;
-    const int64_t n = ctx->fork_max_frames * max_stage_elems(ctx);
-    for (int j = 0; j < 2; ++j) {
-        if (dev_alloc(ctx, &ctx->fkY1[j], (size_t)n) || dev_alloc(ctx, &ctx->fkT2[j], (size_t)n) || dev_alloc(ctx, &ctx->fkH16[j], (size_t)n)) return 1;
-        CK(ctx, cudaEventCreateWithFlags(&ctx->join_ev[j], cudaEventDisableTiming));
-    }
+    for (int j = 0; j < 2; ++j) CK(ctx, cudaEventCreateWithFlags(&ctx->join_ev[j], cudaEventDisableTiming));
     CK(ctx, cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
     CK(ctx, cudaStreamCreateWithFlags(&ctx->fork_stream[1], cudaStreamNonBlocking));
     CK(ctx, cudaStreamCreateWithFlags(&ctx->fork_stream[0], cudaStreamNonBlocking));
@@ -961,8 +965,7 @@ int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out, int16_t *pcm_
     const float *vin = ctx->v0, *vin2 = nullptr, *vin3 = nullptr;   // vin2/vin3: stage output still split in 3 branches
     float *vout[2] = {ctx->VA, ctx->VB};
     const float third = (float)(1.0 / (float)nb);
-    const bool fork_ok = ctx->fork_branches && ctx->fork_stream[0] && !ctx->prof && ctx->debug_stop < 0 && !ctx->use_ref_kernels &&
-                         ctx->last_frames <= ctx->fork_max_frames;
+    const bool fork_ok = ctx->fork_branches && ctx->fork_stream[0] && ctx->fkY1[0] && !ctx->prof && ctx->debug_stop < 0 && !ctx->use_ref_kernels;
     for (int i = 0; i < 8; ++i) ctx->stage_is_split[i] = 0;
     for (int i = 0; i < c.num_upsamples; ++i) {
         if (ctx->debug_stop >= 0 && i >= ctx->debug_stop) return 0;
@@ -1001,7 +1004,7 @@ int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out, int16_t *pcm_
         // branch buffer j, so no conv epilogue reads a running sum.
         const bool split = ctx->branch_sum_in_consumer && !ctx->use_ref_kernels && nb == 3;
         float *branch_out[3] = {ctx->CS, ctx->VA, ctx->VB};
-        // small job: blocks 1 and 2 go to their own streams (own temporaries), joined before the consumer
+        // blocks 1 and 2 go to their own streams (own temporaries), joined before the consumer
         const bool fork = split && fork_ok;
         cudaStream_t main_stream = ctx->stream;
         if (fork) CK(ctx, cudaEventRecord(ctx->fork_ev, main_stream));
