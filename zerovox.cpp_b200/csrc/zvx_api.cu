@@ -863,6 +863,29 @@ int run_decoder(zvx_ctx *ctx, float *mel_out)
     CK(ctx, adain_fc_launch(ctx->adain, ctx->style, ctx->last_B, ctx->adain_gb, ctx->stream));
     if (prof_end(ctx)) return 1;
 
+    // The learned shortcut (1x1 conv of the block input, plus its fp16 copy) does not depend on the block's
+    // norm -> conv1 chain: it runs on a forked stream and is joined before conv2 reads it.
+    const bool fork_ok = ctx->fork_branches && ctx->fork_stream[0] && !ctx->prof && ctx->debug_stop < 0 && !ctx->use_ref_kernels;
+    auto forked = [&](auto body) -> int {
+        if (!fork_ok) return body();
+        cudaStream_t main_stream = ctx->stream;
+        cudaError_t e = cudaEventRecord(ctx->fork_ev, main_stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->fork_stream[0], ctx->fork_ev, 0);
+        if (e != cudaSuccess) return fail(ctx, "fork: %s", cudaGetErrorString(e));
+        ctx->stream = ctx->fork_stream[0];
+        const int rc = body();
+        e = cudaEventRecord(ctx->join_ev[0], ctx->stream);
+        ctx->stream = main_stream;
+        if (rc) return rc;
+        if (e != cudaSuccess) return fail(ctx, "fork: %s", cudaGetErrorString(e));
+        return 0;
+    };
+    auto join = [&]() -> int {
+        if (!fork_ok) return 0;
+        CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->join_ev[0], 0));
+        return 0;
+    };
+
     // ---- encode.0 / encode.1 : ResBlk1d (stylettsdec.cpp:69-149) ----
     const float *x = ctx->enc_in; int ldx = D;
     float *enc_out[2] = {ctx->e0, ctx->catA};
@@ -874,8 +897,11 @@ int run_decoder(zvx_ctx *ctx, float *mel_out)
         if (b.learned_sc) {
             ConvCall s; s.L = &b.conv1x1; s.x = x; s.ldx = ldx; s.pro_mode = PRO_CVT; s.use_bias = false;
             s.out32 = ctx->sc; s.ldo32 = b.cout;
-            if (use_raw_f16(ctx, s, true)) return 1;     // i == 0: x is enc_in; the copy is reused by asr_res below
-            if (run_conv(ctx, s)) return 1;
+            if (forked([&]() -> int {
+                    if (use_raw_f16(ctx, s, true)) return 1;     // i == 0: x is enc_in; the copy is reused by asr_res below
+                    return run_conv(ctx, s);
+                }))
+                return 1;
             sc = ctx->sc; ldsc = b.cout;
         }
         if (run_stats(ctx, x, ldx, 0, b.cin)) return 1;
@@ -888,6 +914,7 @@ int run_decoder(zvx_ctx *ctx, float *mel_out)
         c2.mu = ctx->mu; c2.rstd = ctx->rstd; c2.stat_stride = b.cin; c2.g = b.n2w; c2.b = b.n2b; c2.gb_stride = 0;
         c2.res = sc; c2.ldres = ldsc; c2.scale = inv_sqrt2;
         c2.out32 = enc_out[i]; c2.ldo32 = enc_ld[i];
+        if (b.learned_sc && join()) return 1;
         if (run_norm_conv(ctx, c2)) return 1;
         x = enc_out[i]; ldx = enc_ld[i];
     }
@@ -912,26 +939,30 @@ int run_decoder(zvx_ctx *ctx, float *mel_out)
         AdaBlkW &b = ctx->dec[i];
         const AdainDesc &a1 = ctx->adain.d[b.ada1], &a2 = ctx->adain.d[b.ada2];
         float *h = b.cout == BN ? ctx->h1056 : ctx->h528;
+        const float *sc = din[i]; int ldsc = dinl[i];
+        if (b.learned_sc) {
+            ConvCall s; s.L = &b.conv1x1; s.x = din[i]; s.ldx = dinl[i]; s.pro_mode = PRO_CVT; s.use_bias = false;
+            s.out32 = ctx->sc; s.ldo32 = b.cout;
+            if (forked([&]() -> int {
+                    if (use_raw_f16(ctx, s, true)) return 1;
+                    return run_conv(ctx, s);
+                }))
+                return 1;
+            sc = ctx->sc; ldsc = b.cout;
+        }
         if (run_stats(ctx, din[i], dinl[i], 0, b.cin)) return 1;
         ConvCall c1; c1.L = &b.conv1; c1.x = din[i]; c1.ldx = dinl[i]; c1.pro_mode = PRO_NORM; c1.pro_slope = 0.2f;
         c1.mu = ctx->mu; c1.rstd = ctx->rstd; c1.stat_stride = b.cin;
         c1.g = ctx->adain_gb + a1.out_off; c1.b = ctx->adain_gb + a1.out_off + a1.C; c1.gb_stride = ctx->adain.total;
         c1.out32 = h; c1.ldo32 = b.cout;
         if (run_norm_conv(ctx, c1)) return 1;
-        const float *sc = din[i]; int ldsc = dinl[i];
-        if (b.learned_sc) {
-            ConvCall s; s.L = &b.conv1x1; s.x = din[i]; s.ldx = dinl[i]; s.pro_mode = PRO_CVT; s.use_bias = false;
-            s.out32 = ctx->sc; s.ldo32 = b.cout;
-            if (use_raw_f16(ctx, s, true)) return 1;
-            if (run_conv(ctx, s)) return 1;
-            sc = ctx->sc; ldsc = b.cout;
-        }
         if (run_stats(ctx, h, b.cout, 0, b.cout)) return 1;
         ConvCall c2; c2.L = &b.conv2; c2.x = h; c2.ldx = b.cout; c2.pro_mode = PRO_NORM; c2.pro_slope = 0.2f;
         c2.mu = ctx->mu; c2.rstd = ctx->rstd; c2.stat_stride = b.cout;
         c2.g = ctx->adain_gb + a2.out_off; c2.b = ctx->adain_gb + a2.out_off + a2.C; c2.gb_stride = ctx->adain.total;
         c2.res = sc; c2.ldres = ldsc; c2.scale = inv_sqrt2;
         c2.out32 = dout[i]; c2.ldo32 = doutl[i];
+        if (b.learned_sc && join()) return 1;
         if (run_norm_conv(ctx, c2)) return 1;
     }
     // ---- to_out (stylettsdec.cpp:432-441) ----
