@@ -1019,13 +1019,30 @@ int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out, int16_t *pcm_
                 CK(ctx, sum3_act_f16_launch(vin, vin2, vin3, third, 0.1f, n, ctx->H16, ctx->stream));
                 if (prof_end(ctx)) return 1;
             }
-            for (int phi = 0; phi < s; ++phi) {
+            // the s output phases are independent launches (disjoint rows of U): dealt round-robin to the three streams
+            cudaStream_t main_stream = ctx->stream;
+            if (fork_ok) CK(ctx, cudaEventRecord(ctx->fork_ev, main_stream));
+            bool used[2] = {false, false};
+            int rc = 0;
+            for (int phi = 0; phi < s && !rc; ++phi) {
                 ConvCall u; u.kind = ZVX_K_UPCONV; u.stage = i; u.L = &ctx->up[i]; u.variant = phi; u.x = vin; u.ldx = cin; u.rate_idx = i;
                 u.pro_mode = PRO_LRELU; u.pro_slope = 0.1f; u.out32 = ctx->U; u.ldo32 = ch; u.out_mul = s;
                 if (pre) { u.x = ctx->H16; u.pro_mode = PRO_F16; }
                 else if (vin2) { u.pro_mode = PRO_SUM3; u.x2 = vin2; u.x3 = vin3; u.sum_scale = third; }
-                if (run_conv(ctx, u)) return 1;
+                const int lane_id = fork_ok ? phi % 3 : 0;
+                if (lane_id > 0) {
+                    ctx->stream = ctx->fork_stream[lane_id - 1];
+                    if (!used[lane_id - 1] && cudaStreamWaitEvent(ctx->stream, ctx->fork_ev, 0) != cudaSuccess) rc = 1;
+                    used[lane_id - 1] = true;
+                }
+                if (!rc) rc = run_conv(ctx, u);
+                ctx->stream = main_stream;
             }
+            for (int j = 0; j < 2; ++j)
+                if (used[j] && (cudaEventRecord(ctx->join_ev[j], ctx->fork_stream[j]) != cudaSuccess ||
+                                cudaStreamWaitEvent(main_stream, ctx->join_ev[j], 0) != cudaSuccess))
+                    rc = 1;
+            if (rc) return ctx->err.empty() ? fail(ctx, "up-conv phase launch failed") : 1;
         }
         // MRF: three residual blocks on U, averaged (hifigan.cpp:300-315, :97-183).  When all three run as
         // fused chains, each writes its own output buffer and the branch sum / average is applied by the
