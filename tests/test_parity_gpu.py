@@ -105,6 +105,30 @@ def test_graph_replay_of_single_utterance_calls(ctx, zvx):
             ctx.synth_batch([e for e, _ in big], [s for _, s in big], want_mel=False)
 
 
+@pytest.mark.parametrize("B", [3, 12])
+def test_device_resident_batch_equals_host_batch(ctx, zvx, B):
+    """zvx_synth_batch_device (inputs / outputs in HBM; B >= 8 is split in two halves that run concurrently on the context
+    and its lane) == zvx_synth_batch, bit for bit, twice in a row (stream ordering across calls)."""
+    import ctypes
+    import torch
+    lens = zvx.synth.batch_lengths(B, seed=21)
+    ins = [zvx.synth.make_inputs(int(L), seed=500 + i) for i, L in enumerate(lens)]
+    mels, wavs = ctx.synth_batch([e for e, _ in ins], [s for _, s in ins])
+    d_enc = torch.from_numpy(np.concatenate([e for e, _ in ins])).cuda()
+    d_sty = torch.from_numpy(np.stack([s for _, s in ins])).cuda()
+    F = int(lens.sum())
+    d_mel = torch.empty(F, ctx.num_mels, device="cuda")
+    d_wav = torch.empty(F * ctx.hop, device="cuda")
+    Larr = (ctypes.c_int32 * B)(*[int(x) for x in lens])
+    torch.cuda.synchronize()
+    for _ in range(2):
+        d_wav.zero_()
+        torch.cuda.synchronize()
+        ctx.synth_batch_device(B, d_enc.data_ptr(), d_sty.data_ptr(), Larr, d_mel.data_ptr(), d_wav.data_ptr(), sync=True)
+        assert np.array_equal(d_wav.cpu().numpy(), np.concatenate(wavs))
+        assert np.array_equal(d_mel.cpu().numpy(), np.concatenate(mels))
+
+
 def test_batch_of_more_than_1023_utterances(ctx, zvx):
     """Maximum-size batches: above 1023 utterances the fused MRF kernel no longer keeps the utterance tables in
     shared memory (warp-cooperative search in global memory) and the segment search of the conv kernels needs two

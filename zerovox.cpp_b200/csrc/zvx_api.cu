@@ -105,6 +105,8 @@ struct zvx_ctx {
     // the three independent residual blocks of an MRF stage run on three streams (inside a graph capture: three parallel
     // branches of the graph): a single short utterance leaves most launches under-filled, and for large batches the tail
     // of one block's persistent kernel overlaps the start of the next
+    int device_split = 1;       // zvx_synth_batch_device: two half batches, on the context and on its lane
+    cudaEvent_t split_ev[2] = {nullptr, nullptr};
     int fork_branches = 1;
     cudaStream_t fork_stream[2] = {nullptr, nullptr};
     cudaEvent_t fork_ev = nullptr, join_ev[2] = {nullptr, nullptr};
@@ -1295,6 +1297,8 @@ void zvx_destroy(zvx_ctx *ctx)
         if (ctx->join_ev[j]) cudaEventDestroy(ctx->join_ev[j]);
     }
     if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
+    for (int j = 0; j < 2; ++j)
+        if (ctx->split_ev[j] && !ctx->is_lane) cudaEventDestroy(ctx->split_ev[j]);
     for (void *p : ctx->owned) cudaFree(p);
     if (ctx->pin_tables) cudaFreeHost(ctx->pin_tables);
     if (ctx->pin_in) cudaFreeHost(ctx->pin_in);
@@ -1334,6 +1338,7 @@ int zvx_create(zvx_ctx **out, const zvx_config *cfg, const zvx_tensor_desc *weig
     if (const char *e = getenv("ZVX_CONV_SMEM_KB")) ctx->conv_smem_kb = atoi(e);
     if (const char *e = getenv("ZVX_GRAPHS")) ctx->use_graphs = atoi(e);
     if (const char *e = getenv("ZVX_FORK_BRANCHES")) ctx->fork_branches = atoi(e);
+    if (const char *e = getenv("ZVX_DEVICE_SPLIT")) ctx->device_split = atoi(e);
     if (const char *e = getenv("ZVX_CHUNK_GROUP_MAX")) ctx->chunk_group_max = std::max(1, atoi(e));
     if (const char *e = getenv("ZVX_CONV_PERSISTENT")) ctx->conv_persistent = atoi(e);
     if (const char *e = getenv("ZVX_FUSED_UPCONV")) ctx->use_fused_upconv = atoi(e);
@@ -1462,6 +1467,44 @@ int zvx_synth_batch_device(zvx_ctx *ctx, int32_t B, const float *d_enc, const fl
     if (!ctx) return 1;
     if (!ctx->cfg.with_decoder || !ctx->cfg.with_vocoder) return fail(ctx, "context was built without decoder or vocoder");
     CK(ctx, cudaSetDevice(ctx->device));
+    if (ctx->device_split && B >= 8 && !ctx->prof && ctx->debug_stop < 0) {
+        // two half batches, the second on the lane (own stream + workspace): its HBM-bound small kernels can run under the
+        // first half's tensor-bound persistent kernels and vice versa; the context's stream stays the ordering point
+        int64_t frames = 0, acc = 0;
+        for (int b = 0; b < B; ++b) frames += L[b];
+        int b0 = 0;
+        while (b0 < B - 1 && 2 * (acc + L[b0]) <= frames) acc += L[b0++];
+        if (b0 > 0) {
+            if (make_lane(ctx)) return 1;
+            zvx_ctx *ln = ctx->lane;
+            ln->use_ref_kernels = ctx->use_ref_kernels; ln->use_fused = ctx->use_fused;
+            for (int j = 0; j < 2; ++j)
+                if (!ctx->split_ev[j]) CK(ctx, cudaEventCreateWithFlags(&ctx->split_ev[j], cudaEventDisableTiming));
+            const zvx_config &cfg = ctx->cfg;
+            CK(ctx, cudaEventRecord(ctx->split_ev[0], ctx->stream));
+            // first half on the context
+            if (set_batch(ctx, b0, L)) return 1;
+            CK(ctx, cudaMemcpyAsync(ctx->enc_in, d_enc, sizeof(float) * (size_t)acc * cfg.dim_in, cudaMemcpyDeviceToDevice, ctx->stream));
+            CK(ctx, cudaMemcpyAsync(ctx->style, d_style, sizeof(float) * (size_t)b0 * cfg.style_dim, cudaMemcpyDeviceToDevice, ctx->stream));
+            float *melA = d_mel ? d_mel : ctx->mel;
+            if (run_decoder(ctx, melA)) return 1;
+            if (run_vocoder(ctx, melA, d_wav)) return 1;
+            // second half on the lane, after whatever the caller had queued on the context's stream
+            if (set_batch(ln, B - b0, L + b0)) { ctx->err = ln->err; return 1; }
+            CK(ctx, cudaStreamWaitEvent(ln->stream, ctx->split_ev[0], 0));
+            CK(ctx, cudaMemcpyAsync(ln->enc_in, d_enc + (size_t)acc * cfg.dim_in, sizeof(float) * (size_t)(frames - acc) * cfg.dim_in,
+                                    cudaMemcpyDeviceToDevice, ln->stream));
+            CK(ctx, cudaMemcpyAsync(ln->style, d_style + (size_t)b0 * cfg.style_dim, sizeof(float) * (size_t)(B - b0) * cfg.style_dim,
+                                    cudaMemcpyDeviceToDevice, ln->stream));
+            float *melB = d_mel ? d_mel + (size_t)acc * cfg.num_mels : ln->mel;
+            if (run_decoder(ln, melB) || run_vocoder(ln, melB, d_wav + (size_t)acc * cfg.hop_size)) { ctx->err = ln->err; return 1; }
+            CK(ctx, cudaEventRecord(ctx->split_ev[1], ln->stream));
+            CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->split_ev[1], 0));
+            if (!sync) return 0;
+            if (check_device_error(ln)) { ctx->err = ln->err; return 1; }
+            return check_device_error(ctx);
+        }
+    }
     if (set_batch(ctx, B, L)) return 1;
     const int64_t F = ctx->last_frames;
     // the schedule reads its inputs from the workspace: D2D copies keep the public pointers const
