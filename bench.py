@@ -295,7 +295,7 @@ def main():
 
     # same workload entered one stage earlier: phoneme-rate features + log-durations through
     # zvx_synth_batch_regulated (7 frames per phoneme, the last one shorter, so that every utterance expands to the
-    # same number of frames as above), PCM_16 out.  Extra key; this entry point does not pipeline copies yet.
+    # same number of frames as above), PCM_16 out.  Extra key.
     import math
     FPP = 7
     Pn = [(int(L) + FPP - 1) // FPP for L in lengths]

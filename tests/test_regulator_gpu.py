@@ -23,7 +23,7 @@ def _utterances(zvx, n, seed, dim=528):
     return out
 
 
-@pytest.mark.parametrize("pad_to_max,cap", [(True, 400), (False, 400), (False, 60)])
+@pytest.mark.parametrize("pad_to_max,cap", [(True, 400), (False, 400), (False, 60), (True, 1000)])   # the last one is large enough for the two-lane pipelining
 def test_regulated_synthesis_equals_host_expansion_bit_exact(ctx, zvx, pad_to_max, cap):
     utts = _utterances(zvx, 5, seed=11)
     valid, wavs = ctx.synth_batch_regulated([u[0] for u in utts], [u[1] for u in utts], [u[2] for u in utts], cap, pad_to_max)

@@ -1710,6 +1710,77 @@ int32_t zvx_regulated_frames(const float *log_dur, int32_t P, int32_t max_seq_le
     return (int32_t)std::min<int64_t>(x, max_seq_len);
 }
 
+// one sub-batch [b0, b1) of zvx_synth_batch_regulated on context / lane `c`; everything asynchronous on c->stream.
+// rel[b] = {first frame relative to the utterance, count} per phoneme; `tab` is the caller's staging vector for the packed
+// table (it must stay alive until the stream has been synchronised).
+static int regulated_chunk(zvx_ctx *c, int b0, int b1, const float *const *features, const int32_t *P, const float *const *style,
+                           const std::vector<std::vector<int2>> &rel, const int32_t *L, bool pad, std::vector<int2> &tab,
+                           float *const *mel, float *const *wav, int16_t *const *pcm)
+{
+    zvx_ctx *ctx = c;
+    const zvx_config &cfg = c->cfg;
+    const int n = b1 - b0;
+    if (set_batch(c, n, L + b0)) return 1;
+    int64_t np = 0;
+    for (int b = b0; b < b1; ++b) np += P[b];
+    tab.clear();
+    tab.reserve((size_t)np);
+    for (int b = 0; b < n; ++b)
+        for (const int2 &e : rel[b0 + b]) tab.push_back(make_int2(c->h_seg[b] + e.x, e.y));
+    // staging buffers (grown geometrically; growing synchronises, steady state does not)
+    const size_t need_f = (size_t)np * cfg.dim_in;
+    if (need_f > c->feat_cap) {
+        CK(ctx, cudaStreamSynchronize(c->stream));
+        const size_t cap = std::max(need_f, c->feat_cap * 2);
+        dev_free(c, c->feat); c->feat = nullptr; c->feat_cap = 0;
+        if (dev_alloc(c, &c->feat, cap)) return 1;
+        c->feat_cap = cap;
+    }
+    if ((size_t)np > c->feat_tab_cap) {
+        CK(ctx, cudaStreamSynchronize(c->stream));
+        const size_t cap = std::max((size_t)np, std::max(c->feat_tab_cap * 2, (size_t)1024));
+        dev_free(c, c->feat_tab); c->feat_tab = nullptr; c->feat_tab_cap = 0;
+        if (dev_alloc(c, &c->feat_tab, cap)) return 1;
+        c->feat_tab_cap = cap;
+    }
+    // H2D at PHONEME rate: [sum P][dim_in] instead of [sum L][dim_in] (one copy per run of contiguous host buffers)
+    size_t off = 0;
+    for (int b = b0; b < b1;) {
+        int e = b + 1;
+        size_t rows = (size_t)P[b];
+        while (e < b1 && features[e] == features[e - 1] + (size_t)P[e - 1] * cfg.dim_in) rows += (size_t)P[e++];
+        CK(ctx, cudaMemcpyAsync(c->feat + off * cfg.dim_in, features[b], sizeof(float) * rows * cfg.dim_in, cudaMemcpyHostToDevice, c->stream));
+        off += rows;
+        b = e;
+    }
+    CK(ctx, cudaMemcpyAsync(c->feat_tab, tab.data(), sizeof(int2) * (size_t)np, cudaMemcpyHostToDevice, c->stream));
+    for (int b = 0; b < n;) {
+        int e = b + 1;
+        while (e < n && style[b0 + e] == style[b0 + e - 1] + cfg.style_dim) ++e;
+        CK(ctx, cudaMemcpyAsync(c->style + (size_t)b * cfg.style_dim, style[b0 + b], sizeof(float) * (size_t)(e - b) * cfg.style_dim,
+                                cudaMemcpyHostToDevice, c->stream));
+        b = e;
+    }
+    // the reference clears the whole [max_seq_len][emb] buffer first (fs2encoder.cpp:614): zero tail of every utterance
+    if (pad) CK(ctx, cudaMemsetAsync(c->enc_in, 0, sizeof(float) * (size_t)c->h_seg[n] * cfg.dim_in, c->stream));
+    c->launches++;
+    if (prof_begin(c, ZVX_K_NORM_AFFINE, 0, 0.0, 4.0 * ((double)np + (double)c->h_seg[n]) * cfg.dim_in)) return 1;
+    CK(ctx, length_regulate_launch(c->feat, c->feat_tab, (int)np, cfg.dim_in, c->enc_in, c->stream));
+    if (prof_end(c)) return 1;
+    if (run_decoder(c, c->mel)) return 1;
+    int16_t *d_pcm = reinterpret_cast<int16_t *>(c->wav);
+    if (run_vocoder(c, c->mel, pcm ? nullptr : c->wav, pcm ? d_pcm : nullptr)) return 1;
+    for (int b = 0; b < n; ++b) {
+        const size_t s0 = (size_t)c->h_seg[b] * cfg.hop_size, ns = (size_t)L[b0 + b] * cfg.hop_size;
+        if (pcm) CK(ctx, cudaMemcpyAsync(pcm[b0 + b], d_pcm + s0, sizeof(int16_t) * ns, cudaMemcpyDeviceToHost, c->stream));
+        else     CK(ctx, cudaMemcpyAsync(wav[b0 + b], c->wav + s0, sizeof(float) * ns, cudaMemcpyDeviceToHost, c->stream));
+        if (mel && mel[b0 + b])
+            CK(ctx, cudaMemcpyAsync(mel[b0 + b], c->mel + (size_t)c->h_seg[b] * cfg.num_mels, sizeof(float) * (size_t)L[b0 + b] * cfg.num_mels,
+                                    cudaMemcpyDeviceToHost, c->stream));
+    }
+    return 0;
+}
+
 int zvx_synth_batch_regulated(zvx_ctx *ctx, int32_t B, const float *const *features, const float *const *log_dur, const int32_t *P,
                               const float *const *style, int32_t max_seq_len, int32_t pad_to_max, int32_t *frames_out,
                               float *const *mel, float *const *wav, int16_t *const *pcm)
@@ -1719,78 +1790,44 @@ int zvx_synth_batch_regulated(zvx_ctx *ctx, int32_t B, const float *const *featu
     if (!features || !log_dur || !P || !style || (!wav == !pcm)) return fail(ctx, "zvx_synth_batch_regulated: null argument (exactly one of wav / pcm)");
     if (B <= 0) return fail(ctx, "empty batch");
     if (max_seq_len <= 0) return fail(ctx, "zvx_synth_batch_regulated: max_seq_len must be positive");
-    const zvx_config &cfg = ctx->cfg;
     CK(ctx, cudaSetDevice(ctx->device));
-    // host: durations -> valid frames per utterance, {first packed frame, count} per phoneme
-    std::vector<int32_t> L(B), valid(B);
-    std::vector<int2> tab;
-    int64_t np = 0, frame0 = 0;
+    // host: durations -> valid frames per utterance, {first frame inside the utterance, count} per phoneme
+    std::vector<int32_t> L(B);
+    std::vector<std::vector<int2>> rel(B);
+    int64_t frames = 0;
     for (int b = 0; b < B; ++b) {
         if (P[b] <= 0 || !features[b] || !log_dur[b] || !style[b]) return fail(ctx, "utterance %d: no phonemes / null pointer", b);
-        np += P[b];
-    }
-    tab.reserve((size_t)np);
-    for (int b = 0; b < B; ++b) {
+        rel[b].reserve((size_t)P[b]);
         int64_t x = 0;
         for (int32_t i = 0; i < P[b]; ++i) {
             const int32_t d = x < max_seq_len ? regulated_duration(log_dur[b][i], (int32_t)(max_seq_len - x)) : 0;
-            tab.push_back(make_int2((int)(frame0 + x), d));
+            rel[b].push_back(make_int2((int)x, d));
             x += d;
         }
-        valid[b] = (int32_t)x;
-        if (frames_out) frames_out[b] = valid[b];
-        L[b] = pad_to_max ? max_seq_len : valid[b];
+        if (frames_out) frames_out[b] = (int32_t)x;
+        L[b] = pad_to_max ? max_seq_len : (int32_t)x;
         if (L[b] <= 0) return fail(ctx, "utterance %d: all durations are zero", b);
-        frame0 += L[b];
+        frames += L[b];
     }
-    if (set_batch(ctx, B, L.data())) return 1;
-    // staging buffers (grown geometrically; growing synchronises, steady state does not)
-    const size_t need_f = (size_t)np * cfg.dim_in;
-    if (need_f > ctx->feat_cap) {
-        CK(ctx, cudaStreamSynchronize(ctx->stream));
-        const size_t cap = std::max(need_f, ctx->feat_cap * 2);
-        dev_free(ctx, ctx->feat); ctx->feat = nullptr; ctx->feat_cap = 0;
-        if (dev_alloc(ctx, &ctx->feat, cap)) return 1;
-        ctx->feat_cap = cap;
+    // like zvx_synth_batch: large batches alternate between the context and its lane, so that the copies of one
+    // sub-batch run under the kernels of the other
+    std::vector<int2> tabs[2];
+    int nch = ctx->e2e_chunks > 1 ? 2 : 1;
+    if (ctx->prof || ctx->debug_stop >= 0 || B < 4 || frames < 4096) nch = 1;
+    if (nch == 1) {
+        if (regulated_chunk(ctx, 0, B, features, P, style, rel, L.data(), pad_to_max != 0, tabs[0], mel, wav, pcm)) return 1;
+        return check_device_error(ctx);
     }
-    if ((size_t)np > ctx->feat_tab_cap) {
-        CK(ctx, cudaStreamSynchronize(ctx->stream));
-        const size_t cap = std::max((size_t)np, std::max(ctx->feat_tab_cap * 2, (size_t)1024));
-        dev_free(ctx, ctx->feat_tab); ctx->feat_tab = nullptr; ctx->feat_tab_cap = 0;
-        if (dev_alloc(ctx, &ctx->feat_tab, cap)) return 1;
-        ctx->feat_tab_cap = cap;
-    }
-    // H2D at PHONEME rate: [sum P][dim_in] instead of [sum L][dim_in] (one copy per run of contiguous host buffers)
-    size_t off = 0;
-    for (int b = 0; b < B;) {
-        int e = b + 1;
-        size_t rows = (size_t)P[b];
-        while (e < B && features[e] == features[e - 1] + (size_t)P[e - 1] * cfg.dim_in) rows += (size_t)P[e++];
-        CK(ctx, cudaMemcpyAsync(ctx->feat + off * cfg.dim_in, features[b], sizeof(float) * rows * cfg.dim_in, cudaMemcpyHostToDevice, ctx->stream));
-        off += rows;
-        b = e;
-    }
-    CK(ctx, cudaMemcpyAsync(ctx->feat_tab, tab.data(), sizeof(int2) * (size_t)np, cudaMemcpyHostToDevice, ctx->stream));
-    for (int b = 0; b < B; ++b)
-        CK(ctx, cudaMemcpyAsync(ctx->style + (size_t)b * cfg.style_dim, style[b], sizeof(float) * cfg.style_dim, cudaMemcpyHostToDevice, ctx->stream));
-    // the reference clears the whole [max_seq_len][emb] buffer first (fs2encoder.cpp:614): zero tail of every utterance
-    if (pad_to_max) CK(ctx, cudaMemsetAsync(ctx->enc_in, 0, sizeof(float) * (size_t)frame0 * cfg.dim_in, ctx->stream));
-    ctx->launches++;
-    if (prof_begin(ctx, ZVX_K_NORM_AFFINE, 0, 0.0, 4.0 * ((double)np + (double)frame0) * cfg.dim_in)) return 1;
-    CK(ctx, length_regulate_launch(ctx->feat, ctx->feat_tab, (int)np, cfg.dim_in, ctx->enc_in, ctx->stream));
-    if (prof_end(ctx)) return 1;
-    // (`tab` outlives its asynchronous copy: this function ends with a stream synchronisation)
-    if (run_decoder(ctx, ctx->mel)) return 1;
-    int16_t *d_pcm = reinterpret_cast<int16_t *>(ctx->wav);
-    if (run_vocoder(ctx, ctx->mel, pcm ? nullptr : ctx->wav, pcm ? d_pcm : nullptr)) return 1;
-    for (int b = 0; b < B; ++b) {
-        const size_t s0 = (size_t)ctx->h_seg[b] * cfg.hop_size, n = (size_t)L[b] * cfg.hop_size;
-        if (pcm) CK(ctx, cudaMemcpyAsync(pcm[b], d_pcm + s0, sizeof(int16_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
-        else     CK(ctx, cudaMemcpyAsync(wav[b], ctx->wav + s0, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
-        if (mel && mel[b])
-            CK(ctx, cudaMemcpyAsync(mel[b], ctx->mel + (size_t)ctx->h_seg[b] * cfg.num_mels, sizeof(float) * (size_t)L[b] * cfg.num_mels,
-                                    cudaMemcpyDeviceToHost, ctx->stream));
-    }
+    if (make_lane(ctx)) return 1;
+    ctx->lane->use_ref_kernels = ctx->use_ref_kernels;
+    ctx->lane->use_fused = ctx->use_fused;
+    int b0 = 0;
+    int64_t acc = 0;
+    while (b0 < B - 1 && 2 * (acc + L[b0]) <= frames) acc += L[b0++];
+    if (b0 == 0) b0 = 1;
+    if (regulated_chunk(ctx, 0, b0, features, P, style, rel, L.data(), pad_to_max != 0, tabs[0], mel, wav, pcm)) return 1;
+    if (regulated_chunk(ctx->lane, b0, B, features, P, style, rel, L.data(), pad_to_max != 0, tabs[1], mel, wav, pcm)) { ctx->err = ctx->lane->err; return 1; }
+    if (check_device_error(ctx->lane)) { ctx->err = ctx->lane->err; return 1; }
     return check_device_error(ctx);
 }
 
