@@ -105,6 +105,7 @@ struct zvx_ctx {
     // the three independent residual blocks of an MRF stage run on three streams (inside a graph capture: three parallel
     // branches of the graph): a single short utterance leaves most launches under-filled, and for large batches the tail
     // of one block's persistent kernel overlaps the start of the next
+    int h2d_chain = 1;          // zvx_synth_batch: a sub-batch's input copies wait for the previous sub-batch's
     int device_split = 1;       // zvx_synth_batch_device: two half batches, on the context and on its lane
     cudaEvent_t split_ev[2] = {nullptr, nullptr};
     int fork_branches = 1;
@@ -1339,6 +1340,7 @@ int zvx_create(zvx_ctx **out, const zvx_config *cfg, const zvx_tensor_desc *weig
     if (const char *e = getenv("ZVX_GRAPHS")) ctx->use_graphs = atoi(e);
     if (const char *e = getenv("ZVX_FORK_BRANCHES")) ctx->fork_branches = atoi(e);
     if (const char *e = getenv("ZVX_DEVICE_SPLIT")) ctx->device_split = atoi(e);
+    if (const char *e = getenv("ZVX_H2D_CHAIN")) ctx->h2d_chain = atoi(e);
     if (const char *e = getenv("ZVX_CHUNK_GROUP_MAX")) ctx->chunk_group_max = std::max(1, atoi(e));
     if (const char *e = getenv("ZVX_CONV_PERSISTENT")) ctx->conv_persistent = atoi(e);
     if (const char *e = getenv("ZVX_FUSED_UPCONV")) ctx->use_fused_upconv = atoi(e);
@@ -1528,13 +1530,17 @@ int zvx_vocode_batch_device(zvx_ctx *ctx, int32_t B, const float *d_mel, const i
 
 // one sub-batch [b0, b1) of zvx_synth_batch on context / lane `c`, everything asynchronous on c->stream
 // (wav: float samples; or pcm: 16-bit samples converted by the output conv itself, staged in the same device buffer)
+// wait_ev / done_ev (may be null): input copies start after wait_ev and done_ev is recorded behind them, so that the input
+// copies of consecutive sub-batches do not share the PCIe link (the first sub-batch can start computing earlier)
 static int synth_chunk(zvx_ctx *c, int b0, int b1, const float *const *enc_seq, const float *const *style, const int32_t *L,
-                       float *const *mel, float *const *wav, int16_t *const *pcm = nullptr)
+                       float *const *mel, float *const *wav, int16_t *const *pcm = nullptr, cudaEvent_t wait_ev = nullptr,
+                       cudaEvent_t done_ev = nullptr)
 {
     zvx_ctx *ctx = c;
     const zvx_config &cfg = c->cfg;
     const int n = b1 - b0;
     if (set_batch(c, n, L + b0)) return 1;
+    if (wait_ev) CK(ctx, cudaStreamWaitEvent(c->stream, wait_ev, 0));
     // one copy per run of utterances whose host buffers are contiguous (the common packed layout)
     for (int b = 0; b < n;) {
         int e = b + 1;
@@ -1550,6 +1556,7 @@ static int synth_chunk(zvx_ctx *c, int b0, int b1, const float *const *enc_seq, 
                                 cudaMemcpyHostToDevice, c->stream));
         b = e;
     }
+    if (done_ev) CK(ctx, cudaEventRecord(done_ev, c->stream));
     if (run_decoder(c, c->mel)) return 1;
     if (pcm) {
         int16_t *d_pcm = reinterpret_cast<int16_t *>(c->wav);
@@ -1621,9 +1628,13 @@ static int synth_batch_impl(zvx_ctx *ctx, int32_t B, const float *const *enc_seq
     }
     if (reserve(ctx, maxf, maxb)) return 1;
     if (reserve(ctx->lane, maxf, maxb)) { ctx->err = ctx->lane->err; return 1; }
+    for (int j = 0; j < 2; ++j)
+        if (!ctx->split_ev[j]) CK(ctx, cudaEventCreateWithFlags(&ctx->split_ev[j], cudaEventDisableTiming));
+    const bool chain = ctx->h2d_chain != 0;
     for (size_t q = 0; q + 1 < cut.size(); ++q) {
         zvx_ctx *c = (q & 1) ? ctx->lane : ctx;
-        if (synth_chunk(c, cut[q], cut[q + 1], enc_seq, style, L, mel, wav, pcm)) { if (c != ctx) ctx->err = c->err; return 1; }
+        if (synth_chunk(c, cut[q], cut[q + 1], enc_seq, style, L, mel, wav, pcm, (chain && q > 0) ? ctx->split_ev[(q - 1) & 1] : nullptr,
+                        chain ? ctx->split_ev[q & 1] : nullptr)) { if (c != ctx) ctx->err = c->err; return 1; }
     }
     if (check_device_error(ctx->lane)) { ctx->err = ctx->lane->err; return 1; }
     return check_device_error(ctx);
