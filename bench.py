@@ -54,7 +54,8 @@ def config_dict(args, world):
                     "features[L,528]+style[528] -> mel[L,80] -> wav[L*300], random-init GGUF (zv2gguf layout, seed 1234)",
         "utterances_per_step_per_gpu": args.batch,
         "length_seed": 11,
-        "sharding": f"utterance-sharded x{world}, no collective",
+        "sharding": f"one pool of {args.batch} x {world} utterances dealt longest-first to the least loaded of {world} rank(s) "
+                    f"(sharding.shard_utterances), no collective on the data path",
         "l2": "working set per step (several GB of activations) >> 126 MB L2; no explicit flush",
     }
 
@@ -136,11 +137,15 @@ def reference_arm(args, rank, world):
     from zvxload import zvx
     import refrun
     lengths = zvx.synth.batch_lengths(args.batch, seed=11)
-    L = int(lengths.min())
+    L = int(sorted(lengths)[len(lengths) // 2])      # the median utterance of the batch
     threads = os.cpu_count() or 1
+    cfg = config_dict(args, world)
+    cfg["reference_arm_sample"] = (f"ONE CPU process ({threads} host threads) at every N; each step = one utterance of the workload "
+                                   f"(the median length of the pool, L={L} frames), not the whole batch: the metric is "
+                                   f"normalised (audio-s/s), the batch is the same distribution")
     base = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16xf16->f32",
-            "data": "synthetic", "config": config_dict(args, world)}
+            "data": "synthetic", "config": cfg}
     if not refrun.available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (needs /root/reference at build time)"}))
         return
@@ -149,7 +154,7 @@ def reference_arm(args, rank, world):
     total = sum(timed)
     audio_s = L / FRAMES_PER_AUDIO_S
     value = audio_s * len(timed) / total
-    sample = (f"each step = the shortest utterance of the batch (L={L} frames, {audio_s:.2f} s audio) through the "
+    sample = (f"each step = the median utterance of the batch (L={L} frames, {audio_s:.2f} s audio) through the "
               f"unmodified reference decoder+vocoder ({binary}), ggml CPU backend")
     base.update({"value": value, "ms_per_step": 1000.0 * total / len(timed), "gpu_launches": 0,
                  "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
@@ -209,8 +214,12 @@ def main():
     zvx.synth.write_model(gguf)
     ctx = capi.Context.from_gguf(gguf, device=local_rank)
 
-    B = args.batch
-    lengths = zvx.synth.batch_lengths(B, seed=11 + rank)
+    # configs[3] design at every N: ONE pool of batch x N utterances, dealt longest-first to the least loaded rank
+    # (zerovox.cpp_b200/sharding.py; every rank derives the same assignment from the length list alone)
+    pool = zvx.synth.batch_lengths(args.batch * world, seed=11)
+    mine = zvx.sharding.shard_utterances(pool, world)[rank]
+    lengths = pool[mine]
+    B = len(lengths)
     F = int(lengths.sum())
     audio_s = F / FRAMES_PER_AUDIO_S
     Larr = (ctypes.c_int32 * B)(*[int(x) for x in lengths])
@@ -250,6 +259,12 @@ def main():
     clk = clocks.stop()
     ms_total = max_over_ranks(ms_total)
     total_audio = sum_over_ranks(audio_s)
+    per_rank = [(B, F)]
+    if world > 1:
+        t = torch.tensor([B, F], dtype=torch.int64, device="cuda")
+        gathered = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(gathered, t)
+        per_rank = [(int(x[0]), int(x[1])) for x in gathered]
     value = total_audio * args.steps / (ms_total / 1000.0)
 
     # ---------------- per-launch CUDA-event timing (separate pass: events between all launches) ----------------
@@ -324,6 +339,29 @@ def main():
                "h2d_bytes_per_step": int(poffs[-1]) * (ctx.dim_in * 4 + 4 + 8) + B * ctx.style_dim * 4, "d2h_bytes_per_step": int(F * ctx.hop * 2),
                "phonemes_per_step": int(poffs[-1]), "pcm_checksum": int(h_pcm[:: 997].long().abs().sum())}
 
+    # ---------------- parity of this very build against the committed reference output (configs[0], L = 400) ----------------
+    parity = None
+    gpath = os.path.join(ROOT, "tests", "golden", "ref_L400.npz")
+    if rank == 0 and os.path.exists(gpath):
+        gold = np.load(gpath)
+        p_enc, p_sty = zvx.synth.make_inputs(400)
+
+        def snr_db(ref, x):
+            ref = np.asarray(ref, np.float64).ravel()
+            err = np.asarray(x, np.float64).ravel() - ref
+            return float(10.0 * np.log10(np.sum(ref * ref) / max(np.sum(err * err), 1e-300)))
+
+        p_mels, p_wavs = ctx.synth_batch([p_enc], [p_sty])
+        p_voc = ctx.vocode(gold["mel"])
+        parity = {"against": "tests/golden/ref_L400.npz = output of the unmodified reference (oracle/_ref/zvref_native) for "
+                             "synth.make_inputs(400), generator tests/golden/make_golden.py",
+                  "mel_snr_db": snr_db(gold["mel"], p_mels[0]), "wav_snr_db": snr_db(gold["wav"], p_wavs[0]),
+                  "wav_max_abs_err": float(np.abs(p_wavs[0] - gold["wav"]).max()),
+                  "vocoder_only_snr_db": snr_db(gold["wav"], p_voc),
+                  "vocoder_only_max_abs_err": float(np.abs(p_voc - gold["wav"]).max()),
+                  "gates": "wav >= 60 dB and <= 1e-3 max-abs (north star), mel >= 55 dB (tests/test_parity_gpu.py)",
+                  "reference_self_floor_db": {"mel": snr_db(gold["mel"], gold["mel_v3"]), "wav": snr_db(gold["wav"], gold["wav_v3"])}}
+
     # ---------------- roofline of the dominant kernel ----------------
     peak_tf, peak_gbs, peak_src = measured_peaks()
     by = {}
@@ -366,8 +404,9 @@ def main():
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(F * ctx.dim_in * 4 + B * ctx.style_dim * 4),
                    "d2h_bytes_per_step": int(F * ctx.hop * 4), "wav_checksum": checksum},
            "e2e_pcm16": e2e_pcm, "e2e_regulated_pcm16": e2e_reg,
-           "roofline": roofline, "kernel_breakdown": breakdown,
-           "audio_s_per_step_per_gpu": audio_s}
+           "parity": parity, "roofline": roofline, "kernel_breakdown": breakdown,
+           "audio_s_per_step_per_gpu": audio_s,
+           "shards": {"utterances_per_rank": [x[0] for x in per_rank], "frames_per_rank": [x[1] for x in per_rank]}}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:

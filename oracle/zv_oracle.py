@@ -224,10 +224,12 @@ def wav_file_bytes(pcm, sample_rate):
 
 # ---------------------------------------------------------------------------------------------
 # Length regulator: restatement of the host loop at the end of
-# FS2Encoder::eval, /root/reference/src/fs2encoder.cpp:611-654.  PARITY UNPINNED for this function: the
-# loop is not callable on its own (it sits behind the FastSpeech2 graph, whose weights are not in the
-# repository) and the reference has no test vector for it; tests/test_regulator_*.py therefore check the
-# library against THIS restatement only, plus hand-computed cases.
+# FS2Encoder::eval, /root/reference/src/fs2encoder.cpp:611-654.  PINNED: the unmodified reference program
+# (oracle/_ref/zvfull_*: zerovox.cpp + fs2encoder.cpp compiled where they lie) is run on a random-init GGUF that
+# carries the FastSpeech2 tensors; its graph outputs (features, log-durations), the expanded hidden_state and the
+# returned frame count are committed as tests/golden/regulator_*.npz (generator tests/golden/make_golden.py) and
+# tests/test_regulator_cpu.py checks this function against them bit-exactly (default sentence, a random one, and
+# one whose expansion hits max_seq_len).
 def length_regulate(features, log_dur, max_seq_len):
     """-> (x [max_seq_len][emb] with zero tail, number of valid frames)"""
     import math

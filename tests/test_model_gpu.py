@@ -1,0 +1,74 @@
+"""GPU test of the caller row: host/_build/zvx_model = ZeroVOXModelB200 -- the reference's ZeroVOXModel
+with the B200 decoder / vocoder behind it and the FastSpeech2 encoder left on the host (the reference's own fs2encoder.cpp).
+Checked against what the unmodified reference program produced for the same sentences (tests/golden/regulator_*.npz) and,
+for the valid-frames mode the reference cannot express, against a live reference run at exactly that length."""
+import json
+import os
+import struct
+import subprocess
+import wave
+
+import numpy as np
+import pytest
+
+import zv_oracle
+from conftest import ROOT
+from test_regulator_cpu import regulator_golden
+
+pytestmark = pytest.mark.gpu
+
+EXE = os.path.join(ROOT, "zerovox.cpp_b200", "host", "_build", "zvx_model")
+
+
+def _write_sentence(path, g):
+    with open(path, "wb") as f:
+        f.write(struct.pack("<i", 120))
+        f.write(np.ascontiguousarray(g["src"], np.int32).tobytes())
+        f.write(np.ascontiguousarray(g["puncts"], np.int32).tobytes())
+        f.write(np.ascontiguousarray(g["style"], np.float32).tobytes())
+
+
+def _run(args):
+    r = subprocess.run([EXE] + args, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+@pytest.fixture(scope="module")
+def full_gguf(zvx):
+    return zvx.synth.write_model(zvx.synth.default_model_path(with_fs2=True), with_fs2=True)
+
+
+def test_model_reference_default_mode_matches_reference_program(full_gguf, tmp_path):
+    """max_seq_len frames with the zero tail (what ZeroVOXModel::eval does): frame count and waveform of the reference."""
+    assert os.path.exists(EXE), "host/_build/zvx_model missing (built by __graft_entry__.build() where /root/reference exists)"
+    g, _, frames, T = regulator_golden("default")
+    _write_sentence(tmp_path / "s0.bin", g)
+    j = _run([full_gguf, str(tmp_path / "o"), "--reference-default", str(tmp_path / "s0.bin")])
+    assert j["frames"] == [frames] and j["mode"] == "reference_default"
+    pcm = np.fromfile(tmp_path / "o.0.pcm.i16", dtype=np.int16)
+    assert pcm.size == T * 300
+    ref = zv_oracle.pcm16(g["wav"])
+    assert int(np.abs(pcm.astype(np.int32) - ref.astype(np.int32)).max()) <= 33          # 1e-3 of full scale
+    assert zv_oracle.snr_db(g["wav"], pcm.astype(np.float32) / 32767.0) >= 55.0           # + PCM_16 quantisation noise
+    with wave.open(str(tmp_path / "o.0.wav"), "rb") as w:
+        assert (w.getnchannels(), w.getsampwidth(), w.getframerate(), w.getnframes()) == (1, 2, 24000, T * 300)
+        assert np.array_equal(np.frombuffer(w.readframes(T * 300), dtype="<i2"), pcm)
+
+
+def test_model_valid_frames_and_batched_eval(full_gguf, gguf_path, tmp_path):
+    """f1: only the frames the length regulator produced are synthesised (vs a live reference at that length), and a batch
+    of sentences through ONE GPU call equals the sentences one by one, bit for bit."""
+    import refrun
+    gs = [regulator_golden(n) for n in ("default", "random")]
+    for i, (g, _, _, _) in enumerate(gs):
+        _write_sentence(tmp_path / f"s{i}.bin", g)
+    j = _run([full_gguf, str(tmp_path / "b"), str(tmp_path / "s0.bin"), str(tmp_path / "s1.bin")])
+    assert j["frames"] == [gs[0][2], gs[1][2]] and j["mode"] == "valid_frames"
+    for i, (g, hidden, frames, _) in enumerate(gs):
+        pcm = np.fromfile(tmp_path / f"b.{i}.pcm.i16", dtype=np.int16)
+        assert pcm.size == frames * 300
+        _run([full_gguf, str(tmp_path / f"one{i}"), str(tmp_path / f"s{i}.bin")])
+        assert np.array_equal(np.fromfile(tmp_path / f"one{i}.0.pcm.i16", dtype=np.int16), pcm)
+        ref = refrun.run(gguf_path, frames, hidden[:frames], g["style"])
+        assert int(np.abs(pcm.astype(np.int32) - zv_oracle.pcm16(ref["wav"]).astype(np.int32)).max()) <= 33

@@ -177,6 +177,43 @@ def test_full_size_batch_properties(ctx, zvx):
     assert ctx.kernel_launches() > 0
 
 
+def test_bench_batch_utterances_match_own_length_reference(ctx, zvx, gguf_path):
+    """the bench's own batch (64 utterances, lengths batch_lengths(64, seed=11)) goes through ONE
+    zvx_synth_batch call; the shortest, the longest and two random utterances taken out of it are compared with the live
+    reference, each run in its own process at its own length (statistics span exactly L frames)."""
+    import refrun
+    lengths = zvx.synth.batch_lengths(64, seed=11)
+    ins = [zvx.synth.make_inputs(int(L), seed=1000 + b) for b, L in enumerate(lengths)]
+    mels, wavs = ctx.synth_batch([e for e, _ in ins], [s for _, s in ins])
+    rng = np.random.default_rng(17)
+    picks = {int(np.argmin(lengths)), int(np.argmax(lengths))}
+    while len(picks) < 4:
+        picks.add(int(rng.integers(0, 64)))
+    for b in sorted(picks):
+        L = int(lengths[b])
+        r = refrun.run(gguf_path, L, ins[b][0], ins[b][1])
+        assert wavs[b].shape == (L * 300,)
+        assert zv_oracle.snr_db(r["mel"], mels[b]) >= 55.0, (b, L)
+        assert zv_oracle.snr_db(r["wav"], wavs[b]) >= 60.0, (b, L)
+        assert float(np.abs(r["wav"] - wavs[b]).max()) <= 1e-3, (b, L)
+
+
+def test_large_mean_channels_instance_norm(ctx, zvx, gguf_path):
+    """InstanceNorm statistics with |mean| >> sigma in some channels: the library accumulates sum / sum of squares in
+    double in one pass, the reference subtracts the mean first (ggml-cpu.c:6906-6922); both must agree when the variance is
+    a tiny difference of large numbers."""
+    import refrun
+    L = 96
+    enc, sty = zvx.synth.make_inputs(L, seed=31)
+    enc[:, 0:8] += 60.0
+    enc[:, 100:104] -= 250.0
+    enc[:, 300] = 1000.0 + 1e-3 * enc[:, 300]
+    r = refrun.run(gguf_path, L, enc, sty, stage="dec")
+    mel = ctx.decode(enc, sty)
+    assert np.all(np.isfinite(mel))
+    assert zv_oracle.snr_db(r["mel"], mel) >= 55.0
+
+
 def test_error_behaviour(ctx):
     """Errors surface as exceptions carrying zvx_last_error (reference: std::runtime_error)."""
     from zerovox_cpp_b200 import capi

@@ -1,11 +1,37 @@
 """CPU tests of the length regulator row: the restatement of fs2encoder.cpp:611-654 in
 oracle/zv_oracle.py on hand-computed cases, and the library's host-side frame count (zvx_regulated_frames)
-against it on random and edge inputs.  (Parity of this row is UNPINNED: the reference loop cannot run on its own.)"""
+against it on random and edge inputs.  The restatement itself is pinned by outputs of the unmodified reference program
+(tests/golden/regulator_*.npz, made by tests/golden/make_golden.py from oracle/_ref/zvfull_native)."""
 import math
+import os
 
 import numpy as np
+import pytest
 
 import zv_oracle
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def regulator_golden(name):
+    g = np.load(os.path.join(GOLDEN, f"regulator_{name}.npz"))
+    frames, T = int(g["frames"]), int(g["max_seq_len"])
+    hidden = np.zeros((T, g["feat"].shape[1]), np.float32)
+    hidden[:frames] = g["feat"][g["frame_src"][:frames]]
+    return g, hidden, frames, T
+
+
+@pytest.mark.parametrize("name", ["default", "random", "capped"])
+def test_restatement_pinned_by_reference_outputs(zvx, name):
+    """FS2Encoder::eval of the unmodified reference: hidden_state and the returned frame count, bit-exact."""
+    from zerovox_cpp_b200 import capi
+    g, hidden, frames, T = regulator_golden(name)
+    x, n = zv_oracle.length_regulate(g["feat"], g["logdur"], T)
+    assert n == frames
+    assert np.array_equal(x.view(np.uint32), hidden.view(np.uint32))
+    assert capi.regulated_frames(g["logdur"], T) == frames
+    if name == "capped":
+        assert frames == T          # the expansion was cut at max_seq_len (fs2encoder.cpp:636-640)
 
 
 def test_restated_regulator_hand_cases():

@@ -1,13 +1,49 @@
 """GPU tests of the length regulator row: zvx_synth_batch_regulated (phoneme-rate features
 expanded on the GPU) must equal zvx_synth_batch fed the matrix the restated host loop (fs2encoder.cpp:611-654)
 produces -- bit-exact, the regulator is index work -- in both modes: reference-default (max_seq_len frames, zero
-tail) and valid-frames-only."""
+tail) and valid-frames-only.  Pinned against the unmodified reference program: tests/golden/regulator_*.npz hold what
+ZeroVOXModel::eval / FS2Encoder::eval produced (hidden_state, frame count, mel, wav at max_seq_len = 1500)."""
 import numpy as np
 import pytest
 
 import zv_oracle
+from test_regulator_cpu import regulator_golden
 
 pytestmark = pytest.mark.gpu
+
+
+def test_regulator_matches_reference_program(ctx):
+    """The three reference runs as ONE batch in reference-default mode: the decoder input the GPU expansion writes is
+    bit-identical to the reference's hidden_state, frame counts are the reference's, and the default sentence's mel / wav
+    (1500 frames, zero tail, statistics over the tail: SURVEY.md N2) meet the parity gates."""
+    gs = [regulator_golden(n) for n in ("default", "random", "capped")]
+    T = gs[0][3]
+    valid, wavs, mels = ctx.synth_batch_regulated([g[0]["feat"] for g in gs], [g[0]["logdur"] for g in gs],
+                                                  [g[0]["style"] for g in gs], T, True, want_mel=True)
+    assert valid == [g[2] for g in gs]
+    dim = gs[0][0]["feat"].shape[1]
+    g0 = gs[0][0]
+    assert zv_oracle.snr_db(g0["mel"], mels[0]) >= 55.0
+    assert zv_oracle.snr_db(g0["wav"], wavs[0]) >= 60.0
+    assert float(np.abs(g0["wav"] - wavs[0]).max()) <= 1e-3
+    # decoder input: a single-lane call keeps all three utterances in one workspace
+    for g, hidden, frames, _ in gs:
+        v, _ = ctx.synth_batch_regulated([g["feat"]], [g["logdur"]], [g["style"]], T, True)
+        assert v == [frames]
+        x = ctx.debug_fetch("enc_in", T * dim).reshape(T, dim)
+        assert np.array_equal(x.view(np.uint32), hidden.view(np.uint32))
+
+
+def test_valid_frames_mode_matches_own_length_reference(ctx, gguf_path):
+    """f1: synthesising only the valid frames equals the reference built for exactly that length (live reference run)."""
+    import refrun
+    g, hidden, frames, T = regulator_golden("default")
+    valid, wavs, mels = ctx.synth_batch_regulated([g["feat"]], [g["logdur"]], [g["style"]], T, False, want_mel=True)
+    assert valid == [frames] and wavs[0].size == frames * 300
+    ref = refrun.run(gguf_path, frames, hidden[:frames], g["style"])
+    assert zv_oracle.snr_db(ref["mel"], mels[0]) >= 55.0
+    assert zv_oracle.snr_db(ref["wav"], wavs[0]) >= 60.0
+    assert float(np.abs(ref["wav"] - wavs[0]).max()) <= 1e-3
 
 
 def _utterances(zvx, n, seed, dim=528):

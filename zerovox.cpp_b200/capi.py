@@ -290,8 +290,8 @@ class Context:
         return pcm
 
     def synth_batch_regulated(self, feats: Sequence[np.ndarray], log_durs: Sequence[np.ndarray], style_list: Sequence[np.ndarray],
-                              max_seq_len: int, pad_to_max: bool, pcm16: bool = False):
-        """zvx_synth_batch_regulated: phoneme-rate features + log-durations -> (valid frame counts, waveforms)."""
+                              max_seq_len: int, pad_to_max: bool, pcm16: bool = False, want_mel: bool = False):
+        """zvx_synth_batch_regulated: phoneme-rate features + log-durations -> (valid frame counts, waveforms[, mels])."""
         B = len(feats)
         fs = [np.ascontiguousarray(f, np.float32) for f in feats]
         ds = [np.ascontiguousarray(d, np.float32) for d in log_durs]
@@ -305,8 +305,12 @@ class Context:
         ps = (vp * B)(*[s.ctypes.data for s in stys])
         po = (vp * B)(*[o.ctypes.data for o in outs])
         valid = (C.c_int32 * B)()
-        self._check(self.lib.zvx_synth_batch_regulated(self.h, B, pf, pd, Ps, ps, int(max_seq_len), int(pad_to_max), valid, None,
+        mels = [np.empty((n, self.num_mels), np.float32) for n in frames] if want_mel else None
+        pm = (vp * B)(*[m.ctypes.data for m in mels]) if want_mel else None
+        self._check(self.lib.zvx_synth_batch_regulated(self.h, B, pf, pd, Ps, ps, int(max_seq_len), int(pad_to_max), valid, pm,
                                                        None if pcm16 else po, po if pcm16 else None))
+        if want_mel:
+            return list(valid), outs, mels
         return list(valid), outs
 
     def synth_batch_regulated_ptrs(self, B: int, feat_ptrs, logdur_ptrs, P, style_ptrs, max_seq_len: int, pad_to_max: bool, wav_ptrs, pcm_ptrs):

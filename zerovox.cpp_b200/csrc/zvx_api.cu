@@ -115,6 +115,7 @@ struct zvx_ctx {
     __half *fkH16[2] = {nullptr, nullptr};
     struct GraphEntry { int kind, L, flags; cudaGraphExec_t exec; int64_t launches; };
     std::vector<GraphEntry> graphs;
+    std::map<std::pair<int, int>, int> graph_seen;   // (kind, L) -> calls so far: a length is captured the second time it is seen
     int use_graphs = 1;
     int chunk_group_max = 8;   // zvx_vocode_chunked: at most this many chunks per vocoder pass
     int conv_smem_kb = 100;   // shared-memory budget of a one-tile conv CTA (two CTAs per SM)
@@ -597,13 +598,21 @@ int reserve(zvx_ctx *ctx, int64_t frames, int batch)
 {
     if (batch > ctx->cap_batch || frames > ctx->cap_frames) drop_graphs(ctx);
     const zvx_config &c = ctx->cfg;
+    // Growth frees the old buffers first (they are large), so a failed allocation must leave the context in a state a
+    // smaller retry can recover from: pointers nulled and the capacity zeroed BEFORE anything is freed, the new capacity
+    // published only after every allocation has succeeded.
     if (batch > ctx->cap_batch) {
         const int nb = std::max(std::max(batch, 64), 2 * ctx->cap_batch);   // grow geometrically: every growth reallocates
         const int nr = (int)std::max<size_t>(ctx->rates.size(), 1);
         const int nw = (int)std::max<size_t>(ctx->wincfg.size(), 1);
-        dev_free(ctx, ctx->d_seg); dev_free(ctx, ctx->d_tiles); dev_free(ctx, ctx->d_wins); dev_free(ctx, ctx->mu); dev_free(ctx, ctx->rstd);
-        dev_free(ctx, ctx->adain_gb); dev_free(ctx, ctx->style);
+        ctx->cap_batch = 0;
         if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+        {
+            int **ib[] = {&ctx->d_seg, &ctx->d_tiles, &ctx->d_wins};
+            for (int **b : ib) { dev_free(ctx, *b); *b = nullptr; }
+            float **fb[] = {&ctx->mu, &ctx->rstd, &ctx->adain_gb, &ctx->style};
+            for (float **b : fb) { dev_free(ctx, *b); *b = nullptr; }
+        }
         if (ctx->pin_tables) cudaFreeHost(ctx->pin_tables);
         ctx->pin_tables = nullptr;
         ctx->tables_pending = false;
@@ -619,6 +628,8 @@ int reserve(zvx_ctx *ctx, int64_t frames, int batch)
     }
     if (frames > ctx->cap_frames) {
         const int64_t F = std::max<int64_t>(frames, 256);
+        ctx->cap_frames = 0;
+        if (ctx->stream) cudaStreamSynchronize(ctx->stream);
         float **bufs[] = {&ctx->enc_in, &ctx->sc, &ctx->h528, &ctx->e0, &ctx->h1056, &ctx->catA, &ctx->catB, &ctx->asr,
                           &ctx->d1, &ctx->d2, &ctx->mel, &ctx->v0, &ctx->U, &ctx->CS, &ctx->Y1, &ctx->VA, &ctx->VB, &ctx->T2, &ctx->wav};
         for (float **b : bufs) { dev_free(ctx, *b); *b = nullptr; }
@@ -1179,12 +1190,21 @@ int run_graphed(zvx_ctx *ctx, int kind, int L, F body)
 {
     if (!ctx->use_graphs || ctx->prof || ctx->debug_stop >= 0 || ctx->use_ref_kernels) return body();
     const int flags = ctx->use_fused;
-    for (auto &g : ctx->graphs)
+    for (size_t i = 0; i < ctx->graphs.size(); ++i) {
+        const zvx_ctx::GraphEntry g = ctx->graphs[i];
         if (g.kind == kind && g.L == L && g.flags == flags) {
+            // least-recently-used order: a hit moves to the back, eviction takes the front
+            ctx->graphs.erase(ctx->graphs.begin() + (long)i);
+            ctx->graphs.push_back(g);
             CK(ctx, cudaGraphLaunch(g.exec, ctx->stream));
             ctx->launches += g.launches;
             return 0;
         }
+    }
+    // a length seen for the first time runs directly: natural variable-length traffic would otherwise pay capture +
+    // instantiation of ~100 nodes on almost every call and evict the graphs of the lengths that do repeat
+    if (ctx->graph_seen.size() > 4096) ctx->graph_seen.clear();
+    if (ctx->graph_seen[std::make_pair(kind, L)]++ == 0) return body();
     const int64_t l0 = ctx->launches;
     CK(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
     const int rc = body();
@@ -1245,15 +1265,21 @@ int make_lane(zvx_ctx *parent)
     l->d_seg = l->d_tiles = l->d_wins = l->d_err = l->pin_tables = nullptr;
     l->pin_in_cap = l->pin_out_cap = 0;
     l->graphs.clear();           // the copies of the parent's graph handles are not the lane's to destroy
+    l->graph_seen.clear();
     for (int j = 0; j < 2; ++j) { l->fork_stream[j] = nullptr; l->join_ev[j] = nullptr; l->fkY1[j] = l->fkT2[j] = nullptr; l->fkH16[j] = nullptr; }
     l->fork_ev = nullptr;
     l->feat = nullptr; l->feat_tab = nullptr; l->feat_cap = l->feat_tab_cap = 0;
+    // the lane is published only once it is complete: a half-built lane (null stream) must never be enqueued on
+    auto build = [&]() -> int {
+        zvx_ctx *ctx = parent;   // error reporting goes to the parent
+        CK(ctx, cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking));
+        CK(ctx, cudaEventCreateWithFlags(&l->tables_event, cudaEventDisableTiming));
+        if (dev_alloc(l, &l->d_err, 1)) { ctx->err = l->err; return 1; }
+        CK(ctx, cudaMemset(l->d_err, 0, sizeof(int)));
+        return 0;
+    };
+    if (build()) { zvx_destroy(l); return 1; }
     parent->lane = l;
-    zvx_ctx *ctx = parent;   // error reporting goes to the parent
-    CK(ctx, cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking));
-    CK(ctx, cudaEventCreateWithFlags(&l->tables_event, cudaEventDisableTiming));
-    if (dev_alloc(l, &l->d_err, 1)) { ctx->err = l->err; return 1; }
-    CK(ctx, cudaMemset(l->d_err, 0, sizeof(int)));
     return 0;
 }
 
@@ -1298,6 +1324,8 @@ void zvx_destroy(zvx_ctx *ctx)
         if (ctx->join_ev[j]) cudaEventDestroy(ctx->join_ev[j]);
     }
     if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
+    for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+    ctx->ev_pool.clear();
     for (int j = 0; j < 2; ++j)
         if (ctx->split_ev[j] && !ctx->is_lane) cudaEventDestroy(ctx->split_ev[j]);
     for (void *p : ctx->owned) cudaFree(p);
@@ -1411,6 +1439,7 @@ int zvx_synchronize(zvx_ctx *ctx)
 {
     if (!ctx) return 1;
     CK(ctx, cudaSetDevice(ctx->device));
+    if (ctx->lane && check_device_error(ctx->lane)) { ctx->err = ctx->lane->err; return 1; }
     return check_device_error(ctx);
 }
 
@@ -1557,10 +1586,15 @@ static int synth_chunk(zvx_ctx *c, int b0, int b1, const float *const *enc_seq, 
         b = e;
     }
     if (done_ev) CK(ctx, cudaEventRecord(done_ev, c->stream));
-    if (run_decoder(c, c->mel)) return 1;
+    // a single utterance (the latency path: ZeroVOXModel-style callers) replays decoder + vocoder from one CUDA graph per
+    // length, like zvx_decode / zvx_vocode; batches launch kernel by kernel
+    int16_t *d_pcm = reinterpret_cast<int16_t *>(c->wav);
+    auto compute = [&]() -> int {
+        if (run_decoder(c, c->mel)) return 1;
+        return pcm ? run_vocoder(c, c->mel, nullptr, d_pcm) : run_vocoder(c, c->mel, c->wav);
+    };
+    if (n == 1 ? run_graphed(c, pcm ? 4 : 3, (int)L[b0], compute) : compute()) return 1;
     if (pcm) {
-        int16_t *d_pcm = reinterpret_cast<int16_t *>(c->wav);
-        if (run_vocoder(c, c->mel, nullptr, d_pcm)) return 1;
         for (int b = 0; b < n;) {
             int e = b + 1;
             while (e < n && pcm[b0 + e] == pcm[b0 + e - 1] + (size_t)L[b0 + e - 1] * cfg.hop_size) ++e;
@@ -1569,14 +1603,13 @@ static int synth_chunk(zvx_ctx *c, int b0, int b1, const float *const *enc_seq, 
             b = e;
         }
     } else {
-    if (run_vocoder(c, c->mel, c->wav)) return 1;
-    for (int b = 0; b < n;) {
-        int e = b + 1;
-        while (e < n && wav[b0 + e] == wav[b0 + e - 1] + (size_t)L[b0 + e - 1] * cfg.hop_size) ++e;
-        CK(ctx, cudaMemcpyAsync(wav[b0 + b], c->wav + (size_t)c->h_seg[b] * cfg.hop_size,
-                                sizeof(float) * (size_t)(c->h_seg[e] - c->h_seg[b]) * cfg.hop_size, cudaMemcpyDeviceToHost, c->stream));
-        b = e;
-    }
+        for (int b = 0; b < n;) {
+            int e = b + 1;
+            while (e < n && wav[b0 + e] == wav[b0 + e - 1] + (size_t)L[b0 + e - 1] * cfg.hop_size) ++e;
+            CK(ctx, cudaMemcpyAsync(wav[b0 + b], c->wav + (size_t)c->h_seg[b] * cfg.hop_size,
+                                    sizeof(float) * (size_t)(c->h_seg[e] - c->h_seg[b]) * cfg.hop_size, cudaMemcpyDeviceToHost, c->stream));
+            b = e;
+        }
     }
     for (int b = 0; b < n; ++b)
         if (mel && mel[b0 + b])
@@ -1634,7 +1667,13 @@ static int synth_batch_impl(zvx_ctx *ctx, int32_t B, const float *const *enc_seq
     for (size_t q = 0; q + 1 < cut.size(); ++q) {
         zvx_ctx *c = (q & 1) ? ctx->lane : ctx;
         if (synth_chunk(c, cut[q], cut[q + 1], enc_seq, style, L, mel, wav, pcm, (chain && q > 0) ? ctx->split_ev[(q - 1) & 1] : nullptr,
-                        chain ? ctx->split_ev[q & 1] : nullptr)) { if (c != ctx) ctx->err = c->err; return 1; }
+                        chain ? ctx->split_ev[q & 1] : nullptr)) {
+            if (c != ctx) ctx->err = c->err;
+            // copies into the caller's buffers may still be in flight on either stream: drain both before reporting
+            cudaStreamSynchronize(ctx->stream);
+            cudaStreamSynchronize(ctx->lane->stream);
+            return 1;
+        }
     }
     if (check_device_error(ctx->lane)) { ctx->err = ctx->lane->err; return 1; }
     return check_device_error(ctx);
@@ -1836,8 +1875,16 @@ int zvx_synth_batch_regulated(zvx_ctx *ctx, int32_t B, const float *const *featu
     int64_t acc = 0;
     while (b0 < B - 1 && 2 * (acc + L[b0]) <= frames) acc += L[b0++];
     if (b0 == 0) b0 = 1;
-    if (regulated_chunk(ctx, 0, b0, features, P, style, rel, L.data(), pad_to_max != 0, tabs[0], mel, wav, pcm)) return 1;
-    if (regulated_chunk(ctx->lane, b0, B, features, P, style, rel, L.data(), pad_to_max != 0, tabs[1], mel, wav, pcm)) { ctx->err = ctx->lane->err; return 1; }
+    if (regulated_chunk(ctx, 0, b0, features, P, style, rel, L.data(), pad_to_max != 0, tabs[0], mel, wav, pcm)) {
+        cudaStreamSynchronize(ctx->stream);
+        return 1;
+    }
+    if (regulated_chunk(ctx->lane, b0, B, features, P, style, rel, L.data(), pad_to_max != 0, tabs[1], mel, wav, pcm)) {
+        ctx->err = ctx->lane->err;
+        cudaStreamSynchronize(ctx->stream);          // the first half's copies into the caller's buffers are still in flight
+        cudaStreamSynchronize(ctx->lane->stream);
+        return 1;
+    }
     if (check_device_error(ctx->lane)) { ctx->err = ctx->lane->err; return 1; }
     return check_device_error(ctx);
 }
@@ -1943,6 +1990,7 @@ int zvx_debug_fetch(zvx_ctx *ctx, const char *what, float *dst, int64_t n)
     int64_t have = 0;
     const int64_t F = ctx->last_frames;
     if (w == "mel") { src = ctx->mel; have = F * ctx->cfg.num_mels; }
+    else if (w == "enc_in") { src = ctx->enc_in; have = F * ctx->cfg.dim_in; }      // decoder input (length regulator output)
     else if (w == "v0") { src = ctx->v0; have = F * ctx->chans[0]; }
     else if (w == "u") { src = ctx->U; have = F * max_stage_elems(ctx); }
     else if (w.rfind("stage", 0) == 0 && w.size() == 6) {

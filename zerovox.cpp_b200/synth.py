@@ -123,19 +123,88 @@ def make_tensors(seed: int = 1234) -> Dict[str, np.ndarray]:
     return t
 
 
-def write_model(path: str, seed: int = 1234) -> str:
-    """Write the random-init GGUF to `path` unless it already exists; returns path."""
+NUM_PHONEMES = 154
+NUM_PUNCTS = 6
+MAX_N_PHONEMES = 120
+FS2_LAYERS = 4
+FS2_FILTER = 1024
+FS2_KERNELS = (9, 1)
+VP_FILTER = 256
+VP_KERNEL = 3
+VE_N_BINS = 256
+MAX_SEQ_LEN = 1500
+
+
+def sinusoid_table(n_position: int, d_hid: int) -> np.ndarray:
+    """Position-encoding table as zv2gguf.py:41-62 computes it (float32 angles, then sin / cos in place)."""
+    pos = np.arange(n_position, dtype=np.float64)[:, None]
+    hid = np.arange(d_hid)[None, :]
+    tab = (pos / np.power(10000.0, 2 * (hid // 2) / d_hid)).astype(np.float32)
+    tab[:, 0::2] = np.sin(tab[:, 0::2])
+    tab[:, 1::2] = np.cos(tab[:, 1::2])
+    return tab
+
+
+def make_fs2_tensors(seed: int = 1234) -> Dict[str, np.ndarray]:
+    """The FastSpeech2 encoder + variance adaptor tensors FS2Encoder's constructor looks up
+    (/root/reference/src/fs2encoder.cpp:29-62,152-171,256-261,344-382,504-505), dtypes per
+    zv2gguf.py:156-161 (pos_ffn.w_1/w_2 and the predictors' `conv.w` are F16, the rest F32).  Only the caller side of the
+    hot path (length regulator) and the reference oracle use them.  The duration predictor's output layer
+    is biased so that a random-init model gives durations of a few frames per phoneme."""
+    t: Dict[str, np.ndarray] = {}
+
+    def nrm(name, shape, scale, dtype=np.float32, mean=0.0):
+        t[name] = (mean + scale * _rng(name, seed).standard_normal(shape, dtype=np.float32)).astype(dtype)
+
+    nrm("_pe._enc.src_word_emb.w", (NUM_PHONEMES + 1, EMB_DIM), 1.0)
+    nrm("_pe._enc.punct_embed.w", (NUM_PUNCTS + 1, PUNCT_EMB_DIM), 1.0)
+    t["sinusoid_encoding_table"] = sinusoid_table(MAX_SEQ_LEN + 1, DIM)
+    for i in range(FS2_LAYERS):
+        p = f"_pe._enc.laystk.{i}"
+        for w in ("w_qs", "w_ks", "w_vs", "fc"):
+            nrm(f"{p}.slf_attn.{w}.w", (DIM, DIM), 1.0 / np.sqrt(DIM))
+            nrm(f"{p}.slf_attn.{w}.b", (DIM,), 0.02)
+        nrm(f"{p}.slf_attn.layer_norm.w", (DIM,), 0.1, mean=1.0)
+        nrm(f"{p}.slf_attn.layer_norm.b", (DIM,), 0.02)
+        nrm(f"{p}.pos_ffn.w_1.w", (FS2_FILTER, DIM, FS2_KERNELS[0]), 1.0 / np.sqrt(DIM * FS2_KERNELS[0]), np.float16)
+        nrm(f"{p}.pos_ffn.w_1.b", (FS2_FILTER,), 0.02)
+        nrm(f"{p}.pos_ffn.w_2.w", (DIM, FS2_FILTER, FS2_KERNELS[1]), 1.0 / np.sqrt(FS2_FILTER * FS2_KERNELS[1]), np.float16)
+        nrm(f"{p}.pos_ffn.w_2.b", (DIM,), 0.02)
+        nrm(f"{p}.pos_ffn.layer_norm.w", (DIM,), 0.1, mean=1.0)
+        nrm(f"{p}.pos_ffn.layer_norm.b", (DIM,), 0.02)
+    for vp, out_bias, out_scale in (("duration_predictor", 1.5, 0.6), ("pitch_predictor", 0.5, 0.25), ("engy_pred", 0.5, 0.25)):
+        p = f"_pe._var_adapt.{vp}"
+        nrm(f"{p}.conv_layer.conv1d_1.conv.w", (VP_FILTER, DIM, VP_KERNEL), 1.0 / np.sqrt(DIM * VP_KERNEL), np.float16)
+        nrm(f"{p}.conv_layer.conv1d_1.conv.b", (VP_FILTER,), 0.02)
+        nrm(f"{p}.conv_layer.conv1d_2.conv.w", (VP_FILTER, VP_FILTER, VP_KERNEL), 1.0 / np.sqrt(VP_FILTER * VP_KERNEL), np.float16)
+        nrm(f"{p}.conv_layer.conv1d_2.conv.b", (VP_FILTER,), 0.02)
+        for k in (1, 2):
+            nrm(f"{p}.conv_layer.layer_norm_{k}.w", (VP_FILTER,), 0.1, mean=1.0)
+            nrm(f"{p}.conv_layer.layer_norm_{k}.b", (VP_FILTER,), 0.02)
+        nrm(f"{p}.linear_layer.w", (1, VP_FILTER), out_scale / np.sqrt(VP_FILTER))
+        t[f"{p}.linear_layer.b"] = np.full((1,), out_bias, np.float32)
+    nrm("_pe._var_adapt.pitch_embedding.w", (VE_N_BINS, DIM), 0.3)
+    nrm("_pe._var_adapt.energy_embedding.w", (VE_N_BINS, DIM), 0.3)
+    return t
+
+
+def write_model(path: str, seed: int = 1234, with_fs2: bool = False) -> str:
+    """Write the random-init GGUF to `path` unless it already exists; returns path.  `with_fs2` adds the FastSpeech2
+    encoder tensors (the hot-path tensors are identical either way: every tensor has its own stream)."""
     if not os.path.exists(path):
         tmp = f"{path}.tmp.{os.getpid()}"
-        write_gguf(tmp, KV, make_tensors(seed))
+        tensors = make_tensors(seed)
+        if with_fs2:
+            tensors.update(make_fs2_tensors(seed))
+        write_gguf(tmp, KV, tensors)
         os.replace(tmp, path)
     return path
 
 
-def default_model_path(seed: int = 1234) -> str:
+def default_model_path(seed: int = 1234, with_fs2: bool = False) -> str:
     root = os.environ.get("ZVX_CACHE", "/tmp/zvx_cache")
     os.makedirs(root, exist_ok=True)
-    return os.path.join(root, f"zerovox-random-{seed}.gguf")
+    return os.path.join(root, f"zerovox-random-{'full-' if with_fs2 else ''}{seed}.gguf")
 
 
 def make_inputs(L: int, seed: int = 7) -> Tuple[np.ndarray, np.ndarray]:
