@@ -27,6 +27,8 @@
 //   * Epilogue: warps 0-3 read the accumulator with tcgen05.ld (one row per thread) and
 //     apply bias / residual / branch-sum / scale, writing fp32 and/or the next conv's
 //     fp16 pre-activated operand.
+#include <cstring>
+
 #include "zvx_common.cuh"
 #include "zvx_internal.h"
 #include "ptx_sm100.cuh"
@@ -199,14 +201,17 @@ __device__ __forceinline__ void produce_chunk(const ConvParams &p, const TileCoo
     }
 }
 
-// Epilogue of one warp = 32 accumulator rows (time steps) x NC columns.  tcgen05.ld hands every
-// thread one ROW; writing rows from there costs 32 cache lines per warp instruction (measured:
-// the epilogue took 45 % of a CTA's lifetime on the decoder convs, profiles/r01_ncu_conv_*).  So the
-// warp transposes through a private shared-memory slab, 64 columns at a time: afterwards a half-warp
-// owns 256 contiguous bytes of one row and every global access (residual / branch-sum reads, fp32
-// and fp16 writes) is a full-line transaction.  Residual loads of 4 row pairs are issued before use.
+// Epilogue of one warp = 32 accumulator rows (time steps) x a share of the NC columns.  tcgen05.ld hands every thread
+// one ROW; writing rows from there costs 32 cache lines per warp instruction.  So the warp transposes through a private
+// shared-memory slab, 32 columns at a time: afterwards a quarter-warp owns 128 contiguous bytes of one row and every
+// global access (residual / branch-sum reads, fp32 and fp16 writes) covers whole lines.
+// Round 2 (profiles/r02_ncu_conv_*): this code, not the MMAs, bounded every MRF stage-0 launch and a third of a decoder
+// conv's life -- ~1700 instructions per warp and 64-column pass (64-bit address arithmetic, per-element flag tests, a
+// 5-instruction leaky-ReLU).  Now: row pointers advance by precomputed strides, the flags are hoisted, the residual of a
+// pass is requested before its accumulator columns are pulled out of tensor memory, leaky-ReLU is max(x, a x) (equal to
+// ggml's max(x,0) + a min(x,0) for 0 < a < 1 up to the sign of zero): ~220 instructions per 32-column pass.
 // Fused math, unchanged: ((acc + bias) + residual) + acc_in, times scale; fp16 copy with leaky-ReLU.
-constexpr int EPI_COLS   = 64;
+constexpr int EPI_COLS   = 32;
 constexpr int SLAB_LD    = EPI_COLS + 4;               // floats; +4 keeps the row-wise 16-byte stores conflict-free
 constexpr int SLAB_BYTES = 32 * SLAB_LD * 4;
 
@@ -214,94 +219,84 @@ __device__ __forceinline__ float4 f4_add(float4 a, float4 b)
 {
     return make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z), __fadd_rn(a.w, b.w));
 }
+__device__ __forceinline__ float lrelu_max_f(float x, float a) { return fmaxf(x, __fmul_rn(a, x)); }
 
-// NQ row pairs starting at row rb of the warp's 32-row slab (this thread: row rb + 2 q + rsel, 4 columns)
-template <int NQ>
-__device__ __forceinline__ void epilogue_rows(const ConvParams &p, const float *slab, int rb, int rsel, int cl, int oc, float4 bias,
-                                              int t_first, size_t seg_row0, const float4 (&rs)[NQ], const float4 (&ai)[NQ], const bool (&ok)[NQ])
+// 32 columns x 32 rows of tensor memory -> registers (two x16 loads in flight, one wait)
+__device__ __forceinline__ void tmem_ld16x2(uint32_t taddr, uint32_t (&r)[32])
 {
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-        if (!ok[q]) continue;
-        const int t = t_first + rb + 2 * q + rsel;
-        const size_t orow = (seg_row0 + (size_t)t) * (size_t)p.out_mul + p.out_add;
-        float4 v = *reinterpret_cast<const float4 *>(slab + (rb + 2 * q + rsel) * SLAB_LD + cl);
-        if (p.bias) v = f4_add(v, bias);
-        if (p.res) v = f4_add(v, rs[q]);
-        if (p.acc_in) v = f4_add(ai[q], v);
-        if (p.has_scale) v = make_float4(__fmul_rn(v.x, p.scale), __fmul_rn(v.y, p.scale), __fmul_rn(v.z, p.scale), __fmul_rn(v.w, p.scale));
-        if (p.out32) *reinterpret_cast<float4 *>(p.out32 + orow * (size_t)p.ldo32 + p.o32_ch_off + oc) = v;
-        if (p.out16) {
-            uint2 h;
-            h.x = pack_half2(lrelu_f(v.x, p.out16_slope), lrelu_f(v.y, p.out16_slope));
-            h.y = pack_half2(lrelu_f(v.z, p.out16_slope), lrelu_f(v.w, p.out16_slope));
-            *reinterpret_cast<uint2 *>(p.out16 + orow * (size_t)p.ldo16 + p.o16_ch_off + oc) = h;
-        }
-    }
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%32];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%33];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr), "r"(taddr + 16u));
 }
 
-// DEEP (launches with a residual input and no running branch sum): the residual rows of a whole
-// 64-column pass (16 float4 per thread) are requested BEFORE the pass's accumulator columns are pulled
-// out of tensor memory and transposed, so their L2 / HBM latency is covered by that work instead of
-// being paid once per 8 rows (conv2-type launches were bound by exactly this: 4 warps x 4 loads in
-// flight, profiles/r01_launch_table_*).  It costs registers and code size, which the launches without a
-// residual (more co-resident CTAs, nothing to wait for) do not want: they keep the short loop.
-template <bool DEEP>
+// Columns are handled in passes of EPI_COLS; this warp takes the passes pass0, pass0 + pass_step, ... (the persistent
+// kernel runs two warps per lane quarter).  trow: tensor-memory address of the warp's lane quarter, column 0 of the tile.
 __device__ __forceinline__ void epilogue_tile(const ConvParams &p, uint32_t trow, float *slab, int lane, int t_first, int seg_len,
-                                              size_t seg_row0, int nchunk, int NC)
+                                              size_t seg_row0, int nchunk, int NC, int pass0, int pass_step)
 {
-    const int cl   = (lane & 15) * 4;       // this lane's 4 columns inside the 64-column pass
-    const int rsel = lane >> 4;             // which row of a row pair
-    for (int col0 = 0; col0 < NC; col0 += EPI_COLS) {
+    const int cl   = (lane & 7) * 4;        // this lane's 4 columns inside the 32-column pass
+    const int rsel = lane >> 3;             // which row of a group of 4
+    const bool has_res = p.res != nullptr, has_acc = p.acc_in != nullptr, has_o32 = p.out32 != nullptr, has_o16 = p.out16 != nullptr;
+    const float scale = p.has_scale ? p.scale : 1.0f;          // v * 1.0f == v
+    const float slope = p.out16_slope;
+    const int rows_valid = seg_len - t_first - rsel;            // iteration i (row 4 i + rsel) is inside the utterance iff 4 i < rows_valid
+    // element offsets of row (t_first + rsel), advancing by 4 rows per iteration
+    const size_t orow0 = (seg_row0 + (size_t)(t_first + rsel)) * (size_t)p.out_mul + p.out_add;
+    const size_t rstep = (size_t)4 * p.out_mul;
+    const float *res_row = has_res ? p.res + orow0 * (size_t)p.ldres + p.res_ch_off : nullptr;
+    const float *acc_row = has_acc ? p.acc_in + orow0 * (size_t)p.ldo32 + p.o32_ch_off : nullptr;
+    float *o32_row = has_o32 ? p.out32 + orow0 * (size_t)p.ldo32 + p.o32_ch_off : nullptr;
+    __half *o16_row = has_o16 ? p.out16 + orow0 * (size_t)p.ldo16 + p.o16_ch_off : nullptr;
+    const size_t res_step = rstep * (size_t)p.ldres, o32_step = rstep * (size_t)p.ldo32, o16_step = rstep * (size_t)p.ldo16;
+    const float4 *srow = reinterpret_cast<const float4 *>(slab + rsel * SLAB_LD + cl);
+    float4 *drow = reinterpret_cast<float4 *>(slab + lane * SLAB_LD);
+
+    for (int col0 = pass0 * EPI_COLS; col0 < NC; col0 += pass_step * EPI_COLS) {
         const int cw = min(EPI_COLS, NC - col0);
         const int oc = nchunk * NC + col0 + cl;
-        float4 rsd[DEEP ? 16 : 1];
-        bool okd[DEEP ? 16 : 1];
-        if (DEEP) {
+        const bool col_ok = cl < cw;
+        // residual rows of the pass first: their latency is covered by the tensor-memory read-out and the transpose
+        float4 rs[8];
+        if (has_res) {
 #pragma unroll
-            for (int q = 0; q < (DEEP ? 16 : 1); ++q) {
-                const int t = t_first + 2 * q + rsel;
-                okd[q] = cl < cw && t < seg_len;
-                rsd[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (okd[q]) {
-                    const size_t orow = (seg_row0 + (size_t)t) * (size_t)p.out_mul + p.out_add;
-                    rsd[q] = *reinterpret_cast<const float4 *>(p.res + orow * (size_t)p.ldres + p.res_ch_off + oc);
-                }
+            for (int i = 0; i < 8; ++i) {
+                rs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (col_ok && 4 * i < rows_valid) rs[i] = *reinterpret_cast<const float4 *>(res_row + (size_t)i * res_step + oc);
             }
         }
-        for (int cc = 0; cc < cw; cc += 16) {
-            uint32_t r[16];
-            tmem_ld16(trow + (uint32_t)(col0 + cc), r);
-            float4 *d = reinterpret_cast<float4 *>(slab + lane * SLAB_LD + cc);
+        {
+            uint32_t r[32];
+            tmem_ld16x2(trow + (uint32_t)col0, r);
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                d[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
-                                   __uint_as_float(r[4 * q + 3]));
+            for (int q = 0; q < 8; ++q)
+                drow[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+                                      __uint_as_float(r[4 * q + 3]));
         }
         __syncwarp();
-        if (cl < cw) {
+        if (col_ok) {
             float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
             if (p.bias) bias = __ldg(reinterpret_cast<const float4 *>(p.bias + oc));
-            if (DEEP) {
-                float4 aid[DEEP ? 16 : 1];      // (never read: DEEP launches have no acc_in)
 #pragma unroll
-                for (int q = 0; q < (DEEP ? 16 : 1); ++q) aid[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                epilogue_rows<DEEP ? 16 : 1>(p, slab, 0, rsel, cl, oc, bias, t_first, seg_row0, rsd, aid, okd);
-            } else {
-                for (int rb = 0; rb < 32; rb += 8) {
-                    float4 rs[4], ai[4];
-                    bool ok[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int t = t_first + rb + 2 * q + rsel;
-                        ok[q] = t < seg_len;
-                        const size_t orow = (seg_row0 + (size_t)t) * (size_t)p.out_mul + p.out_add;
-                        rs[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        ai[q] = rs[q];
-                        if (ok[q] && p.res) rs[q] = *reinterpret_cast<const float4 *>(p.res + orow * (size_t)p.ldres + p.res_ch_off + oc);
-                        if (ok[q] && p.acc_in) ai[q] = *reinterpret_cast<const float4 *>(p.acc_in + orow * (size_t)p.ldo32 + p.o32_ch_off + oc);
+            for (int i = 0; i < 8; ++i) {
+                if (4 * i < rows_valid) {
+                    float4 v = srow[i * SLAB_LD];
+                    if (p.bias) v = f4_add(v, bias);
+                    if (has_res) v = f4_add(v, rs[i]);
+                    if (has_acc) v = f4_add(*reinterpret_cast<const float4 *>(acc_row + (size_t)i * o32_step + oc), v);
+                    v = make_float4(__fmul_rn(v.x, scale), __fmul_rn(v.y, scale), __fmul_rn(v.z, scale), __fmul_rn(v.w, scale));
+                    if (has_o32) *reinterpret_cast<float4 *>(o32_row + (size_t)i * o32_step + oc) = v;
+                    if (has_o16) {
+                        uint2 h;
+                        h.x = pack_half2(lrelu_max_f(v.x, slope), lrelu_max_f(v.y, slope));
+                        h.y = pack_half2(lrelu_max_f(v.z, slope), lrelu_max_f(v.w, slope));
+                        *reinterpret_cast<uint2 *>(o16_row + (size_t)i * o16_step + oc) = h;
                     }
-                    epilogue_rows<4>(p, slab, rb, rsel, cl, oc, bias, t_first, seg_row0, rs, ai, ok);
                 }
             }
         }
@@ -310,7 +305,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams &p, uint32_t trow
 }
 
 // ------------------------------------------------------------------ the kernel
-template <int MODE, int MT, bool DEEP>
+template <int MODE, int MT>
 __global__ void __launch_bounds__(128 * MT + 64) conv_umma_kernel(const ConvParams p)
 {
     constexpr int N_PRODUCERS = 128 * MT;
@@ -342,8 +337,17 @@ __global__ void __launch_bounds__(128 * MT + 64) conv_umma_kernel(const ConvPara
     const uint32_t a_base        = smem_base + SMEM_HEADER;
     const uint32_t b_base        = a_base + p.a_stages * a_stage_bytes;
 
+    // ---- thread-block cluster: CL CTAs = CL time tiles of the same N-chunk share every weight stage.  Each CTA fetches
+    //      1/CL of a stage and multicasts it to all of them, so the L2 -> SM weight traffic (the bound of these kernels:
+    //      a 128-row tile uses every weight byte once) drops by CL.  CTAs that pad the grid recompute the last tile and
+    //      store nothing: they must keep consuming the shared stages. ----
+    const int CL         = p.cluster;
+    const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
+    const uint16_t cmask = (uint16_t)((1u << CL) - 1u);
+    const bool live      = (int)blockIdx.x < p.n_tiles;
+
     // ---- which tile of which utterance ----
-    const int tile    = blockIdx.x;
+    const int tile    = live ? (int)blockIdx.x : p.n_tiles - 1;
     const int u       = find_segment_warp(p.tile_start, p.B, tile);
     const int t0      = (tile - __ldg(p.tile_start + u)) * ROWS_CTA;
     const int seg_f0  = __ldg(p.seg_start + u);
@@ -359,14 +363,14 @@ __global__ void __launch_bounds__(128 * MT + 64) conv_umma_kernel(const ConvPara
         }
         for (int s = 0; s < p.b_stages; ++s) {
             mbar_init(smem_u32(b_full + s), 1);
-            mbar_init(smem_u32(b_empty + s), 1);
+            mbar_init(smem_u32(b_empty + s), (uint32_t)CL);       // a stage is free when every CTA of the cluster has used it
         }
         mbar_init(smem_u32(acc_full), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == MMA_WARP) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
     tc_fence_before_sync();
-    __syncthreads();
+    if (CL > 1) cluster_sync_all(); else __syncthreads();        // peers' barriers are initialised before anything is multicast
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -396,8 +400,10 @@ __global__ void __launch_bounds__(128 * MT + 64) conv_umma_kernel(const ConvPara
         // every MMA has completed (acc_full), so the operand stages are dead: their memory is the slab
         const int  mt    = warp >> 2;                       // M-tile this warp drains
         const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)mt * acc_stride;
-        epilogue_tile<DEEP>(p, trow, reinterpret_cast<float *>(smem + SMEM_HEADER + (size_t)warp * SLAB_BYTES), lane,
-                      t0 + mt * TILE_M + (warp & 3) * 32, seg_len, seg_row0, nchunk, NC);
+        // (the stage memory doubles as the transpose slabs: no peer may still be multicasting into it -- every stage this
+        //  CTA waited for was the last one its peers sent, and they send nothing after the final K-chunk)
+        epilogue_tile(p, trow, reinterpret_cast<float *>(smem + SMEM_HEADER + (size_t)warp * SLAB_BYTES), lane,
+                      t0 + mt * TILE_M + (warp & 3) * 32, live ? seg_len : 0, seg_row0, nchunk, NC, 0, 1);
     } else if (warp == MMA_WARP) {
         // =================== MMA issuer (one elected lane of a converged warp) ===================
         const uint32_t leader = elect_one();
@@ -429,7 +435,8 @@ __global__ void __launch_bounds__(128 * MT + 64) conv_umma_kernel(const ConvPara
                             acc = 1u;
                         }
                     }
-                    umma_commit(smem_u32(b_empty + sb));
+                    if (CL > 1) umma_commit_multicast(smem_u32(b_empty + sb), cmask);
+                    else umma_commit(smem_u32(b_empty + sb));
                 }
                 accum = 1u;
                 __syncwarp();
@@ -451,10 +458,15 @@ __global__ void __launch_bounds__(128 * MT + 64) conv_umma_kernel(const ConvPara
             uint32_t phb = 0;
             for (int c = 0; c < nkc; ++c) {
                 const uint32_t bytes = (uint32_t)min(KCHUNK, Cin - c * KCHUNK) * NC * 2u;
+                const uint32_t part = bytes / (uint32_t)CL;          // this CTA's share of the stage (a multiple of 16 bytes)
                 for (int a = 0; a < ntaps; ++a, src += bytes) {
+                    // b_empty counts the commits of ALL CTAs of the cluster: the share goes into every peer's stage
                     mbar_wait(smem_u32(b_empty + sb), phb ^ 1u, p.err_flag);
                     mbar_arrive_expect_tx(smem_u32(b_full + sb), bytes);
-                    bulk_copy_g2s(b_base + sb * b_stage_bytes, src, bytes, smem_u32(b_full + sb));
+                    if (CL > 1)
+                        bulk_copy_g2s_multicast(b_base + sb * b_stage_bytes + crank * part, src + crank * part, part, smem_u32(b_full + sb), cmask);
+                    else
+                        bulk_copy_g2s(b_base + sb * b_stage_bytes, src, bytes, smem_u32(b_full + sb));
                     if (++sb == b_stages) { sb = 0; phb ^= 1u; }
                 }
             }
@@ -463,7 +475,7 @@ __global__ void __launch_bounds__(128 * MT + 64) conv_umma_kernel(const ConvPara
     }
 
     tc_fence_before_sync();
-    __syncthreads();
+    if (CL > 1) cluster_sync_all(); else __syncthreads();        // no CTA exits while a peer may still signal its barriers
     if (warp == MMA_WARP) {
         tc_fence_after_sync();
         tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
@@ -479,9 +491,10 @@ __global__ void __launch_bounds__(128 * MT + 64) conv_umma_kernel(const ConvPara
 // L2 round trip of cp.async.bulk.  (Two co-resident one-tile CTAs run in lockstep and reach their
 // epilogues together; the per-launch timings in profiles/ show conv2-type launches paying their
 // whole epilogue.)
-constexpr int PK_THREADS = 320;
+constexpr int PK_THREADS   = 448;     // warps 0-3 A producers, 4-7 and 10-13 epilogue, 8 MMA issuer, 9 weight loader
+constexpr int PK_EPI_WARPS = 8;       // two warps per tensor-memory lane quarter, alternating 32-column passes
 
-template <int MODE, bool DEEP>
+template <int MODE>
 __global__ void __launch_bounds__(PK_THREADS, 1) conv_umma_pk_kernel(const ConvParams p, const int total_tiles, const int nchunks)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -536,7 +549,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) conv_umma_pk_kernel(const ConvP
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(smem_u32(acc_full + s), 1);
-            mbar_init(smem_u32(acc_empty + s), 128);
+            mbar_init(smem_u32(acc_empty + s), 32 * PK_EPI_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -565,11 +578,14 @@ __global__ void __launch_bounds__(PK_THREADS, 1) conv_umma_pk_kernel(const ConvP
                 if (++sa == p.a_stages) { sa = 0; ph ^= 1u; }
             }
         }
-    } else if (warp < 8) {
+    } else if (warp < 8 || warp >= 10) {
         // =================== epilogue ===================
-        // (runs under the next item's main loop, so its transpose slabs sit behind the operand stages)
+        // (runs under the next item's main loop, so its transpose slabs sit behind the operand stages).  A warp reads
+        // the tensor-memory lanes of quarter warp % 4; the two warps of a quarter alternate the 32-column passes.
+        const int eidx = warp < 8 ? warp - 4 : warp - 10 + 4;      // 0..7
+        const int egrp = eidx >> 2;                                // which of the two warps of the lane quarter
         float *slab = reinterpret_cast<float *>(smem + SMEM_HEADER + (size_t)p.a_stages * a_stage_bytes + (size_t)p.b_stages * b_stage_bytes +
-                                                (size_t)(warp & 3) * SLAB_BYTES);
+                                                (size_t)eidx * SLAB_BYTES);
         int n = 0;
         for (int w = blockIdx.x; w < total_items; w += gridDim.x, ++n) {
             const TileCoord tc = coord(w);
@@ -577,7 +593,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) conv_umma_pk_kernel(const ConvP
             mbar_wait(smem_u32(acc_full + buf), (uint32_t)(n >> 1) & 1u, p.err_flag);
             tc_fence_after_sync();
             const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)buf * acc_stride;
-            epilogue_tile<DEEP>(p, trow, slab, lane, tc.t0 + (warp & 3) * 32, tc.seg_len, tc.seg_row0, tc.nchunk, NC);
+            epilogue_tile(p, trow, slab, lane, tc.t0 + (warp & 3) * 32, tc.seg_len, tc.seg_row0, tc.nchunk, NC, egrp, 2);
             tc_fence_before_sync();
             mbar_arrive(smem_u32(acc_empty + buf));
         }
@@ -711,7 +727,7 @@ size_t conv_umma_pk_plan(ConvParams &p, size_t smem_budget)
     const size_t a_stage = (size_t)(kc_max >> 3) * p.a_rows * 16;
     const size_t b_stage = (size_t)kc_max * p.NC * 2;
     int as = 3, bs = 2;
-    smem_budget -= 4 * SLAB_BYTES;      // epilogue transpose slabs behind the stages
+    smem_budget -= PK_EPI_WARPS * SLAB_BYTES;      // epilogue transpose slabs behind the stages
     while (bs < MAX_B_STAGES && SMEM_HEADER + as * a_stage + (bs + 1) * b_stage <= smem_budget) ++bs;
     while (as < MAX_A_STAGES && SMEM_HEADER + (as + 1) * a_stage + bs * b_stage <= smem_budget) ++as;
     p.a_stages = as;
@@ -719,7 +735,7 @@ size_t conv_umma_pk_plan(ConvParams &p, size_t smem_budget)
     int cols = 32;
     while (cols < 2 * ((p.NC + 31) & ~31)) cols <<= 1;
     p.tmem_cols = cols;
-    return SMEM_HEADER + as * a_stage + bs * b_stage + 4 * SLAB_BYTES;
+    return SMEM_HEADER + as * a_stage + bs * b_stage + PK_EPI_WARPS * SLAB_BYTES;
 }
 
 template <int MODE>
@@ -728,8 +744,7 @@ static cudaError_t launch_pk(const ConvParams &p, int total_tiles, int num_sms, 
     const int nchunks = p.Cout / p.NC;
     const int items = total_tiles * nchunks;
     const int grid = items < num_sms ? items : num_sms;
-    if (p.res && !p.acc_in) conv_umma_pk_kernel<MODE, true><<<grid, PK_THREADS, smem, st>>>(p, total_tiles, nchunks);
-    else conv_umma_pk_kernel<MODE, false><<<grid, PK_THREADS, smem, st>>>(p, total_tiles, nchunks);
+    conv_umma_pk_kernel<MODE><<<grid, PK_THREADS, smem, st>>>(p, total_tiles, nchunks);
     return cudaGetLastError();
 }
 
@@ -747,13 +762,37 @@ cudaError_t conv_umma_pk_launch(const ConvParams &p, int total_tiles, int num_sm
     return cudaErrorInvalidValue;
 }
 
+// launch with a thread-block cluster of p.cluster CTAs along x (1: plain launch)
+template <typename K>
+static cudaError_t launch_clustered(K kernel, dim3 grid, int threads, size_t smem, cudaStream_t st, const ConvParams &p)
+{
+    if (p.cluster <= 1) {
+        kernel<<<grid, threads, smem, st>>>(p);
+        return cudaGetLastError();
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(threads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)p.cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, p);
+}
+
 template <int MODE, int MT>
 static cudaError_t launch_mode(const ConvParams &p, int total_tiles, size_t smem, cudaStream_t st)
 {
-    dim3 grid(total_tiles, p.Cout / p.NC, 1);
-    if (p.res && !p.acc_in) conv_umma_kernel<MODE, MT, true><<<grid, 128 * MT + 64, smem, st>>>(p);
-    else conv_umma_kernel<MODE, MT, false><<<grid, 128 * MT + 64, smem, st>>>(p);
-    return cudaGetLastError();
+    ConvParams q = p;
+    if (q.cluster != 2 && q.cluster != 4) q.cluster = 1;
+    q.n_tiles = total_tiles;
+    dim3 grid((total_tiles + q.cluster - 1) / q.cluster * q.cluster, p.Cout / p.NC, 1);
+    return launch_clustered(conv_umma_kernel<MODE, MT>, grid, 128 * MT + 64, smem, st, q);
 }
 
 template <int MODE>
@@ -761,12 +800,9 @@ static cudaError_t init_mode()
 {
     cudaError_t e;
     const int kMax = 227 * 1024;
-    if ((e = cudaFuncSetAttribute(conv_umma_pk_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(conv_umma_pk_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(conv_umma_kernel<MODE, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(conv_umma_kernel<MODE, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(conv_umma_kernel<MODE, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax)) != cudaSuccess) return e;
-    return cudaFuncSetAttribute(conv_umma_kernel<MODE, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
+    if ((e = cudaFuncSetAttribute(conv_umma_pk_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(conv_umma_kernel<MODE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax)) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(conv_umma_kernel<MODE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
 }
 
 cudaError_t conv_umma_init()

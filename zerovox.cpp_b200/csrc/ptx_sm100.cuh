@@ -58,6 +58,25 @@ __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void *src, uin
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
+// ---- thread-block clusters: weight stages shared by the CTAs of a cluster (multicast bulk copy) ----
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// The copy lands at the same shared-memory offset in every CTA of `mask` and completes `bytes` on the mbarrier at the
+// same offset in each of them.
+__device__ __forceinline__ void bulk_copy_g2s_multicast(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint16_t mask)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+                 : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async_smem()
 {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -95,6 +114,12 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
 __device__ __forceinline__ void umma_commit(uint32_t bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// completion of all earlier MMAs of this thread arrives on the mbarrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t mask)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+                 : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16])
 {

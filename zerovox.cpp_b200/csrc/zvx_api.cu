@@ -119,6 +119,8 @@ struct zvx_ctx {
     int use_graphs = 1;
     int chunk_group_max = 8;   // zvx_vocode_chunked: at most this many chunks per vocoder pass
     int conv_smem_kb = 100;   // shared-memory budget of a one-tile conv CTA (two CTAs per SM)
+    int conv_cluster = 1;   // CTAs per cluster of the one-tile conv kernel sharing every weight stage by multicast; measured on
+                            // B200 (profiles/r02_conv_cluster_ab.txt): 2 -> +7 %, 4 -> +19 % time on the decoder convs, so off
     int conv_mt2 = 0;   // two M-tiles per CTA: measured slower on B200 while the A producer is the limit (profiles/)
     std::vector<int> tile256_cfg;                 // per rate index: wincfg entry of the 256-row tiling
     int num_sms = 148;
@@ -816,6 +818,12 @@ int run_conv(zvx_ctx *ctx, const ConvCall &cc)
         } else {
             const size_t smem = conv_umma_plan(p, p.mt == 2 ? 226 * 1024 : (size_t)ctx->conv_smem_kb * 1024);
             if (smem > 227 * 1024) return fail(ctx, "conv needs %zu bytes of shared memory", smem);
+            p.cluster = 1;
+            if (ctx->conv_cluster > 1 && tiles >= 2 * ctx->conv_cluster && (int64_t)L.IC * v.ntaps >= 512) {
+                p.cluster = ctx->conv_cluster;
+                const int kc_last = L.IC % 64 ? L.IC % 64 : 64;
+                if (((size_t)kc_last * L.NC * 2) % (16 * (size_t)p.cluster) != 0) p.cluster = 1;   // shares must be 16-byte multiples
+            }
             CK(ctx, conv_umma_launch(p, tiles, smem, ctx->stream));
         }
     }
@@ -1364,6 +1372,7 @@ int zvx_create(zvx_ctx **out, const zvx_config *cfg, const zvx_tensor_desc *weig
     if (const char *e = getenv("ZVX_DEC_PREPASS")) ctx->dec_prepass = atoi(e);
     if (const char *e = getenv("ZVX_BRANCH_SUM_IN_CONSUMER")) ctx->branch_sum_in_consumer = atoi(e);
     if (const char *e = getenv("ZVX_CONV_MT2")) ctx->conv_mt2 = atoi(e);
+    if (const char *e = getenv("ZVX_CONV_CLUSTER")) ctx->conv_cluster = atoi(e);
     if (const char *e = getenv("ZVX_CONV_SMEM_KB")) ctx->conv_smem_kb = atoi(e);
     if (const char *e = getenv("ZVX_GRAPHS")) ctx->use_graphs = atoi(e);
     if (const char *e = getenv("ZVX_FORK_BRANCHES")) ctx->fork_branches = atoi(e);

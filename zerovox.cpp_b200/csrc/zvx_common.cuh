@@ -88,6 +88,8 @@ struct ConvParams {
     int          a_stages;
     int          b_stages;
     int          tmem_cols;   // power of two >= max(32, NC)
+    int          cluster;     // CTAs per thread-block cluster (1, 2 or 4): they share every weight stage (multicast)
+    int          n_tiles;     // tiles of the launch (CTAs beyond it pad the grid to a multiple of `cluster`)
     int         *err_flag;    // device int set on pipeline timeout
 };
 
