@@ -139,6 +139,12 @@ struct zvx_ctx {
     float *v0 = nullptr, *U = nullptr, *CS = nullptr, *Y1 = nullptr, *VA = nullptr, *VB = nullptr, *T2 = nullptr, *wav = nullptr;
     int branch_sum_in_consumer = 1;               // fused stages: write the 3 branch outputs, the next kernel sums them
     int stage_is_split[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // set per run: stage i's output lives in CS/VA/VB (3 buffers)
+    // per-conv MRF path (stage 0, 256 channels): fp16 copies lrelu(U) (shared by the three blocks) and lrelu(y) (per
+    // branch) written by the producing conv's epilogue, so that every conv1 reads a ready-made fp16 operand (cp.async)
+    // instead of converting fp32 rows in its producer warps; sized for the stages that are not fused (chain_elems per frame)
+    __half *U16 = nullptr, *Y16[3] = {nullptr, nullptr, nullptr};
+    int64_t chain_elems = 0;
+    int mrf_f16_chain = 1;
     __half *H16 = nullptr, *X16 = nullptr, *R16 = nullptr;   // X16: decoder conv operand (normalised, activated, fp16); R16: raw input as fp16
     int dec_prepass = 1;
     int *d_seg = nullptr;                         // [B+1] frames prefix
@@ -642,6 +648,8 @@ int reserve(zvx_ctx *ctx, int64_t frames, int batch)
         }
         dev_free(ctx, ctx->X16); ctx->X16 = nullptr;
         dev_free(ctx, ctx->R16); ctx->R16 = nullptr;
+        dev_free(ctx, ctx->U16); ctx->U16 = nullptr;
+        for (int j = 0; j < 3; ++j) { dev_free(ctx, ctx->Y16[j]); ctx->Y16[j] = nullptr; }
         const int D = c.dim_in, BN = 2 * D, R = c.residual_dim;
         if (c.with_decoder) {
             if (dev_alloc(ctx, &ctx->X16, F * (BN + R)) || dev_alloc(ctx, &ctx->R16, F * (BN + R))) return 1;
@@ -659,6 +667,19 @@ int reserve(zvx_ctx *ctx, int64_t frames, int batch)
                 dev_alloc(ctx, &ctx->T2, F * S) ||
                 dev_alloc(ctx, &ctx->H16, F * S) || dev_alloc(ctx, &ctx->wav, F * c.hop_size))
                 return 1;
+            // fp16 operand chain of the stages that run conv by conv
+            ctx->chain_elems = 0;
+            if (ctx->mrf_f16_chain)
+                for (int i = 0; i < c.num_upsamples; ++i) {
+                    bool all_fused = ctx->use_fused != 0;
+                    for (int j = 0; j < c.num_resblocks; ++j) all_fused = all_fused && ctx->fused[(size_t)i * c.num_resblocks + j].CH != 0;
+                    if (!all_fused) ctx->chain_elems = std::max<int64_t>(ctx->chain_elems, (int64_t)ctx->rates[i + 1] * ctx->chans[i + 1]);
+                }
+            if (ctx->chain_elems > 0) {
+                if (dev_alloc(ctx, &ctx->U16, F * ctx->chain_elems)) return 1;
+                for (int j = 0; j < 3; ++j)
+                    if (dev_alloc(ctx, &ctx->Y16[j], F * ctx->chain_elems)) return 1;
+            }
             // per-branch temporaries of the forked MRF stages (run_vocoder): + 2 x (2 fp32 + 1 fp16) stage buffers
             if (ctx->fork_branches)
                 for (int j = 0; j < 2; ++j)
@@ -1024,12 +1045,18 @@ int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out, int16_t *pcm_
         if (ctx->debug_stop >= 0 && i >= ctx->debug_stop) return 0;
         const int cin = ctx->chans[i], ch = ctx->chans[i + 1];
         const int s = c.upsample_scales[i];
+        // does a block of this stage run conv by conv, and does the fp16 chain fit the workspace?
+        bool any_unfused = false;
+        for (int j = 0; j < nb; ++j) any_unfused = any_unfused || !(ctx->use_fused && ctx->fused[(size_t)i * nb + j].CH);
+        const bool chain = any_unfused && !ctx->use_ref_kernels && ctx->U16 && nb <= 3 &&
+                           (int64_t)ctx->rates[i + 1] * ch <= ctx->chain_elems;
         // leaky_relu(0.1) -> ConvTranspose1d, one launch per output phase (hifigan.cpp:281-297, :22-71)
         if (ctx->use_fused_upconv && ctx->upf[i].OC) {
             ConvCall u; u.kind = ZVX_K_UPCONV; u.stage = i; u.L = &ctx->upf[i]; u.x = vin; u.ldx = cin; u.rate_idx = i;
             u.pro_mode = PRO_LRELU; u.pro_slope = 0.1f; u.out32 = ctx->U; u.ldo32 = s * ch; u.out_mul = 1;
             if (vin2) { u.pro_mode = PRO_SUM3; u.x2 = vin2; u.x3 = vin3; u.sum_scale = third; }
             u.flops = 2.0 * (double)ctx->last_frames * ctx->rates[i] * s * ch * cin * (ctx->up[i].K / s);
+            if (chain) { u.out16 = ctx->U16; u.ldo16 = s * ch; u.out16_slope = 0.1f; }
             if (run_conv(ctx, u)) return 1;
         } else {
             const bool pre = vin2 && !ctx->use_ref_kernels;
@@ -1051,6 +1078,7 @@ int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out, int16_t *pcm_
                 u.pro_mode = PRO_LRELU; u.pro_slope = 0.1f; u.out32 = ctx->U; u.ldo32 = ch; u.out_mul = s;
                 if (pre) { u.x = ctx->H16; u.pro_mode = PRO_F16; }
                 else if (vin2) { u.pro_mode = PRO_SUM3; u.x2 = vin2; u.x3 = vin3; u.sum_scale = third; }
+                if (chain) { u.out16 = ctx->U16; u.ldo16 = ch; u.out16_slope = 0.1f; }
                 const int lane_id = fork_ok ? phi % 3 : 0;
                 if (lane_id > 0) {
                     ctx->stream = ctx->fork_stream[lane_id - 1];
@@ -1146,6 +1174,7 @@ int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out, int16_t *pcm_
                 const float *yin = d == 0 ? ctx->U : Y;
                 ConvCall c1; c1.kind = ZVX_K_MRF_CONV; c1.stage = i; c1.L = &ctx->mrf1[idx]; c1.x = yin; c1.ldx = ch; c1.rate_idx = i + 1;
                 c1.pro_mode = PRO_LRELU; c1.pro_slope = 0.1f;
+                if (chain) { c1.x = d == 0 ? ctx->U16 : ctx->Y16[j]; c1.pro_mode = PRO_F16; }   // lrelu(.) already applied by the writer
                 c1.out16 = bH16; c1.ldo16 = ch; c1.out16_slope = 0.1f;
                 if (run_conv(ctx, c1)) return 1;
                 ConvCall c2; c2.kind = ZVX_K_MRF_CONV; c2.stage = i; c2.L = &ctx->mrf2[idx]; c2.x = bH16; c2.ldx = ch; c2.rate_idx = i + 1; c2.pro_mode = PRO_F16;
@@ -1159,6 +1188,7 @@ int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out, int16_t *pcm_
                     c2.out32 = Y;
                 }
                 c2.ldo32 = ch;
+                if (chain && !last) { c2.out16 = ctx->Y16[j]; c2.ldo16 = ch; c2.out16_slope = 0.1f; }
                 if (run_conv(ctx, c2)) return 1;
             }
         }
@@ -1270,6 +1300,7 @@ int make_lane(zvx_ctx *parent)
                     &l->mu, &l->rstd, &l->adain_gb, &l->v0, &l->U, &l->CS, &l->Y1, &l->VA, &l->VB, &l->T2, &l->wav, &l->pin_in, &l->pin_out};
     for (float **q : fp) *q = nullptr;
     l->H16 = l->X16 = l->R16 = nullptr;
+    l->U16 = nullptr; l->Y16[0] = l->Y16[1] = l->Y16[2] = nullptr; l->chain_elems = 0;
     l->d_seg = l->d_tiles = l->d_wins = l->d_err = l->pin_tables = nullptr;
     l->pin_in_cap = l->pin_out_cap = 0;
     l->graphs.clear();           // the copies of the parent's graph handles are not the lane's to destroy
@@ -1373,6 +1404,7 @@ int zvx_create(zvx_ctx **out, const zvx_config *cfg, const zvx_tensor_desc *weig
     if (const char *e = getenv("ZVX_BRANCH_SUM_IN_CONSUMER")) ctx->branch_sum_in_consumer = atoi(e);
     if (const char *e = getenv("ZVX_CONV_MT2")) ctx->conv_mt2 = atoi(e);
     if (const char *e = getenv("ZVX_CONV_CLUSTER")) ctx->conv_cluster = atoi(e);
+    if (const char *e = getenv("ZVX_MRF_F16_CHAIN")) ctx->mrf_f16_chain = atoi(e);
     if (const char *e = getenv("ZVX_CONV_SMEM_KB")) ctx->conv_smem_kb = atoi(e);
     if (const char *e = getenv("ZVX_GRAPHS")) ctx->use_graphs = atoi(e);
     if (const char *e = getenv("ZVX_FORK_BRANCHES")) ctx->fork_branches = atoi(e);
