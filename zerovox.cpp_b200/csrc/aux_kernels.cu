@@ -72,6 +72,49 @@ cudaError_t stats_launch(const float *x, int ld, int ch_off, int C, const int *s
 }
 
 // ---------------------------------------------------------------------------------
+// Second half of the statistics that the conv epilogues start (ConvParams::stats_out): per (utterance, channel) the
+// per-tile (sum, sum of squares) pairs are added up in tile order -> mean / rstd exactly like stats_kernel.  Channels
+// [C, C + C_tail) are copied from tail_mu / tail_rstd ([B][C_tail]; the asr_res part of the concatenated decoder input,
+// whose statistics are computed once).  grid (ceil((C + C_tail) / 128), B).
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) stats_finalize_kernel(const double2 *__restrict__ part, int C, const int *__restrict__ tile_start,
+                                                             const int *__restrict__ seg_start, int rate, const float *__restrict__ tail_mu,
+                                                             const float *__restrict__ tail_rstd, int C_tail, float *__restrict__ mu,
+                                                             float *__restrict__ rstd)
+{
+    const int u = blockIdx.y;
+    const int c = blockIdx.x * 128 + threadIdx.x;
+    const int stride = C + C_tail;
+    if (c >= stride) return;
+    if (c >= C) {
+        mu[(size_t)u * stride + c]   = tail_mu[(size_t)u * C_tail + (c - C)];
+        rstd[(size_t)u * stride + c] = tail_rstd[(size_t)u * C_tail + (c - C)];
+        return;
+    }
+    const int t0 = tile_start[u], t1 = tile_start[u + 1];
+    double s = 0.0, s2 = 0.0;
+    for (int t = t0; t < t1; ++t) {
+        const double2 v = part[(size_t)t * C + c];
+        s += v.x;
+        s2 += v.y;
+    }
+    const double n = (double)(seg_start[u + 1] - seg_start[u]) * rate;
+    const double mean_d = s / n;
+    double var_d = s2 / n - mean_d * mean_d;
+    if (var_d < 0.0) var_d = 0.0;
+    mu[(size_t)u * stride + c]   = (float)mean_d;
+    rstd[(size_t)u * stride + c] = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn((float)var_d, 1e-5f)));
+}
+
+cudaError_t stats_finalize_launch(const double2 *part, int C, const int *tile_start, const int *seg_start, int B, int rate,
+                                  const float *tail_mu, const float *tail_rstd, int C_tail, float *mu, float *rstd, cudaStream_t st)
+{
+    dim3 grid((C + C_tail + 127) / 128, B);
+    stats_finalize_kernel<<<grid, 128, 0, st>>>(part, C, tile_start, seg_start, rate, tail_mu, tail_rstd, C_tail, mu, rstd);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------
 // AdaIN style projection for all AdaIN layers at once:  h = fc_w . s + fc_b;
 // gamma1 = 1 + h[:C]; beta = h[C:]   (/root/reference/src/stylettsdec.cpp:177-189).
 // One warp per output row n of the concatenated (sum 2C) x style_dim weight; the row is

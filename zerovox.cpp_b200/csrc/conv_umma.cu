@@ -254,8 +254,10 @@ __device__ __forceinline__ void tmem_ld16x2(uint32_t taddr, uint32_t (&r)[32])
 
 // Columns are handled in passes of EPI_COLS; this warp takes the passes pass0, pass0 + pass_step, ... (the persistent
 // kernel runs two warps per lane quarter).  trow: tensor-memory address of the warp's lane quarter, column 0 of the tile.
+// stat_row (one-tile kernel, may be null): [NC] double2 of this warp's lane quarter, filled with the column sums / sums of
+// squares of the final values over the warp's valid rows.
 __device__ __forceinline__ void epilogue_tile(const ConvParams &p, uint32_t trow, float *slab, int lane, int t_first, int seg_len,
-                                              size_t seg_row0, int nchunk, int NC, int pass0, int pass_step)
+                                              size_t seg_row0, int nchunk, int NC, int pass0, int pass_step, double2 *stat_row = nullptr)
 {
     const int cl   = (lane & 7) * 4;        // this lane's 4 columns inside the 32-column pass
     const int rsel = lane >> 3;             // which row of a group of 4
@@ -296,6 +298,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams &p, uint32_t trow
                                       __uint_as_float(r[4 * q + 3]));
         }
         __syncwarp();
+        double sx[4] = {0.0, 0.0, 0.0, 0.0}, sq[4] = {0.0, 0.0, 0.0, 0.0};
         if (col_ok) {
             float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
             if (p.bias) bias = __ldg(reinterpret_cast<const float4 *>(p.bias + oc));
@@ -308,6 +311,11 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams &p, uint32_t trow
                     if (has_acc) v = f4_add(*reinterpret_cast<const float4 *>(acc_row + (size_t)i * o32_step + oc), v);
                     v = make_float4(__fmul_rn(v.x, scale), __fmul_rn(v.y, scale), __fmul_rn(v.z, scale), __fmul_rn(v.w, scale));
                     if (has_o32) *reinterpret_cast<float4 *>(o32_row + (size_t)i * o32_step + oc) = v;
+                    if (stat_row) {
+                        const double d0 = (double)v.x, d1 = (double)v.y, d2 = (double)v.z, d3 = (double)v.w;
+                        sx[0] += d0; sx[1] += d1; sx[2] += d2; sx[3] += d3;
+                        sq[0] = fma(d0, d0, sq[0]); sq[1] = fma(d1, d1, sq[1]); sq[2] = fma(d2, d2, sq[2]); sq[3] = fma(d3, d3, sq[3]);
+                    }
                     if (has_o16) {
                         uint2 h;
                         h.x = pack_half2(lrelu_max_f(v.x, slope), lrelu_max_f(v.y, slope));
@@ -315,6 +323,20 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams &p, uint32_t trow
                         *reinterpret_cast<uint2 *>(o16_row + (size_t)i * o16_step + oc) = h;
                     }
                 }
+            }
+        }
+        if (stat_row) {
+            // the four lanes l, l+8, l+16, l+24 hold the same columns (row groups 0..3): warp-shuffle reduction in a fixed order
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                sx[k] += __shfl_xor_sync(0xffffffffu, sx[k], 8);
+                sq[k] += __shfl_xor_sync(0xffffffffu, sq[k], 8);
+                sx[k] += __shfl_xor_sync(0xffffffffu, sx[k], 16);
+                sq[k] += __shfl_xor_sync(0xffffffffu, sq[k], 16);
+            }
+            if (rsel == 0 && col_ok) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) stat_row[col0 + cl + k] = make_double2(sx[k], sq[k]);
             }
         }
         __syncwarp();
@@ -419,8 +441,22 @@ __global__ void __launch_bounds__(128 * MT + 64) conv_umma_kernel(const ConvPara
         const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)mt * acc_stride;
         // (the stage memory doubles as the transpose slabs: no peer may still be multicasting into it -- every stage this
         //  CTA waited for was the last one its peers sent, and they send nothing after the final K-chunk)
+        // statistics partials of the 4 * MT lane quarters sit behind the slabs (also dead stage memory)
+        double2 *stat_all = reinterpret_cast<double2 *>(smem + SMEM_HEADER + (size_t)(4 * MT) * SLAB_BYTES);
+        double2 *stat_row = p.stats_out ? stat_all + (size_t)warp * NC : nullptr;
         epilogue_tile(p, trow, reinterpret_cast<float *>(smem + SMEM_HEADER + (size_t)warp * SLAB_BYTES), lane,
-                      t0 + mt * TILE_M + (warp & 3) * 32, live ? seg_len : 0, seg_row0, nchunk, NC, 0, 1);
+                      t0 + mt * TILE_M + (warp & 3) * 32, live ? seg_len : 0, seg_row0, nchunk, NC, 0, 1, stat_row);
+        if (p.stats_out) {
+            // all lane quarters of the tile, summed in a fixed order, one (sum, sum of squares) per output channel
+            asm volatile("bar.sync 1, %0;" ::"r"(N_PRODUCERS) : "memory");
+            if (live)
+                for (int c = tid; c < NC; c += N_PRODUCERS) {
+                    double a = 0.0, b = 0.0;
+#pragma unroll
+                    for (int q = 0; q < 4 * MT; ++q) { const double2 v = stat_all[(size_t)q * NC + c]; a += v.x; b += v.y; }
+                    p.stats_out[(size_t)blockIdx.x * p.Cout + (size_t)nchunk * NC + c] = make_double2(a, b);
+                }
+        }
     } else if (warp == MMA_WARP) {
         // =================== MMA issuer (one elected lane of a converged warp) ===================
         const uint32_t leader = elect_one();
@@ -730,7 +766,8 @@ size_t conv_umma_plan(ConvParams &p, size_t smem_budget)
     while (cols < p.mt * ((p.NC + 31) & ~31)) cols <<= 1;
     p.tmem_cols = cols;
     // the epilogue reuses the stage memory for its transpose slabs (one per producer warp)
-    const size_t stages = as * a_stage + bs * b_stage, slabs = (size_t)4 * p.mt * SLAB_BYTES;
+    const size_t stages = as * a_stage + bs * b_stage,
+                 slabs = (size_t)4 * p.mt * SLAB_BYTES + (p.stats_out ? (size_t)4 * p.mt * p.NC * sizeof(double2) : 0);
     return SMEM_HEADER + (stages > slabs ? stages : slabs);
 }
 

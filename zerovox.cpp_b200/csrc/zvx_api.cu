@@ -136,6 +136,11 @@ struct zvx_ctx {
     float *enc_in = nullptr, *sc = nullptr, *h528 = nullptr, *e0 = nullptr, *h1056 = nullptr, *catA = nullptr,
           *catB = nullptr, *asr = nullptr, *d1 = nullptr, *d2 = nullptr, *mel = nullptr, *style = nullptr;
     float *mu = nullptr, *rstd = nullptr, *adain_gb = nullptr;
+    // InstanceNorm statistics fused into the producing conv's epilogue: per-tile partial sums (stat_part, [tiles][C]) +
+    // a finalize launch; asr_mu / asr_rstd: statistics of the asr_res part of the concatenated decoder input (computed once)
+    double2 *stat_part = nullptr; size_t stat_part_cap = 0;
+    float *asr_mu = nullptr, *asr_rstd = nullptr;
+    int fused_stats = 1;
     float *v0 = nullptr, *U = nullptr, *CS = nullptr, *Y1 = nullptr, *VA = nullptr, *VB = nullptr, *T2 = nullptr, *wav = nullptr;
     int branch_sum_in_consumer = 1;               // fused stages: write the 3 branch outputs, the next kernel sums them
     int stage_is_split[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // set per run: stage i's output lives in CS/VA/VB (3 buffers)
@@ -618,7 +623,7 @@ int reserve(zvx_ctx *ctx, int64_t frames, int batch)
         {
             int **ib[] = {&ctx->d_seg, &ctx->d_tiles, &ctx->d_wins};
             for (int **b : ib) { dev_free(ctx, *b); *b = nullptr; }
-            float **fb[] = {&ctx->mu, &ctx->rstd, &ctx->adain_gb, &ctx->style};
+            float **fb[] = {&ctx->mu, &ctx->rstd, &ctx->adain_gb, &ctx->style, &ctx->asr_mu, &ctx->asr_rstd};
             for (float **b : fb) { dev_free(ctx, *b); *b = nullptr; }
         }
         if (ctx->pin_tables) cudaFreeHost(ctx->pin_tables);
@@ -631,6 +636,7 @@ int reserve(zvx_ctx *ctx, int64_t frames, int batch)
         if (dev_alloc(ctx, &ctx->mu, (size_t)nb * maxc) || dev_alloc(ctx, &ctx->rstd, (size_t)nb * maxc)) return 1;
         if (dev_alloc(ctx, &ctx->adain_gb, (size_t)nb * std::max(ctx->adain.total, 1))) return 1;
         if (dev_alloc(ctx, &ctx->style, (size_t)nb * c.style_dim)) return 1;
+        if (dev_alloc(ctx, &ctx->asr_mu, (size_t)nb * std::max(c.residual_dim, 1)) || dev_alloc(ctx, &ctx->asr_rstd, (size_t)nb * std::max(c.residual_dim, 1))) return 1;
         CK(ctx, cudaMallocHost(&ctx->pin_tables, sizeof(int) * (size_t)(nr + 1 + nw) * (nb + 1)));
         ctx->cap_batch = nb;
     }
@@ -736,6 +742,18 @@ int set_batch(zvx_ctx *ctx, int B, const int32_t *L, bool reserve_workspace = tr
     }
     CK(ctx, cudaEventRecord(ctx->tables_event, ctx->stream));
     ctx->tables_pending = true;
+    if (ctx->cfg.with_decoder && ctx->fused_stats) {
+        // per-tile statistics partials of the widest decoder conv output
+        const size_t need = (size_t)ctx->total_tiles[0] * (size_t)(2 * ctx->cfg.dim_in);
+        if (need > ctx->stat_part_cap) {
+            CK(ctx, cudaStreamSynchronize(ctx->stream));
+            const size_t cap = std::max(need, ctx->stat_part_cap * 2);
+            dev_free(ctx, ctx->stat_part); ctx->stat_part = nullptr; ctx->stat_part_cap = 0;
+            if (dev_alloc(ctx, &ctx->stat_part, cap)) return 1;
+            ctx->stat_part_cap = cap;
+            drop_graphs(ctx);
+        }
+    }
     if (ctx->fork_branches && ctx->cfg.with_vocoder && ensure_fork(ctx)) return 1;
     ctx->last_B = B;
     ctx->last_frames = frames;
@@ -785,6 +803,7 @@ struct ConvCall {
     __half *out16 = nullptr; int ldo16 = 0, o16_ch_off = 0; float out16_slope = 0.f;
     int out_mul = 1;
     double flops = 0.0;        // algorithmic FLOPs of the launch when they differ from 2*rows*OC*IC*taps
+    bool stats = false;        // the epilogue also emits the per-tile statistics partials of the output (ctx->stat_part)
 };
 
 int run_conv(zvx_ctx *ctx, const ConvCall &cc)
@@ -812,6 +831,7 @@ int run_conv(zvx_ctx *ctx, const ConvCall &cc)
     p.out32 = cc.out32; p.ldo32 = cc.ldo32; p.o32_ch_off = cc.o32_ch_off;
     p.out16 = cc.out16; p.ldo16 = cc.ldo16; p.o16_ch_off = cc.o16_ch_off; p.out16_slope = cc.out16_slope;
     p.out_mul = cc.out_mul; p.out_add = v.out_add;
+    p.stats_out = cc.stats ? ctx->stat_part : nullptr;
     p.err_flag = ctx->d_err;
     int tiles = ctx->total_tiles[cc.rate_idx];
     // two M-tiles per CTA (each weight stage feeds 256 rows) whenever that still fills the GPU
@@ -856,6 +876,17 @@ int run_stats(zvx_ctx *ctx, const float *x, int ld, int ch_off, int C)
     ctx->launches++;
     if (prof_begin(ctx, ZVX_K_STATS, 0, 0.0, 2.0 * (double)ctx->last_frames * C * sizeof(float))) return 1;
     CK(ctx, stats_launch(x, ld, ch_off, C, ctx->d_seg, ctx->last_B, 1, ctx->mu, ctx->rstd, ctx->stream));
+    return prof_end(ctx);
+}
+
+// mean / rstd of the tensor the previous conv launch wrote (its epilogue left per-tile partials in ctx->stat_part);
+// C_tail > 0: the asr_res channels of the concatenated decoder input follow, copied from ctx->asr_mu / asr_rstd
+int run_stats_finalize(zvx_ctx *ctx, int C, int C_tail)
+{
+    ctx->launches++;
+    if (prof_begin(ctx, ZVX_K_STATS, 0, 0.0, 16.0 * (double)ctx->total_tiles[0] * C)) return 1;
+    CK(ctx, stats_finalize_launch(ctx->stat_part, C, ctx->d_tiles, ctx->d_seg, ctx->last_B, 1, ctx->asr_mu, ctx->asr_rstd, C_tail,
+                                  ctx->mu, ctx->rstd, ctx->stream));
     return prof_end(ctx);
 }
 
@@ -929,6 +960,11 @@ int run_decoder(zvx_ctx *ctx, float *mel_out)
         return 0;
     };
 
+    // InstanceNorm statistics (ggml_norm, ggml-cpu.c:6880-6929; call sites stylettsdec.cpp:94-98,119-123,191): the conv that
+    // WRITES a tensor leaves per-tile sums in its epilogue and a small finalize launch turns them into mean / rstd right
+    // before the consumer; only tensors no conv of this schedule produced (enc_in, the asr_res branch) take the stand-alone pass
+    const bool fs = ctx->fused_stats && !ctx->use_ref_kernels && !ctx->conv_mt2 && ctx->stat_part;
+
     // ---- encode.0 / encode.1 : ResBlk1d (stylettsdec.cpp:69-149) ----
     const float *x = ctx->enc_in; int ldx = D;
     float *enc_out[2] = {ctx->e0, ctx->catA};
@@ -947,16 +983,16 @@ int run_decoder(zvx_ctx *ctx, float *mel_out)
                 return 1;
             sc = ctx->sc; ldsc = b.cout;
         }
-        if (run_stats(ctx, x, ldx, 0, b.cin)) return 1;
+        if (fs && i > 0 ? run_stats_finalize(ctx, b.cin, 0) : run_stats(ctx, x, ldx, 0, b.cin)) return 1;
         ConvCall c1; c1.L = &b.conv1; c1.x = x; c1.ldx = ldx; c1.pro_mode = PRO_NORM; c1.pro_slope = 0.2f;
         c1.mu = ctx->mu; c1.rstd = ctx->rstd; c1.stat_stride = b.cin; c1.g = b.n1w; c1.b = b.n1b; c1.gb_stride = 0;
-        c1.out32 = enc_h[i]; c1.ldo32 = b.cin;
+        c1.out32 = enc_h[i]; c1.ldo32 = b.cin; c1.stats = fs;
         if (run_norm_conv(ctx, c1)) return 1;
-        if (run_stats(ctx, enc_h[i], b.cin, 0, b.cin)) return 1;
+        if (fs ? run_stats_finalize(ctx, b.cin, 0) : run_stats(ctx, enc_h[i], b.cin, 0, b.cin)) return 1;
         ConvCall c2; c2.L = &b.conv2; c2.x = enc_h[i]; c2.ldx = b.cin; c2.pro_mode = PRO_NORM; c2.pro_slope = 0.2f;
         c2.mu = ctx->mu; c2.rstd = ctx->rstd; c2.stat_stride = b.cin; c2.g = b.n2w; c2.b = b.n2b; c2.gb_stride = 0;
         c2.res = sc; c2.ldres = ldsc; c2.scale = inv_sqrt2;
-        c2.out32 = enc_out[i]; c2.ldo32 = enc_ld[i];
+        c2.out32 = enc_out[i]; c2.ldo32 = enc_ld[i]; c2.stats = fs;
         if (b.learned_sc && join()) return 1;
         if (run_norm_conv(ctx, c2)) return 1;
         x = enc_out[i]; ldx = enc_ld[i];
@@ -972,6 +1008,13 @@ int run_decoder(zvx_ctx *ctx, float *mel_out)
         CK(ctx, norm_affine_launch(ctx->asr, R, R, ctx->d_seg, ctx->last_B, ctx->mu, ctx->rstd, ctx->asr1w, ctx->asr1b,
                                    ctx->catA, ctx->catB, CAT, BN, ctx->stream));
         if (prof_end(ctx)) return 1;
+        if (fs) {
+            // statistics of the asr_res channels of the concatenated input: the same for decode.0-2, computed once
+            ctx->launches++;
+            if (prof_begin(ctx, ZVX_K_STATS, 0, 0.0, 2.0 * (double)ctx->last_frames * R * sizeof(float))) return 1;
+            CK(ctx, stats_launch(ctx->catA, CAT, BN, R, ctx->d_seg, ctx->last_B, 1, ctx->asr_mu, ctx->asr_rstd, ctx->stream));
+            if (prof_end(ctx)) return 1;
+        }
     }
     // ---- decode.0-4 : AdainResBlk1d (stylettsdec.cpp:242-304) ----
     const float *din[5]  = {ctx->catA, ctx->catB, ctx->catA, ctx->d1, ctx->d2};
@@ -993,18 +1036,18 @@ int run_decoder(zvx_ctx *ctx, float *mel_out)
                 return 1;
             sc = ctx->sc; ldsc = b.cout;
         }
-        if (run_stats(ctx, din[i], dinl[i], 0, b.cin)) return 1;
+        if (fs ? run_stats_finalize(ctx, dinl[i] == CAT ? BN : b.cin, dinl[i] == CAT ? R : 0) : run_stats(ctx, din[i], dinl[i], 0, b.cin)) return 1;
         ConvCall c1; c1.L = &b.conv1; c1.x = din[i]; c1.ldx = dinl[i]; c1.pro_mode = PRO_NORM; c1.pro_slope = 0.2f;
         c1.mu = ctx->mu; c1.rstd = ctx->rstd; c1.stat_stride = b.cin;
         c1.g = ctx->adain_gb + a1.out_off; c1.b = ctx->adain_gb + a1.out_off + a1.C; c1.gb_stride = ctx->adain.total;
-        c1.out32 = h; c1.ldo32 = b.cout;
+        c1.out32 = h; c1.ldo32 = b.cout; c1.stats = fs;
         if (run_norm_conv(ctx, c1)) return 1;
-        if (run_stats(ctx, h, b.cout, 0, b.cout)) return 1;
+        if (fs ? run_stats_finalize(ctx, b.cout, 0) : run_stats(ctx, h, b.cout, 0, b.cout)) return 1;
         ConvCall c2; c2.L = &b.conv2; c2.x = h; c2.ldx = b.cout; c2.pro_mode = PRO_NORM; c2.pro_slope = 0.2f;
         c2.mu = ctx->mu; c2.rstd = ctx->rstd; c2.stat_stride = b.cout;
         c2.g = ctx->adain_gb + a2.out_off; c2.b = ctx->adain_gb + a2.out_off + a2.C; c2.gb_stride = ctx->adain.total;
         c2.res = sc; c2.ldres = ldsc; c2.scale = inv_sqrt2;
-        c2.out32 = dout[i]; c2.ldo32 = doutl[i];
+        c2.out32 = dout[i]; c2.ldo32 = doutl[i]; c2.stats = fs && i < 4;
         if (b.learned_sc && join()) return 1;
         if (run_norm_conv(ctx, c2)) return 1;
     }
@@ -1301,6 +1344,7 @@ int make_lane(zvx_ctx *parent)
     for (float **q : fp) *q = nullptr;
     l->H16 = l->X16 = l->R16 = nullptr;
     l->U16 = nullptr; l->Y16[0] = l->Y16[1] = l->Y16[2] = nullptr; l->chain_elems = 0;
+    l->stat_part = nullptr; l->stat_part_cap = 0; l->asr_mu = l->asr_rstd = nullptr;
     l->d_seg = l->d_tiles = l->d_wins = l->d_err = l->pin_tables = nullptr;
     l->pin_in_cap = l->pin_out_cap = 0;
     l->graphs.clear();           // the copies of the parent's graph handles are not the lane's to destroy
@@ -1405,6 +1449,7 @@ int zvx_create(zvx_ctx **out, const zvx_config *cfg, const zvx_tensor_desc *weig
     if (const char *e = getenv("ZVX_CONV_MT2")) ctx->conv_mt2 = atoi(e);
     if (const char *e = getenv("ZVX_CONV_CLUSTER")) ctx->conv_cluster = atoi(e);
     if (const char *e = getenv("ZVX_MRF_F16_CHAIN")) ctx->mrf_f16_chain = atoi(e);
+    if (const char *e = getenv("ZVX_FUSED_STATS")) ctx->fused_stats = atoi(e);
     if (const char *e = getenv("ZVX_CONV_SMEM_KB")) ctx->conv_smem_kb = atoi(e);
     if (const char *e = getenv("ZVX_GRAPHS")) ctx->use_graphs = atoi(e);
     if (const char *e = getenv("ZVX_FORK_BRANCHES")) ctx->fork_branches = atoi(e);

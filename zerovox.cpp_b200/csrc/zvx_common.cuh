@@ -82,6 +82,10 @@ struct ConvParams {
     float        out16_slope;
     int          out_mul;     // output row = seg_out_start + t*out_mul + out_add (polyphase up-conv)
     int          out_add;
+    // InstanceNorm statistics of the OUTPUT, fused into the epilogue (one-tile kernel): per (tile, output channel) the sum
+    // and the sum of squares of the final values over the tile's valid rows, in double; stats_finalize_kernel turns them
+    // into mean / rstd per (utterance, channel).  No atomics: fixed summation order, batch-independent results.
+    double2     *stats_out;   // [n_tiles][Cout] or null
     // ---- smem geometry (host computed) ----
     int          mt;          // M-tiles (128 rows each) per CTA: 1 or 2
     int          a_rows;      // rows per A stage (>= 128*mt + (ntaps-1)*tap_step)

@@ -32,6 +32,10 @@ cudaError_t mrf_fused_launch(int CH, const mrf::Params &p, int total_windows, cu
 cudaError_t stats_launch(const float *x, int ld, int ch_off, int C, const int *seg_start, int B, int rate,
                          float *mu, float *rstd, cudaStream_t st);
 
+// finish the statistics started by the conv epilogues (ConvParams::stats_out); channels [C, C + C_tail) are copied
+cudaError_t stats_finalize_launch(const double2 *part, int C, const int *tile_start, const int *seg_start, int B, int rate,
+                                  const float *tail_mu, const float *tail_rstd, int C_tail, float *mu, float *rstd, cudaStream_t st);
+
 struct AdainDesc {
     const float *fc_w;    // (2C, style_dim) row-major
     const float *fc_b;    // (2C)
