@@ -29,6 +29,8 @@
 //     fp16 pre-activated operand.
 #include <cstring>
 
+#include <cuda.h>
+
 #include "zvx_common.cuh"
 #include "zvx_internal.h"
 #include "ptx_sm100.cuh"
@@ -256,9 +258,11 @@ __device__ __forceinline__ void tmem_ld16x2(uint32_t taddr, uint32_t (&r)[32])
 // kernel runs two warps per lane quarter).  trow: tensor-memory address of the warp's lane quarter, column 0 of the tile.
 // stat_row (one-tile kernel, may be null): [NC] double2 of this warp's lane quarter, filled with the column sums / sums of
 // squares of the final values over the warp's valid rows.
+template <bool STATS>
 __device__ __forceinline__ void epilogue_tile(const ConvParams &p, uint32_t trow, float *slab, int lane, int t_first, int seg_len,
-                                              size_t seg_row0, int nchunk, int NC, int pass0, int pass_step, double2 *stat_row = nullptr)
+                                              size_t seg_row0, int nchunk, int NC, int pass0, int pass_step, double2 *stat_row_ = nullptr)
 {
+    double2 *const stat_row = STATS ? stat_row_ : nullptr;      // (kernels whose outputs never feed a norm compile without the sums)
     const int cl   = (lane & 7) * 4;        // this lane's 4 columns inside the 32-column pass
     const int rsel = lane >> 3;             // which row of a group of 4
     const bool has_res = p.res != nullptr, has_acc = p.acc_in != nullptr, has_o32 = p.out32 != nullptr, has_o16 = p.out16 != nullptr;
@@ -345,7 +349,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams &p, uint32_t trow
 
 // ------------------------------------------------------------------ the kernel
 template <int MODE, int MT>
-__global__ void __launch_bounds__(128 * MT + 64) conv_umma_kernel(const ConvParams p)
+__global__ void __launch_bounds__(128 * MT + 64) conv_umma_kernel(const ConvParams p, const __grid_constant__ CUtensorMap a_map)
 {
     constexpr int N_PRODUCERS = 128 * MT;
     constexpr int MMA_WARP    = 4 * MT;
@@ -357,6 +361,7 @@ __global__ void __launch_bounds__(128 * MT + 64) conv_umma_kernel(const ConvPara
     uint64_t *b_full     = bars + 2 * MAX_A_STAGES;               // [MAX_B_STAGES]
     uint64_t *b_empty    = bars + 2 * MAX_A_STAGES + MAX_B_STAGES;
     uint64_t *acc_full   = bars + 2 * MAX_A_STAGES + 2 * MAX_B_STAGES;
+    uint64_t *a_land     = acc_full + 1;                            // [MAX_A_STAGES] TMA mode: the box of a stage has landed
     uint32_t *tmem_slot  = reinterpret_cast<uint32_t *>(smem + 240);
 
     const int tid  = threadIdx.x;
@@ -375,6 +380,7 @@ __global__ void __launch_bounds__(128 * MT + 64) conv_umma_kernel(const ConvPara
     const uint32_t smem_base     = smem_u32(smem);
     const uint32_t a_base        = smem_base + SMEM_HEADER;
     const uint32_t b_base        = a_base + p.a_stages * a_stage_bytes;
+    const bool tma = MODE == PRO_F16 && p.use_tma;
 
     // ---- thread-block cluster: CL CTAs = CL time tiles of the same N-chunk share every weight stage.  Each CTA fetches
     //      1/CL of a stage and multicasts it to all of them, so the L2 -> SM weight traffic (the bound of these kernels:
@@ -397,9 +403,11 @@ __global__ void __launch_bounds__(128 * MT + 64) conv_umma_kernel(const ConvPara
 
     if (tid == 0) {
         for (int s = 0; s < p.a_stages; ++s) {
-            mbar_init(smem_u32(a_full + s), N_PRODUCERS);
+            mbar_init(smem_u32(a_full + s), tma ? 1u : (uint32_t)N_PRODUCERS);
             mbar_init(smem_u32(a_empty + s), 1);
+            mbar_init(smem_u32(a_land + s), 1);
         }
+        if (tma) tma_prefetch_desc(&a_map);
         for (int s = 0; s < p.b_stages; ++s) {
             mbar_init(smem_u32(b_full + s), 1);
             mbar_init(smem_u32(b_empty + s), (uint32_t)CL);       // a stage is free when every CTA of the cluster has used it
@@ -417,7 +425,50 @@ __global__ void __launch_bounds__(128 * MT + 64) conv_umma_kernel(const ConvPara
     if (warp < MMA_WARP) {
         // =================== A producers ===================
         const int need_rows = ROWS_CTA + (ntaps - 1) * p.tap_step;
-        {
+        if (tma) {
+            // TMA mode: one elected thread asks for the halo tile of every 64-channel chunk as ONE 3-D box
+            // (8 channels x a_rows rows x 8 channel groups -> exactly the no-swizzle K-major stage layout); rows beyond
+            // the buffer arrive as zeros.  Rows outside THIS utterance (the packed neighbours) are zeroed by warp 1 after
+            // the box has landed -- only the first / last tile of an utterance has any -- and warp 1 then hands the
+            // stage to the MMA warp.  Warps 2.. wait for the epilogue.
+            const int row_first = t0 + p.tap_off0;                          // utterance row of stage row 0
+            if (warp == 0) {
+                if (lane == 0) {
+                    const int gr = (int)((long long)seg_row0 - p.tma_row0) + row_first;
+                    const uint32_t box_bytes = 8u * lbo_a;
+                    int sa = 0;
+                    uint32_t ph = 0;
+                    for (int c = 0; c < nkc; ++c) {
+                        mbar_wait(smem_u32(a_empty + sa), ph ^ 1u, p.err_flag);
+                        mbar_arrive_expect_tx(smem_u32(a_land + sa), box_bytes);
+                        tma_load_3d(a_base + sa * a_stage_bytes, &a_map, 0, gr, c * (KCHUNK / 8), smem_u32(a_land + sa));
+                        if (++sa == p.a_stages) { sa = 0; ph ^= 1u; }
+                    }
+                }
+                __syncwarp();
+            } else if (warp == 1) {
+                const int lo_end = min(max(-row_first, 0), need_rows);           // stage rows [0, lo_end) precede the utterance
+                const int hi_beg = min(max(seg_len - row_first, 0), need_rows);  // stage rows [hi_beg, need_rows) follow it
+                const int nbad = lo_end + (need_rows - hi_beg);
+                int sa = 0;
+                uint32_t ph = 0;
+                for (int c = 0; c < nkc; ++c) {
+                    mbar_wait(smem_u32(a_land + sa), ph, p.err_flag);
+                    if (nbad > 0) {
+                        uint8_t *stage = smem + SMEM_HEADER + (size_t)sa * a_stage_bytes;
+                        for (int i = lane; i < nbad * 8; i += 32) {
+                            const int g = i & 7, k = i >> 3;
+                            const int rho = k < lo_end ? k : hi_beg + (k - lo_end);
+                            *reinterpret_cast<uint4 *>(stage + (size_t)g * lbo_a + (size_t)rho * 16) = make_uint4(0u, 0u, 0u, 0u);
+                        }
+                        fence_proxy_async_smem();
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(a_full + sa));
+                    if (++sa == p.a_stages) { sa = 0; ph ^= 1u; }
+                }
+            }
+        } else {
             int sa = 0;
             uint32_t ph = 0;
             for (int c = 0; c < nkc; ++c) {
@@ -443,10 +494,11 @@ __global__ void __launch_bounds__(128 * MT + 64) conv_umma_kernel(const ConvPara
         //  CTA waited for was the last one its peers sent, and they send nothing after the final K-chunk)
         // statistics partials of the 4 * MT lane quarters sit behind the slabs (also dead stage memory)
         double2 *stat_all = reinterpret_cast<double2 *>(smem + SMEM_HEADER + (size_t)(4 * MT) * SLAB_BYTES);
-        double2 *stat_row = p.stats_out ? stat_all + (size_t)warp * NC : nullptr;
-        epilogue_tile(p, trow, reinterpret_cast<float *>(smem + SMEM_HEADER + (size_t)warp * SLAB_BYTES), lane,
+        constexpr bool STATS = MODE == PRO_F16 || MODE == PRO_NORM;      // the decoder convs (conv_umma_plan enforces it)
+        double2 *stat_row = STATS && p.stats_out ? stat_all + (size_t)warp * NC : nullptr;
+        epilogue_tile<STATS>(p, trow, reinterpret_cast<float *>(smem + SMEM_HEADER + (size_t)warp * SLAB_BYTES), lane,
                       t0 + mt * TILE_M + (warp & 3) * 32, live ? seg_len : 0, seg_row0, nchunk, NC, 0, 1, stat_row);
-        if (p.stats_out) {
+        if (STATS && p.stats_out) {
             // all lane quarters of the tile, summed in a fixed order, one (sum, sum of squares) per output channel
             asm volatile("bar.sync 1, %0;" ::"r"(N_PRODUCERS) : "memory");
             if (live)
@@ -646,7 +698,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) conv_umma_pk_kernel(const ConvP
             mbar_wait(smem_u32(acc_full + buf), (uint32_t)(n >> 1) & 1u, p.err_flag);
             tc_fence_after_sync();
             const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)buf * acc_stride;
-            epilogue_tile(p, trow, slab, lane, tc.t0 + (warp & 3) * 32, tc.seg_len, tc.seg_row0, tc.nchunk, NC, egrp, 2);
+            epilogue_tile<false>(p, trow, slab, lane, tc.t0 + (warp & 3) * 32, tc.seg_len, tc.seg_row0, tc.nchunk, NC, egrp, 2);
             tc_fence_before_sync();
             mbar_arrive(smem_u32(acc_empty + buf));
         }
@@ -740,7 +792,10 @@ size_t conv_umma_plan(ConvParams &p, size_t smem_budget)
 {
     const int kc_max    = p.Cin < KCHUNK ? p.Cin : KCHUNK;
     const int need_rows = TILE_M * p.mt + (p.ntaps - 1) * p.tap_step;
-    p.a_rows            = round_a_rows(need_rows, kc_max);
+    // TMA boxes: at most 256 rows, always 8 channel groups (a partial last chunk is zero-filled), rows exactly the box
+    if (p.stats_out && p.pro_mode != PRO_F16 && p.pro_mode != PRO_NORM) p.stats_out = nullptr;
+    if (p.use_tma && (p.pro_mode != PRO_F16 || need_rows > 256 || p.Cin < KCHUNK || p.ldx % 8 || p.x_ch_off % 8)) p.use_tma = 0;
+    p.a_rows            = p.use_tma ? need_rows : round_a_rows(need_rows, kc_max);
     const size_t a_stage = (size_t)(kc_max >> 3) * p.a_rows * 16;
     const size_t b_stage = (size_t)kc_max * p.NC * 2;
     const int nkc        = (p.Cin + KCHUNK - 1) / KCHUNK;
@@ -818,10 +873,10 @@ cudaError_t conv_umma_pk_launch(const ConvParams &p, int total_tiles, int num_sm
 
 // launch with a thread-block cluster of p.cluster CTAs along x (1: plain launch)
 template <typename K>
-static cudaError_t launch_clustered(K kernel, dim3 grid, int threads, size_t smem, cudaStream_t st, const ConvParams &p)
+static cudaError_t launch_clustered(K kernel, dim3 grid, int threads, size_t smem, cudaStream_t st, const ConvParams &p, const CUtensorMap &a_map)
 {
     if (p.cluster <= 1) {
-        kernel<<<grid, threads, smem, st>>>(p);
+        kernel<<<grid, threads, smem, st>>>(p, a_map);
         return cudaGetLastError();
     }
     cudaLaunchConfig_t cfg = {};
@@ -836,7 +891,33 @@ static cudaError_t launch_clustered(K kernel, dim3 grid, int threads, size_t sme
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kernel, p);
+    return cudaLaunchKernelEx(&cfg, kernel, p, a_map);
+}
+
+// Tensor map of a PRO_F16 operand buffer for the TMA-staged A tiles: the [rows][ldx] fp16 matrix (first channel x_ch_off)
+// seen as (8 channels, rows, C/8 channel groups) with strides (2, 2 ldx, 16) bytes, box (8, box_rows, 8), no swizzle:
+// a box lands as [group][row][8 channels] = the K-major no-swizzle operand layout with LBO = box_rows * 16 bytes.
+static cudaError_t make_a_map(const ConvParams &p, long long rows_total, CUtensorMap *out)
+{
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        const cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+        if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) return cudaErrorNotSupported;
+        encode = reinterpret_cast<encode_fn>(fn);
+    }
+    void *base = const_cast<__half *>(reinterpret_cast<const __half *>(p.x) + (size_t)p.tma_row0 * p.ldx + p.x_ch_off);
+    const cuuint64_t dims[3] = {8, (cuuint64_t)rows_total, (cuuint64_t)(p.Cin / 8)};
+    const cuuint64_t strides[2] = {(cuuint64_t)p.ldx * 2, 16};
+    const cuuint32_t box[3] = {8, (cuuint32_t)p.a_rows, 8};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
 template <int MODE, int MT>
@@ -846,7 +927,15 @@ static cudaError_t launch_mode(const ConvParams &p, int total_tiles, size_t smem
     if (q.cluster != 2 && q.cluster != 4) q.cluster = 1;
     q.n_tiles = total_tiles;
     dim3 grid((total_tiles + q.cluster - 1) / q.cluster * q.cluster, p.Cout / p.NC, 1);
-    return launch_clustered(conv_umma_kernel<MODE, MT>, grid, 128 * MT + 64, smem, st, q);
+    CUtensorMap a_map;
+    memset(&a_map, 0, sizeof a_map);
+    if (MODE == PRO_F16 && q.use_tma) {
+        const cudaError_t e = make_a_map(q, q.tma_rows, &a_map);
+        if (e != cudaSuccess) return e;
+    } else {
+        q.use_tma = 0;
+    }
+    return launch_clustered(conv_umma_kernel<MODE, MT>, grid, 128 * MT + 64, smem, st, q, a_map);
 }
 
 template <int MODE>

@@ -77,6 +77,17 @@ __device__ __forceinline__ void bulk_copy_g2s_multicast(uint32_t dst, const void
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(mask)
                  : "memory");
 }
+// TMA: one 3-D tile of a tensor map (cuTensorMapEncodeTiled) -> shared memory; out-of-bounds elements arrive as zeros
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void *tmap, int c0, int c1, int c2, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void *tmap)
+{
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async_smem()
 {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -119,6 +119,7 @@ struct zvx_ctx {
     int use_graphs = 1;
     int chunk_group_max = 8;   // zvx_vocode_chunked: at most this many chunks per vocoder pass
     int conv_smem_kb = 100;   // shared-memory budget of a one-tile conv CTA (two CTAs per SM)
+    int conv_tma = 1;       // PRO_F16 operands of the one-tile conv kernel staged by TMA (cp.async.bulk.tensor) instead of cp.async
     int conv_cluster = 1;   // CTAs per cluster of the one-tile conv kernel sharing every weight stage by multicast; measured on
                             // B200 (profiles/r02_conv_cluster_ab.txt): 2 -> +7 %, 4 -> +19 % time on the decoder convs, so off
     int conv_mt2 = 0;   // two M-tiles per CTA: measured slower on B200 while the A producer is the limit (profiles/)
@@ -857,6 +858,9 @@ int run_conv(zvx_ctx *ctx, const ConvCall &cc)
             if (smem > 227 * 1024) return fail(ctx, "conv needs %zu bytes of shared memory", smem);
             CK(ctx, conv_umma_pk_launch(p, tiles, ctx->num_sms, smem, ctx->stream));
         } else {
+            p.use_tma = ctx->conv_tma && p.pro_mode == PRO_F16;
+            p.tma_row0 = 0;
+            p.tma_rows = (long long)ctx->last_frames * p.rate_in;
             const size_t smem = conv_umma_plan(p, p.mt == 2 ? 226 * 1024 : (size_t)ctx->conv_smem_kb * 1024);
             if (smem > 227 * 1024) return fail(ctx, "conv needs %zu bytes of shared memory", smem);
             p.cluster = 1;
@@ -1448,6 +1452,7 @@ int zvx_create(zvx_ctx **out, const zvx_config *cfg, const zvx_tensor_desc *weig
     if (const char *e = getenv("ZVX_BRANCH_SUM_IN_CONSUMER")) ctx->branch_sum_in_consumer = atoi(e);
     if (const char *e = getenv("ZVX_CONV_MT2")) ctx->conv_mt2 = atoi(e);
     if (const char *e = getenv("ZVX_CONV_CLUSTER")) ctx->conv_cluster = atoi(e);
+    if (const char *e = getenv("ZVX_CONV_TMA")) ctx->conv_tma = atoi(e);
     if (const char *e = getenv("ZVX_MRF_F16_CHAIN")) ctx->mrf_f16_chain = atoi(e);
     if (const char *e = getenv("ZVX_FUSED_STATS")) ctx->fused_stats = atoi(e);
     if (const char *e = getenv("ZVX_CONV_SMEM_KB")) ctx->conv_smem_kb = atoi(e);

@@ -86,6 +86,11 @@ struct ConvParams {
     // and the sum of squares of the final values over the tile's valid rows, in double; stats_finalize_kernel turns them
     // into mean / rstd per (utterance, channel).  No atomics: fixed summation order, batch-independent results.
     double2     *stats_out;   // [n_tiles][Cout] or null
+    // PRO_F16 operand staged by TMA (cp.async.bulk.tensor.3d, one box = a halo tile of 64 channels) instead of per-thread
+    // 16-byte cp.async; the kernel's tensor-map argument describes the [rows][ldx] fp16 buffer as (8 ch, rows, C/8 groups)
+    int          use_tma;
+    long long    tma_row0;    // first row of the tensor map inside the buffer (rows are addressed relative to it)
+    long long    tma_rows;    // rows of the buffer the tensor map covers
     // ---- smem geometry (host computed) ----
     int          mt;          // M-tiles (128 rows each) per CTA: 1 or 2
     int          a_rows;      // rows per A stage (>= 128*mt + (ntaps-1)*tap_step)
