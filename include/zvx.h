@@ -85,6 +85,15 @@ int zvx_vocode(zvx_ctx *ctx, const float *mel, int32_t L, float *wav);
 int zvx_synth_batch(zvx_ctx *ctx, int32_t B, const float *const *enc_seq, const float *const *style,
                     const int32_t *L, float *const *mel, float *const *wav);
 
+/* Pipelined form of zvx_synth_batch / zvx_synth_batch_pcm16 (exactly one of wav / pcm non-NULL): submit returns once the
+ * copies and kernels of the batch are enqueued; every buffer passed to it -- inputs and outputs -- must stay untouched
+ * until zvx_synth_batch_wait has returned (0 = every submitted batch completed).  Replaces a loop of ZeroVOXModel::eval
+ * calls (zerovox.cpp:326-334) for callers that synthesise batch after batch: the device -> host copy of batch i runs
+ * under the host -> device copy and the kernels of batch i + 1. */
+int zvx_synth_batch_submit(zvx_ctx *ctx, int32_t B, const float *const *enc_seq, const float *const *style,
+                           const int32_t *L, float *const *mel, float *const *wav, int16_t *const *pcm);
+int zvx_synth_batch_wait(zvx_ctx *ctx);
+
 /* Output stage: the waveform leaves the GPU as signed 16-bit PCM.
  * Replaces, for the batch, the float -> short conversion libsndfile performs inside
  * sf_write_float() when ZeroVOXModel::write_wav_file writes its SF_FORMAT_PCM_16 file

@@ -249,3 +249,30 @@ def test_fused_mrf_chain_matches_layerwise_path_and_reference(ctx, zvx):
     together = ctx.vocode_batch(mels)
     for m, w in zip(mels, together):
         assert np.array_equal(ctx.vocode(m), w)
+
+
+def test_pipelined_submit_wait_equals_synchronous_call(ctx, zvx):
+    """zvx_synth_batch_submit x 3 + one zvx_synth_batch_wait (consecutive batches overlap their copies and kernels on the
+    context's two streams) must give, bit for bit, what three synchronous zvx_synth_batch calls give."""
+    import ctypes
+    lens = zvx.synth.batch_lengths(10, seed=33, lo=300, hi=700)          # > 4096 frames: the two-lane path
+    rounds = []
+    for r in range(3):
+        ins = [zvx.synth.make_inputs(int(L), seed=700 + 10 * r + i) for i, L in enumerate(lens)]
+        rounds.append(([np.ascontiguousarray(e) for e, _ in ins], [np.ascontiguousarray(s) for _, s in ins]))
+    ref = [ctx.synth_batch(e, s, want_mel=False)[1] for e, s in rounds]
+    vp = ctypes.c_void_p
+    B = len(lens)
+    Larr = (ctypes.c_int32 * B)(*[int(x) for x in lens])
+    outs = [[np.empty(int(L) * 300, np.float32) for L in lens] for _ in range(3)]
+    keep = []
+    for r, (e, s) in enumerate(rounds):
+        pe = (vp * B)(*[a.ctypes.data for a in e])
+        ps = (vp * B)(*[a.ctypes.data for a in s])
+        pw = (vp * B)(*[a.ctypes.data for a in outs[r]])
+        keep.append((pe, ps, pw))
+        ctx.synth_batch_submit_ptrs(B, pe, ps, Larr, wav_ptrs=pw)
+    ctx.synth_batch_wait()
+    for r in range(3):
+        for a, b in zip(outs[r], ref[r]):
+            assert np.array_equal(a, b)

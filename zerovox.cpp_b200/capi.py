@@ -56,6 +56,7 @@ EXPORTS = [
     "zvx_kernel_launches", "zvx_reserve", "zvx_set_debug_kernels", "zvx_test_conv", "zvx_debug_fetch",
     "zvx_set_debug_stop", "zvx_profile_begin", "zvx_profile_end", "zvx_set_fused_mrf", "zvx_vocode_batch", "zvx_vocode_chunked",
     "zvx_synth_batch_pcm16", "zvx_vocode_pcm16", "zvx_write_wav_pcm16", "zvx_synth_batch_regulated", "zvx_regulated_frames",
+    "zvx_synth_batch_submit", "zvx_synth_batch_wait",
 ]
 
 _lib = None
@@ -85,6 +86,10 @@ def load_library() -> C.CDLL:
     lib.zvx_vocode.restype = i32
     lib.zvx_synth_batch.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(i32), C.POINTER(vp), C.POINTER(vp)]
     lib.zvx_synth_batch.restype = i32
+    lib.zvx_synth_batch_submit.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(i32), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    lib.zvx_synth_batch_submit.restype = i32
+    lib.zvx_synth_batch_wait.argtypes = [vp]
+    lib.zvx_synth_batch_wait.restype = i32
     lib.zvx_vocode_batch.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(i32), C.POINTER(vp)]
     lib.zvx_vocode_batch.restype = i32
     lib.zvx_synth_batch_pcm16.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(i32), C.POINTER(vp), C.POINTER(vp)]
@@ -320,6 +325,13 @@ class Context:
     def synth_batch_ptrs(self, B: int, enc_ptrs, style_ptrs, lengths, mel_ptrs, wav_ptrs):
         """Raw-pointer form (host pointers as ints) for bench.py: no numpy allocation in the timed region."""
         self._check(self.lib.zvx_synth_batch(self.h, B, enc_ptrs, style_ptrs, lengths, mel_ptrs, wav_ptrs))
+
+    def synth_batch_submit_ptrs(self, B: int, enc_ptrs, style_ptrs, lengths, wav_ptrs=None, pcm_ptrs=None):
+        """zvx_synth_batch_submit (raw host pointers): returns once the batch is enqueued; call synth_batch_wait()."""
+        self._check(self.lib.zvx_synth_batch_submit(self.h, B, enc_ptrs, style_ptrs, lengths, None, wav_ptrs, pcm_ptrs))
+
+    def synth_batch_wait(self):
+        self._check(self.lib.zvx_synth_batch_wait(self.h))
 
     def synth_batch_device(self, B: int, d_enc: int, d_style: int, lengths, d_mel: int, d_wav: int, sync: bool = False):
         self._check(self.lib.zvx_synth_batch_device(self.h, B, d_enc, d_style, lengths, d_mel or None, d_wav, int(sync)))

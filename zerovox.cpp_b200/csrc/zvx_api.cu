@@ -1710,7 +1710,7 @@ static int synth_chunk(zvx_ctx *c, int b0, int b1, const float *const *enc_seq, 
 }
 
 static int synth_batch_impl(zvx_ctx *ctx, int32_t B, const float *const *enc_seq, const float *const *style, const int32_t *L,
-                            float *const *mel, float *const *wav, int16_t *const *pcm)
+                            float *const *mel, float *const *wav, int16_t *const *pcm, bool wait = true)
 {
     if (!ctx) return 1;
     if (!ctx->cfg.with_decoder || !ctx->cfg.with_vocoder) return fail(ctx, "context was built without decoder or vocoder");
@@ -1729,7 +1729,7 @@ static int synth_batch_impl(zvx_ctx *ctx, int32_t B, const float *const *enc_seq
     if (ctx->prof || ctx->debug_stop >= 0 || B < 2 * nch || frames < 4096) nch = 1;
     if (nch == 1) {
         if (synth_chunk(ctx, 0, B, enc_seq, style, L, mel, wav, pcm)) return 1;
-        return check_device_error(ctx);
+        return wait ? check_device_error(ctx) : 0;
     }
     if (make_lane(ctx)) return 1;
     ctx->lane->use_ref_kernels = ctx->use_ref_kernels;
@@ -1766,6 +1766,7 @@ static int synth_batch_impl(zvx_ctx *ctx, int32_t B, const float *const *enc_seq
             return 1;
         }
     }
+    if (!wait) return 0;
     if (check_device_error(ctx->lane)) { ctx->err = ctx->lane->err; return 1; }
     return check_device_error(ctx);
 }
@@ -1775,6 +1776,25 @@ int zvx_synth_batch(zvx_ctx *ctx, int32_t B, const float *const *enc_seq, const 
 {
     if (ctx && !wav) return fail(ctx, "zvx_synth_batch: null argument");
     return synth_batch_impl(ctx, B, enc_seq, style, L, mel, wav, nullptr);
+}
+
+// Pipelined form: zvx_synth_batch_submit enqueues the copies and kernels of one batch and returns; the caller's buffers
+// (inputs AND outputs) must stay untouched until zvx_synth_batch_wait has returned.  Consecutive submits keep both copy
+// engines and the SMs busy: a batch's sub-batches alternate between the context's two streams, so the D2H of batch i
+// runs under the H2D and the kernels of batch i + 1 instead of a host synchronisation in between.
+int zvx_synth_batch_submit(zvx_ctx *ctx, int32_t B, const float *const *enc_seq, const float *const *style, const int32_t *L,
+                           float *const *mel, float *const *wav, int16_t *const *pcm)
+{
+    if (ctx && (!wav == !pcm)) return fail(ctx, "zvx_synth_batch_submit: exactly one of wav / pcm");
+    return synth_batch_impl(ctx, B, enc_seq, style, L, mel, wav, pcm, false);
+}
+
+int zvx_synth_batch_wait(zvx_ctx *ctx)
+{
+    if (!ctx) return 1;
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (ctx->lane && check_device_error(ctx->lane)) { ctx->err = ctx->lane->err; return 1; }
+    return check_device_error(ctx);
 }
 
 int zvx_synth_batch_pcm16(zvx_ctx *ctx, int32_t B, const float *const *enc_seq, const float *const *style, const int32_t *L,
