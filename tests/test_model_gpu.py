@@ -39,7 +39,21 @@ def full_gguf(zvx):
     return zvx.synth.write_model(zvx.synth.default_model_path(with_fs2=True), with_fs2=True)
 
 
-def test_model_reference_default_mode_matches_reference_program(full_gguf, tmp_path):
+@pytest.fixture(scope="module")
+def ref_v3(full_gguf):
+    """The unmodified reference program built with the SAME flags as zvx_model's host-side encoder (-march=x86-64-v3), run
+    live on this box for the default sentence.  (The committed golden comes from the -march=native build: the variance
+    adaptor quantises pitch / energy into 256 buckets, fs2encoder.cpp:442-474, so an ISA-level difference of 1e-7 can flip
+    a bucket and change a phoneme's features by a whole embedding row -- ISA builds of the reference are not comparable
+    with each other at the waveform level, 25 dB measured.)"""
+    import refrun
+    exe = os.path.join(ROOT, "oracle", "_ref", "zvfull_v3")
+    assert os.path.exists(exe), "oracle/_ref/zvfull_v3 missing"
+    g = regulator_golden("default")[0]
+    return refrun.run_full(full_gguf, g["src"], g["puncts"], g["style"], stages="full", binary=exe)
+
+
+def test_model_reference_default_mode_matches_reference_program(full_gguf, ref_v3, tmp_path):
     """max_seq_len frames with the zero tail (what ZeroVOXModel::eval does): frame count and waveform of the reference."""
     assert os.path.exists(EXE), "host/_build/zvx_model missing (built by __graft_entry__.build() where /root/reference exists)"
     g, _, frames, T = regulator_golden("default")
@@ -48,19 +62,17 @@ def test_model_reference_default_mode_matches_reference_program(full_gguf, tmp_p
     assert j["frames"] == [frames] and j["mode"] == "reference_default"
     pcm = np.fromfile(tmp_path / "o.0.pcm.i16", dtype=np.int16)
     assert pcm.size == T * 300
-    ref = zv_oracle.pcm16(g["wav"])
-    # The encoder here is the reference's fs2encoder.cpp built for x86-64-v3 (host/Makefile), the golden run used the
-    # -march=native build: the two differ at the reference's own ISA-to-ISA floor (~61 dB), which adds to the
-    # GPU path's distance from the reference.  Gate: 2e-3 of full scale and 55 dB (PCM_16 quantisation noise included).
+    assert ref_v3["frames"] == frames
+    ref = zv_oracle.pcm16(ref_v3["wav"])
     lsb = int(np.abs(pcm.astype(np.int32) - ref.astype(np.int32)).max())
-    snr = zv_oracle.snr_db(g["wav"], pcm.astype(np.float32) / 32767.0)
-    assert lsb <= 66 and snr >= 55.0, (lsb, snr)
+    snr = zv_oracle.snr_db(ref_v3["wav"], pcm.astype(np.float32) / 32767.0)
+    assert lsb <= 33 and snr >= 58.0, (lsb, snr)          # 1e-3 of full scale; 60 dB minus the PCM_16 quantisation noise
     with wave.open(str(tmp_path / "o.0.wav"), "rb") as w:
         assert (w.getnchannels(), w.getsampwidth(), w.getframerate(), w.getnframes()) == (1, 2, 24000, T * 300)
         assert np.array_equal(np.frombuffer(w.readframes(T * 300), dtype="<i2"), pcm)
 
 
-def test_model_valid_frames_and_batched_eval(full_gguf, gguf_path, tmp_path):
+def test_model_valid_frames_and_batched_eval(full_gguf, gguf_path, ref_v3, tmp_path):
     """f1: only the frames the length regulator produced are synthesised (vs a live reference at that length), and a batch
     of sentences through ONE GPU call equals the sentences one by one, bit for bit."""
     import refrun
@@ -74,7 +86,8 @@ def test_model_valid_frames_and_batched_eval(full_gguf, gguf_path, tmp_path):
         assert pcm.size == frames * 300
         _run([full_gguf, str(tmp_path / f"one{i}"), str(tmp_path / f"s{i}.bin")])
         assert np.array_equal(np.fromfile(tmp_path / f"one{i}.0.pcm.i16", dtype=np.int16), pcm)
-        ref = refrun.run(gguf_path, frames, hidden[:frames], g["style"])
-        lsb = int(np.abs(pcm.astype(np.int32) - zv_oracle.pcm16(ref["wav"]).astype(np.int32)).max())
-        snr = zv_oracle.snr_db(ref["wav"], pcm.astype(np.float32) / 32767.0)
-        assert lsb <= 66 and snr >= 55.0, (i, lsb, snr)
+        if i == 0:      # own-length reference fed the hidden_state of the same-ISA encoder run
+            ref = refrun.run(gguf_path, frames, ref_v3["hidden"][:frames], g["style"])
+            lsb = int(np.abs(pcm.astype(np.int32) - zv_oracle.pcm16(ref["wav"]).astype(np.int32)).max())
+            snr = zv_oracle.snr_db(ref["wav"], pcm.astype(np.float32) / 32767.0)
+            assert lsb <= 33 and snr >= 58.0, (i, lsb, snr)
