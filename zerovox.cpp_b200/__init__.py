@@ -3,4 +3,4 @@
 The directory name contains a dot, so it is imported through `zvxload.py` at the repo
 root (`from zvxload import zvx`), which registers it as module `zerovox_cpp_b200`.
 """
-from . import gguf_io, synth, sharding  # noqa: F401
+from . import gguf_io, synth, sharding, convert  # noqa: F401
