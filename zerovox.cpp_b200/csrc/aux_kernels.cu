@@ -376,7 +376,7 @@ constexpr int OC_MAX_K = 16;
 
 // Generic shape: weights staged in shared memory.
 __global__ void __launch_bounds__(128) out_conv_kernel(const float *__restrict__ x, const float *__restrict__ x2,
-                                                       const float *__restrict__ x3, float sum_scale, int C, int K,
+                                                       const float *__restrict__ x3, const __half *__restrict__ x16, float sum_scale, int C, int K,
                                                        const __half *__restrict__ w_raw, const float *__restrict__ bias,
                                                        float slope, const int *__restrict__ seg_start,
                                                        const int *__restrict__ tile_start, int B, int rate,
@@ -402,9 +402,13 @@ __global__ void __launch_bounds__(128) out_conv_kernel(const float *__restrict__
         const int t = t0 - pad + r;
         float v = 0.f;
         if (t >= 0 && t < seg_len) {
-            float xv = x[(row0 + t) * C + c];
-            if (x2) xv = __fmul_rn(__fadd_rn(__fadd_rn(xv, x2[(row0 + t) * C + c]), x3[(row0 + t) * C + c]), sum_scale);
-            v = __half2float(__float2half_rn(lrelu_f(xv, slope)));
+            if (x16) {
+                v = __half2float(x16[(row0 + t) * C + c]);          // already averaged, activated and rounded by the producer
+            } else {
+                float xv = x[(row0 + t) * C + c];
+                if (x2) xv = __fmul_rn(__fadd_rn(__fadd_rn(xv, x2[(row0 + t) * C + c]), x3[(row0 + t) * C + c]), sum_scale);
+                v = __half2float(__float2half_rn(lrelu_f(xv, slope)));
+            }
         }
         tile[r * (C + 1) + c] = v;
     }
@@ -426,7 +430,8 @@ __global__ void __launch_bounds__(128) out_conv_kernel(const float *__restrict__
 struct OutConvW { float w[7 * 32]; float bias; };      // [k][c]
 
 __global__ void __launch_bounds__(128) out_conv_32x7_kernel(const float *__restrict__ x, const float *__restrict__ x2,
-                                                            const float *__restrict__ x3, float sum_scale, const OutConvW W, float slope,
+                                                            const float *__restrict__ x3, const __half *__restrict__ x16, float sum_scale,
+                                                            const OutConvW W, float slope,
                                                             const int *__restrict__ seg_start,
                                                             const int *__restrict__ tile_start, int B, int rate,
                                                             float *__restrict__ wav, int16_t *__restrict__ pcm)
@@ -443,6 +448,19 @@ __global__ void __launch_bounds__(128) out_conv_32x7_kernel(const float *__restr
         const int r = i >> 3, c4 = (i & 7) * 4;
         const int t = t0 - (K - 1) / 2 + r;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (x16) {
+            // ready-made operand (the last residual block's final phase averaged the branches, applied the
+            // leaky-ReLU and rounded to fp16): 8 bytes per 4 channels instead of 3 x 16
+            float *d = tile + r * LD + c4;
+            if (t >= 0 && t < seg_len) {
+                const uint2 h = *reinterpret_cast<const uint2 *>(x16 + (row0 + t) * C + c4);
+                const __half2 h01 = *reinterpret_cast<const __half2 *>(&h.x), h23 = *reinterpret_cast<const __half2 *>(&h.y);
+                d[0] = __low2float(h01); d[1] = __high2float(h01); d[2] = __low2float(h23); d[3] = __high2float(h23);
+            } else {
+                d[0] = d[1] = d[2] = d[3] = 0.f;
+            }
+            continue;
+        }
         if (t >= 0 && t < seg_len) {
             v = *reinterpret_cast<const float4 *>(x + (row0 + t) * C + c4);
             if (x2) {
@@ -477,7 +495,7 @@ __global__ void __launch_bounds__(128) out_conv_32x7_kernel(const float *__restr
     store_sample(tanhf(__fadd_rn(__fadd_rn(acc0, acc1), W.bias)), row0 + t, wav, pcm);
 }
 
-cudaError_t out_conv_launch(const float *x, const float *x2, const float *x3, float sum_scale, int C, int K, const __half *w_raw, const float *bias, const float *w_host_kc,
+cudaError_t out_conv_launch(const float *x, const float *x2, const float *x3, const __half *x16, float sum_scale, int C, int K, const __half *w_raw, const float *bias, const float *w_host_kc,
                             float bias_host, float slope, const int *seg_start, const int *tile_start, int B, int rate,
                             int total_tiles, float *wav, int16_t *pcm, cudaStream_t st)
 {
@@ -485,12 +503,12 @@ cudaError_t out_conv_launch(const float *x, const float *x2, const float *x3, fl
         OutConvW W;
         for (int i = 0; i < 7 * 32; ++i) W.w[i] = w_host_kc[i];
         W.bias = bias_host;
-        out_conv_32x7_kernel<<<total_tiles, 128, 0, st>>>(x, x2, x3, sum_scale, W, slope, seg_start, tile_start, B, rate, wav, pcm);
+        out_conv_32x7_kernel<<<total_tiles, 128, 0, st>>>(x, x2, x3, x16, sum_scale, W, slope, seg_start, tile_start, B, rate, wav, pcm);
         return cudaGetLastError();
     }
     if (C > OC_MAX_C || K > OC_MAX_K) return cudaErrorInvalidValue;
     const size_t smem = (OC_MAX_K * OC_MAX_C + (128 + OC_MAX_K) * (OC_MAX_C + 1)) * sizeof(float);
-    out_conv_kernel<<<total_tiles, 128, smem, st>>>(x, x2, x3, sum_scale, C, K, w_raw, bias, slope, seg_start, tile_start, B, rate, wav, pcm);
+    out_conv_kernel<<<total_tiles, 128, smem, st>>>(x, x2, x3, x16, sum_scale, C, K, w_raw, bias, slope, seg_start, tile_start, B, rate, wav, pcm);
     return cudaGetLastError();
 }
 

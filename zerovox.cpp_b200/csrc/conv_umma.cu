@@ -564,14 +564,19 @@ __global__ void __launch_bounds__(128 * MT + 64) conv_umma_kernel(const ConvPara
             for (int c = 0; c < nkc; ++c) {
                 const uint32_t bytes = (uint32_t)min(KCHUNK, Cin - c * KCHUNK) * NC * 2u;
                 const uint32_t part = bytes / (uint32_t)CL;          // this CTA's share of the stage (a multiple of 16 bytes)
+#ifdef ZVX_WHATIF_HALF_WEIGHTS
+                const uint32_t wbytes = (bytes / 32u) * 16u;         // timing experiment only (wrong results): half the weight stream
+#else
+                const uint32_t wbytes = bytes;
+#endif
                 for (int a = 0; a < ntaps; ++a, src += bytes) {
                     // b_empty counts the commits of ALL CTAs of the cluster: the share goes into every peer's stage
                     mbar_wait(smem_u32(b_empty + sb), phb ^ 1u, p.err_flag);
-                    mbar_arrive_expect_tx(smem_u32(b_full + sb), bytes);
+                    mbar_arrive_expect_tx(smem_u32(b_full + sb), CL > 1 ? bytes : wbytes);
                     if (CL > 1)
                         bulk_copy_g2s_multicast(b_base + sb * b_stage_bytes + crank * part, src + crank * part, part, smem_u32(b_full + sb), cmask);
                     else
-                        bulk_copy_g2s(b_base + sb * b_stage_bytes, src, bytes, smem_u32(b_full + sb));
+                        bulk_copy_g2s(b_base + sb * b_stage_bytes, src, wbytes, smem_u32(b_full + sb));
                     if (++sb == b_stages) { sb = 0; phb ^= 1u; }
                 }
             }

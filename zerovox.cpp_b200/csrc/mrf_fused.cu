@@ -463,8 +463,11 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
                         const float4 b4 = make_float4(__ldg(L.bias + rq), __ldg(L.bias + rq + 8), __ldg(L.bias + rq + 16), __ldg(L.bias + rq + 24));
                         tmem_wait_ld();
                         if (has_next) publish();
-                        float *oq = p.out + (w.row0 + (size_t)tw) * CH + c4;
-                        const float *aq = p.acc_in ? p.acc_in + (w.row0 + (size_t)tw) * CH + c4 : nullptr;
+                        const size_t base = (w.row0 + (size_t)tw) * CH + c4;
+                        float *oq = p.out ? p.out + base : nullptr;
+                        uint16_t *hq = p.out16 ? p.out16 + base : nullptr;
+                        const float *aq = p.acc_in ? p.acc_in + base : nullptr;
+                        const float *aq2 = p.acc_in2 ? p.acc_in2 + base : nullptr;
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
                             const int tau = S * (colw + 8 * (i >> 1) + 2 * (lane & 3) + (i & 1)) + sQ;
@@ -473,17 +476,29 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
                                 float4 v = make_float4(__fadd_rn(__uint_as_float(r0[i0]), b4.x), __fadd_rn(__uint_as_float(r0[i0 + 2]), b4.y),
                                                        __fadd_rn(__uint_as_float(r1[i0]), b4.z), __fadd_rn(__uint_as_float(r1[i0 + 2]), b4.w));
                                 if (aq) {
-                                    const float4 a = *reinterpret_cast<const float4 *>(aq + (size_t)tau * CH);
+                                    float4 a = *reinterpret_cast<const float4 *>(aq + (size_t)tau * CH);
+                                    if (aq2) {       // (y_0 + y_1) + y_2: the reference's order (hifigan.cpp:300-311)
+                                        const float4 a2 = *reinterpret_cast<const float4 *>(aq2 + (size_t)tau * CH);
+                                        a = make_float4(__fadd_rn(a.x, a2.x), __fadd_rn(a.y, a2.y), __fadd_rn(a.z, a2.z), __fadd_rn(a.w, a2.w));
+                                    }
                                     v = make_float4(__fadd_rn(a.x, v.x), __fadd_rn(a.y, v.y), __fadd_rn(a.z, v.z), __fadd_rn(a.w, v.w));
                                 }
                                 if (p.has_scale) v = make_float4(__fmul_rn(v.x, p.scale), __fmul_rn(v.y, p.scale), __fmul_rn(v.z, p.scale), __fmul_rn(v.w, p.scale));
-                                *reinterpret_cast<float4 *>(oq + (size_t)tau * CH) = v;
+                                if (oq) *reinterpret_cast<float4 *>(oq + (size_t)tau * CH) = v;
+                                if (hq) {
+                                    uint2 h;
+                                    h.x = pack_h2(lrelu_max(v.x, p.out16_slope), lrelu_max(v.y, p.out16_slope));
+                                    h.y = pack_h2(lrelu_max(v.z, p.out16_slope), lrelu_max(v.w, p.out16_slope));
+                                    *reinterpret_cast<uint2 *>(hq + (size_t)tau * CH) = h;
+                                }
                             }
                         }
                     } else {
                     const float bias = __ldg(L.bias + oc);
-                    float *out = p.out + w.row0 * CH + gc;
+                    float *out = p.out ? p.out + w.row0 * CH + gc : nullptr;
+                    uint16_t *out16 = p.out16 ? p.out16 + w.row0 * CH + gc : nullptr;
                     const float *ain = p.acc_in ? p.acc_in + w.row0 * CH + gc : nullptr;
+                    const float *ain2 = p.acc_in2 ? p.acc_in2 + w.row0 * CH + gc : nullptr;
                     uint32_t r0[32], r1[32];
                     tmem_ld32(tlane + acc_col + (uint32_t)colw, r0);
                     tmem_ld32(tlane + acc_col + (uint32_t)(colw + 32), r1);
@@ -500,7 +515,9 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
                                 for (int i = 0; i < 16; ++i) {
                                     const int tau = S * (col0 + 16 * h + i) + s;
                                     const int t   = tw + tau;
-                                    a[i] = (tau >= p.halo && tau < p.halo + p.valid && t < T) ? ain[(size_t)t * CH] : 0.f;
+                                    const bool ok = tau >= p.halo && tau < p.halo + p.valid && t < T;
+                                    a[i] = ok ? ain[(size_t)t * CH] : 0.f;
+                                    if (ok && ain2) a[i] = __fadd_rn(a[i], ain2[(size_t)t * CH]);
                                 }
                             }
 #pragma unroll
@@ -511,7 +528,8 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
                                     float v = __fadd_rn(__uint_as_float(r[16 * h + i]), bias);
                                     if (ain) v = __fadd_rn(a[i], v);
                                     if (p.has_scale) v = __fmul_rn(v, p.scale);
-                                    out[(size_t)t * CH] = v;
+                                    if (out) out[(size_t)t * CH] = v;
+                                    if (out16) out16[(size_t)t * CH] = __half_as_ushort(__float2half_rn(lrelu_max(v, p.out16_slope)));
                                 }
                             }
                         }
@@ -599,9 +617,11 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
                 const char *ybase = reinterpret_cast<const char *>(p.y_in + (wn.row0 + (size_t)lo) * CH);
                 const int nlines = (hi - lo) * (CH * 4) / 128;
                 for (int i = lane; i < nlines; i += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(ybase + (size_t)i * 128));
-                if (p.acc_in) {
+                for (int k = 0; k < 2; ++k) {
+                    const float *acc = k ? p.acc_in2 : p.acc_in;
+                    if (!acc) continue;
                     const int alo = max(wn.tw + p.halo, 0), ahi = min(wn.tw + p.halo + p.valid, wn.T);
-                    const char *abase = reinterpret_cast<const char *>(p.acc_in + (wn.row0 + (size_t)alo) * CH);
+                    const char *abase = reinterpret_cast<const char *>(acc + (wn.row0 + (size_t)alo) * CH);
                     const int alines = (ahi - alo) * (CH * 4) / 128;
                     for (int i = lane; i < alines; i += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(abase + (size_t)i * 128));
                 }

@@ -137,7 +137,10 @@ struct Layer {
 struct Params {
     const float    *y_in;       // [rows][CH] fp32 block input (up-conv output)
     const float    *acc_in;     // running sum over residual blocks or null, indexed like out
-    float          *out;        // [rows][CH] fp32
+    const float    *acc_in2;    // second addend (stage hand-off: the other two blocks' outputs are summed here) or null
+    float          *out;        // [rows][CH] fp32 or null
+    uint16_t       *out16;      // [rows][CH] fp16(leaky_relu(result, out16_slope)): the next conv's ready-made operand, or null
+    float           out16_slope;
     float           scale;      // out = (acc_in + y) * scale when has_scale
     int             has_scale;
     float           in_slope;   // leaky-relu slope of the first conv input (0.1)

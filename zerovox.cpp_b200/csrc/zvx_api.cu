@@ -151,6 +151,14 @@ struct zvx_ctx {
     __half *U16 = nullptr, *Y16[3] = {nullptr, nullptr, nullptr};
     int64_t chain_elems = 0;
     int mrf_f16_chain = 1;
+    // stage hand-off of the fused MRF stages: the last residual block's final phase adds the other two blocks' outputs,
+    // averages, applies the consumer's leaky-ReLU and writes ONE fp16 operand (S16, ping-pong per stage) instead of three
+    // fp32 tensors that the next up-conv / the output conv would each read (12 -> 2 bytes per element on the consumer side)
+    // Measured on B200 (profiles/r02_stage_handoff_ab.txt): consumers -0.63 ms (out_conv 0.80 -> 0.46, up-convs -0.30), but
+    // the final phase of the last block, which sits between two windows of the persistent kernel, pays the two extra
+    // reads: stages 1-3 +1.6 ms.  Off by default; the code stays as the measured alternative (ZVX_STAGE_HANDOFF=1).
+    __half *S16[2] = {nullptr, nullptr};
+    int stage_handoff = 0;
     __half *H16 = nullptr, *X16 = nullptr, *R16 = nullptr;   // X16: decoder conv operand (normalised, activated, fp16); R16: raw input as fp16
     int dec_prepass = 1;
     int *d_seg = nullptr;                         // [B+1] frames prefix
@@ -656,6 +664,7 @@ int reserve(zvx_ctx *ctx, int64_t frames, int batch)
         dev_free(ctx, ctx->X16); ctx->X16 = nullptr;
         dev_free(ctx, ctx->R16); ctx->R16 = nullptr;
         dev_free(ctx, ctx->U16); ctx->U16 = nullptr;
+        for (int j = 0; j < 2; ++j) { dev_free(ctx, ctx->S16[j]); ctx->S16[j] = nullptr; }
         for (int j = 0; j < 3; ++j) { dev_free(ctx, ctx->Y16[j]); ctx->Y16[j] = nullptr; }
         const int D = c.dim_in, BN = 2 * D, R = c.residual_dim;
         if (c.with_decoder) {
@@ -674,6 +683,9 @@ int reserve(zvx_ctx *ctx, int64_t frames, int batch)
                 dev_alloc(ctx, &ctx->T2, F * S) ||
                 dev_alloc(ctx, &ctx->H16, F * S) || dev_alloc(ctx, &ctx->wav, F * c.hop_size))
                 return 1;
+            if (ctx->stage_handoff)
+                for (int j = 0; j < 2; ++j)
+                    if (dev_alloc(ctx, &ctx->S16[j], F * S)) return 1;
             // fp16 operand chain of the stages that run conv by conv
             ctx->chain_elems = 0;
             if (ctx->mrf_f16_chain)
@@ -1084,6 +1096,7 @@ int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out, int16_t *pcm_
         if (run_conv(ctx, ic)) return 1;
     }
     const float *vin = ctx->v0, *vin2 = nullptr, *vin3 = nullptr;   // vin2/vin3: stage output still split in 3 branches
+    const __half *vin16 = nullptr;                                  // stage output handed over as ONE ready-made fp16 operand
     float *vout[2] = {ctx->VA, ctx->VB};
     const float third = (float)(1.0 / (float)nb);
     const bool fork_ok = ctx->fork_branches && ctx->fork_stream[0] && ctx->fkY1[0] && !ctx->prof && ctx->debug_stop < 0 && !ctx->use_ref_kernels;
@@ -1101,12 +1114,13 @@ int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out, int16_t *pcm_
         if (ctx->use_fused_upconv && ctx->upf[i].OC) {
             ConvCall u; u.kind = ZVX_K_UPCONV; u.stage = i; u.L = &ctx->upf[i]; u.x = vin; u.ldx = cin; u.rate_idx = i;
             u.pro_mode = PRO_LRELU; u.pro_slope = 0.1f; u.out32 = ctx->U; u.ldo32 = s * ch; u.out_mul = 1;
-            if (vin2) { u.pro_mode = PRO_SUM3; u.x2 = vin2; u.x3 = vin3; u.sum_scale = third; }
+            if (vin16) { u.x = vin16; u.pro_mode = PRO_F16; }
+            else if (vin2) { u.pro_mode = PRO_SUM3; u.x2 = vin2; u.x3 = vin3; u.sum_scale = third; }
             u.flops = 2.0 * (double)ctx->last_frames * ctx->rates[i] * s * ch * cin * (ctx->up[i].K / s);
             if (chain) { u.out16 = ctx->U16; u.ldo16 = s * ch; u.out16_slope = 0.1f; }
             if (run_conv(ctx, u)) return 1;
         } else {
-            const bool pre = vin2 && !ctx->use_ref_kernels;
+            const bool pre = vin2 && !vin16 && !ctx->use_ref_kernels;
             if (pre) {
                 // one pass makes the fp16 operand lrelu(mean of the 3 branches) for all s phase launches
                 const size_t n = (size_t)ctx->last_frames * ctx->rates[i] * cin;
@@ -1123,7 +1137,8 @@ int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out, int16_t *pcm_
             for (int phi = 0; phi < s && !rc; ++phi) {
                 ConvCall u; u.kind = ZVX_K_UPCONV; u.stage = i; u.L = &ctx->up[i]; u.variant = phi; u.x = vin; u.ldx = cin; u.rate_idx = i;
                 u.pro_mode = PRO_LRELU; u.pro_slope = 0.1f; u.out32 = ctx->U; u.ldo32 = ch; u.out_mul = s;
-                if (pre) { u.x = ctx->H16; u.pro_mode = PRO_F16; }
+                if (vin16) { u.x = vin16; u.pro_mode = PRO_F16; }
+                else if (pre) { u.x = ctx->H16; u.pro_mode = PRO_F16; }
                 else if (vin2) { u.pro_mode = PRO_SUM3; u.x2 = vin2; u.x3 = vin3; u.sum_scale = third; }
                 if (chain) { u.out16 = ctx->U16; u.ldo16 = ch; u.out16_slope = 0.1f; }
                 const int lane_id = fork_ok ? phi % 3 : 0;
@@ -1149,6 +1164,13 @@ int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out, int16_t *pcm_
         // branch buffer j, so no conv epilogue reads a running sum.
         const bool split = ctx->branch_sum_in_consumer && !ctx->use_ref_kernels && nb == 3;
         float *branch_out[3] = {ctx->CS, ctx->VA, ctx->VB};
+        // stage hand-off: every block of the stage is a fused chain -> the last chain of the last block runs after the
+        // other blocks, sums the three outputs in the reference's order and emits the consumer's fp16 operand
+        bool handoff = split && ctx->stage_handoff && ctx->S16[0] && ctx->use_fused && ctx->debug_stop < 0;
+        for (int j = 0; j < nb; ++j) handoff = handoff && ctx->fused[(size_t)i * nb + j].CH != 0;
+        const FusedChain *deferred = nullptr;
+        const float *deferred_yin = nullptr;
+        int deferred_CH = 0, deferred_ncol = 0;
         // blocks 1 and 2 go to their own streams (own temporaries), joined before the consumer
         const bool fork = split && fork_ok;
         cudaStream_t main_stream = ctx->stream;
@@ -1177,6 +1199,10 @@ int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out, int16_t *pcm_
                 for (size_t q = 0; q < fb.chains.size(); ++q) {
                     const FusedChain &fc = fb.chains[q];
                     const bool lastc = q + 1 == fb.chains.size();
+                    if (handoff && lastc && j == nb - 1) {        // launched after the join, below
+                        deferred = &fc; deferred_yin = yin; deferred_CH = fb.CH; deferred_ncol = fb.ncol;
+                        break;
+                    }
                     mrf::Params fp;
                     memset(&fp, 0, sizeof fp);
                     fp.y_in = yin;
@@ -1239,8 +1265,41 @@ int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out, int16_t *pcm_
                 if (run_conv(ctx, c2)) return 1;
             }
         }
-        if (split) { vin = branch_out[0]; vin2 = branch_out[1]; vin3 = branch_out[2]; ctx->stage_is_split[i] = 1; }
-        else { vin = vout[i & 1]; vin2 = vin3 = nullptr; }
+        if (deferred) {
+            const FusedChain &fc = *deferred;
+            mrf::Params fp;
+            memset(&fp, 0, sizeof fp);
+            fp.y_in = deferred_yin;
+            fp.in_slope = 0.1f;
+            fp.tbl0 = fc.tbl0;
+            fp.nlayers = fc.nlayers;
+            for (int l = 0; l < fc.nlayers; ++l) fp.L[l] = fc.layers[l];
+            fp.seg_start = ctx->d_seg;
+            fp.win_start = ctx->d_wins + (size_t)fc.wincfg * (ctx->cap_batch + 1);
+            fp.B = ctx->last_B;
+            fp.ncol = deferred_ncol;
+            fp.prefetch = ctx->fused_prefetch;
+            fp.flags = ctx->fused_flags;
+            fp.resident_ctas = ctx->fused_persistent ? ctx->num_sms * (deferred_ncol == 128 ? 2 : 1) : 0;
+            fp.rate = ctx->rates[i + 1];
+            fp.halo = fc.halo;
+            fp.valid = fc.valid;
+            fp.err_flag = ctx->d_err;
+            fp.acc_in = branch_out[0];                     // c = ((y_0 + y_1) + y_2) / 3   (hifigan.cpp:300-315)
+            fp.acc_in2 = branch_out[1];
+            fp.has_scale = 1; fp.scale = third;
+            fp.out = nullptr;
+            fp.out16 = reinterpret_cast<uint16_t *>(ctx->S16[i & 1]);
+            fp.out16_slope = i + 1 == c.num_upsamples ? 0.01f : 0.1f;      // leaky_relu of the consumer (hifigan.cpp:281 / :324)
+            ctx->launches++;
+            const double rows = (double)ctx->last_frames * fp.rate;
+            if (prof_begin(ctx, ZVX_K_MRF_CONV, i, rows * fc.flops_per_row, 0.0)) return 1;
+            CK(ctx, mrf_fused_launch(deferred_CH, fp, ctx->total_wins[fc.wincfg], ctx->stream));
+            if (prof_end(ctx)) return 1;
+            vin = vin2 = vin3 = nullptr;
+            vin16 = ctx->S16[i & 1];
+        } else if (split) { vin = branch_out[0]; vin2 = branch_out[1]; vin3 = branch_out[2]; vin16 = nullptr; ctx->stage_is_split[i] = 1; }
+        else { vin = vout[i & 1]; vin2 = vin3 = nullptr; vin16 = nullptr; }
     }
     if (ctx->debug_stop >= 0) return 0;
     // leaky_relu(0.01) -> output_conv -> tanh (hifigan.cpp:324-345)
@@ -1252,7 +1311,7 @@ int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out, int16_t *pcm_
                        rows * (ctx->chans[last] + 1) * sizeof(float)))
             return 1;
     }
-    CK(ctx, out_conv_launch(vin, vin2, vin3, third, ctx->chans[last], ctx->output_conv.K, ctx->output_conv.raw, ctx->output_conv.bias,
+    CK(ctx, out_conv_launch(vin, vin2, vin3, vin16, third, ctx->chans[last], ctx->output_conv.K, ctx->output_conv.raw, ctx->output_conv.bias,
                             ctx->out_w_kc.empty() ? nullptr : ctx->out_w_kc.data(), ctx->out_b_host, 0.01f,
                             ctx->d_seg, ctx->d_tiles + (size_t)last * (ctx->cap_batch + 1), ctx->last_B, ctx->rates[last],
                             ctx->total_tiles[last], wav_out, pcm_out, ctx->stream));
@@ -1349,6 +1408,7 @@ int make_lane(zvx_ctx *parent)
     l->H16 = l->X16 = l->R16 = nullptr;
     l->U16 = nullptr; l->Y16[0] = l->Y16[1] = l->Y16[2] = nullptr; l->chain_elems = 0;
     l->stat_part = nullptr; l->stat_part_cap = 0; l->asr_mu = l->asr_rstd = nullptr;
+    l->S16[0] = l->S16[1] = nullptr;
     l->d_seg = l->d_tiles = l->d_wins = l->d_err = l->pin_tables = nullptr;
     l->pin_in_cap = l->pin_out_cap = 0;
     l->graphs.clear();           // the copies of the parent's graph handles are not the lane's to destroy
@@ -1455,6 +1515,7 @@ int zvx_create(zvx_ctx **out, const zvx_config *cfg, const zvx_tensor_desc *weig
     if (const char *e = getenv("ZVX_CONV_TMA")) ctx->conv_tma = atoi(e);
     if (const char *e = getenv("ZVX_MRF_F16_CHAIN")) ctx->mrf_f16_chain = atoi(e);
     if (const char *e = getenv("ZVX_FUSED_STATS")) ctx->fused_stats = atoi(e);
+    if (const char *e = getenv("ZVX_STAGE_HANDOFF")) ctx->stage_handoff = atoi(e);
     if (const char *e = getenv("ZVX_CONV_SMEM_KB")) ctx->conv_smem_kb = atoi(e);
     if (const char *e = getenv("ZVX_GRAPHS")) ctx->use_graphs = atoi(e);
     if (const char *e = getenv("ZVX_FORK_BRANCHES")) ctx->fork_branches = atoi(e);

@@ -69,7 +69,8 @@ cudaError_t cvt_f16_launch(const float *x, int ldx, int ch_off, int C, size_t ro
 // wav = tanh(conv_k(leaky_relu(x, slope)) + b), single output channel
 // w_host_kc: host copy of the weights as fp32 [K][C] (constant-bank fast path for C = 32, K = 7), may be null
 // x2 / x3 non-null: input = ((x + x2) + x3) * sum_scale (MRF branch average applied by the consumer)
-cudaError_t out_conv_launch(const float *x, const float *x2, const float *x3, float sum_scale, int C, int K, const __half *w_raw, const float *bias, const float *w_host_kc,
+// x16 non-null: the input arrives averaged, activated and rounded to fp16 (stage hand-off of the fused MRF kernel)
+cudaError_t out_conv_launch(const float *x, const float *x2, const float *x3, const __half *x16, float sum_scale, int C, int K, const __half *w_raw, const float *bias, const float *w_host_kc,
                             float bias_host, float slope, const int *seg_start, const int *tile_start, int B, int rate,
                             int total_tiles, float *wav, int16_t *pcm, cudaStream_t st);
 
