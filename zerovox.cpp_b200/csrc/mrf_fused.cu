@@ -100,13 +100,28 @@ __device__ __forceinline__ void tmem_st_16x256b_x4(uint32_t taddr, const uint32_
         : "memory");
 }
 
+// 16 lanes x 16 columns (column groups cg = 0..1)
+__device__ __forceinline__ void tmem_st_16x256b_x2(uint32_t taddr, const uint32_t (&r)[8])
+{
+    asm volatile("tcgen05.st.sync.aligned.16x256b.x2.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+                 "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+
 template <int CH, int NCOL>
 struct FCfg {
     using G = mrf::Geo<CH, NCOL>;
     static constexpr int EPI_WARPS = NCOL / 16;            // 64 columns per warp, 4 lane quarters
     static constexpr int EPI       = EPI_WARPS * 32;
-    static constexpr int THREADS   = EPI + 64;
+    // + one warpgroup: MMA warp, loader warp, two idle warps.  Registers are handed out per CTA in units of four
+    // warps, so the two idle warps cost nothing, and a complete warpgroup can give its registers away
+    // (setmaxnreg): the kernel is compiled for 96 (NCOL = 256) / 80 (NCOL = 128) registers per thread, the last
+    // warpgroup shrinks to REGS_AUX and the epilogue warpgroups grow to REGS_EPI --
+    // 640 x 96 = 512 x 112 + 128 x 32,  384 x 80 = 256 x 104 + 128 x 32.
+    static constexpr int THREADS   = EPI + 128;
     static constexpr int CTAS      = NCOL == 128 ? 2 : 1;
+    static constexpr int REGS_EPI  = NCOL == 128 ? 104 : 112;
+    static constexpr int REGS_AUX  = 32;
     static constexpr int TBL_WORDS = G::S * NCOL;
     // utterance tables (seg_start, win_start: 1 + B entries each) are copied to shared memory when the
     // batch is small enough; every window looks its utterance up in them
@@ -229,6 +244,7 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
     auto hcol = [&](int iter) { return (uint32_t)((iter & 1) ? NCOL : 0); };
 
     if (warp < EPI_WARPS) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(C::REGS_EPI));
         // =================== prologue + epilogues ===================
         const int quarter = warp & 3;
         const int colw    = (warp >> 2) * 64;          // this warp's 64 columns
@@ -254,58 +270,66 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
 #endif
         // y window -> tensor memory columns [ybase, ybase + NCOL) (fp32), lrelu(y) -> buffer 0 (fp16).
         // Uses table slot 1; does NOT arrive on act_ready.
-        auto prologue = [&](const Win &w, uint32_t ybase) {
-            if (w.interior && !(p.flags & 1)) {
-                // per 32-column half: 8 float4 loads per thread (its 4 channels x 8 columns), all in flight
-                // before the first use; a warp instruction covers 4 time steps x one 128-byte line
-                const float *yq = p.y_in + (w.row0 + (size_t)w.tw) * CH + c4;
-#pragma unroll 1
-                for (int hc = 0; hc < 2; ++hc) {
-                    const int col0 = colw + 32 * hc;
-                    const uint16_t *tb = tbl_s + sQ * NCOL + col0;
-                    float4 f[8];
-#ifdef ZVX_FUSED_PHASES
-                    if (dbg) c_l0 = clock64();
-#endif
+        // Interior windows, per 16-column quarter qc of this warp's 64 columns: 4 float4 loads per thread (its 4
+        // channels x 4 columns); a warp instruction covers 4 time steps x one 128-byte line.  The loads are software-
+        // pipelined: quarter 0 is requested by the caller one layer ahead (before the wait for the second-to-last
+        // conv, where these warps idle anyway), quarter q + 1 before quarter q is placed, so that no L2 round trip
+        // is exposed.
+        auto y_loads = [&](const Win &w, int qc, float4 (&f)[4]) {
+            const float *yq = p.y_in + (w.row0 + (size_t)w.tw) * CH + c4;
+            const int col0 = colw + 16 * qc;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int tau = S * (col0 + 8 * (i >> 1) + 2 * (lane & 3) + (i & 1)) + sQ;
-                        f[i] = tau < G::WP ? __ldg(reinterpret_cast<const float4 *>(yq + (size_t)tau * CH)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-#ifdef ZVX_FUSED_PHASES
-                    if (dbg) {
-                        asm volatile("" ::"f"(f[0].x), "f"(f[1].x), "f"(f[2].x), "f"(f[3].x), "f"(f[4].x), "f"(f[5].x), "f"(f[6].x), "f"(f[7].x) : "memory");
-                        const long long c = clock64();
-                        c_ld += c - c_l0;
-                        c_l0 = c;
-                    }
-#endif
+            for (int i = 0; i < 4; ++i) {
+                const int tau = S * (col0 + 8 * (i >> 1) + 2 * (lane & 3) + (i & 1)) + sQ;
+                f[i] = tau < G::WP ? __ldg(reinterpret_cast<const float4 *>(yq + (size_t)tau * CH)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        auto y_place = [&](int qc, const float4 (&f)[4], uint32_t ybase) {
+            const int col0 = colw + 16 * qc;
+            const uint16_t *tb = tbl_s + sQ * NCOL + col0;
 #pragma unroll
-                    for (int lh = 0; lh < 2; ++lh) {
-                        const int rb = quarter * 32 + lh * 16;
-                        uint32_t v[16];
+            for (int lh = 0; lh < 2; ++lh) {
+                const int rb = quarter * 32 + lh * 16;
+                uint32_t v[8];
 #pragma unroll
-                        for (int cg = 0; cg < 4; ++cg) {
-                            v[4 * cg + 0] = __float_as_uint(lh ? f[2 * cg].z : f[2 * cg].x);
-                            v[4 * cg + 1] = __float_as_uint(lh ? f[2 * cg + 1].z : f[2 * cg + 1].x);
-                            v[4 * cg + 2] = __float_as_uint(lh ? f[2 * cg].w : f[2 * cg].y);
-                            v[4 * cg + 3] = __float_as_uint(lh ? f[2 * cg + 1].w : f[2 * cg + 1].y);
-                        }
-                        tmem_st_16x256b_x4(tmem_base + ((uint32_t)rb << 16) + ybase + (uint32_t)col0, v);
-                        const uint32_t gbase = buf0 + (uint32_t)((rb % CH) >> 3) * LBO_B + (uint32_t)(mi & 1) * LBO_B;
-#pragma unroll
-                        for (int pr = 0; pr < 2; ++pr) {
-                            uint32_t h[4];
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const int i0 = 8 * pr + 2 * q;   // (cg = 2pr + q/2, row A/B = q & 1)
-                                h[q] = pack_h2(lrelu_max(__uint_as_float(v[i0]), p.in_slope), lrelu_max(__uint_as_float(v[i0 + 1]), p.in_slope));
-                            }
-                            const uint32_t e = tb[8 * (2 * pr + (mi >> 1)) + r8];
-                            stmatrix_x4_trans(gbase + e * 16u, h[0], h[1], h[2], h[3]);
-                        }
-                    }
+                for (int cg = 0; cg < 2; ++cg) {
+                    v[4 * cg + 0] = __float_as_uint(lh ? f[2 * cg].z : f[2 * cg].x);
+                    v[4 * cg + 1] = __float_as_uint(lh ? f[2 * cg + 1].z : f[2 * cg + 1].x);
+                    v[4 * cg + 2] = __float_as_uint(lh ? f[2 * cg].w : f[2 * cg].y);
+                    v[4 * cg + 3] = __float_as_uint(lh ? f[2 * cg + 1].w : f[2 * cg + 1].y);
                 }
+                tmem_st_16x256b_x2(tmem_base + ((uint32_t)rb << 16) + ybase + (uint32_t)col0, v);
+                const uint32_t gbase = buf0 + (uint32_t)((rb % CH) >> 3) * LBO_B + (uint32_t)(mi & 1) * LBO_B;
+                uint32_t h[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q)      // (cg = q / 2, row A/B = q & 1)
+                    h[q] = pack_h2(lrelu_max(__uint_as_float(v[2 * q]), p.in_slope), lrelu_max(__uint_as_float(v[2 * q + 1]), p.in_slope));
+                const uint32_t e = tb[8 * (mi >> 1) + r8];
+                stmatrix_x4_trans(gbase + e * 16u, h[0], h[1], h[2], h[3]);
+            }
+        };
+        auto prologue = [&](const Win &w, uint32_t ybase, bool preloaded, float4 (&f0)[4]) {
+            if (w.interior && !(p.flags & 1)) {
+#ifdef ZVX_FUSED_PHASES
+                if (dbg) c_l0 = clock64();
+#endif
+                if (!preloaded) y_loads(w, 0, f0);
+                float4 f1[4];
+                y_loads(w, 1, f1);
+#ifdef ZVX_FUSED_PHASES
+                if (dbg) {
+                    asm volatile("" ::"f"(f0[0].x), "f"(f0[1].x), "f"(f0[2].x), "f"(f0[3].x) : "memory");
+                    const long long c = clock64();
+                    c_ld += c - c_l0;
+                    c_l0 = c;
+                }
+#endif
+                y_place(0, f0, ybase);
+                y_loads(w, 2, f0);
+                y_place(1, f1, ybase);
+                y_loads(w, 3, f1);
+                y_place(2, f0, ybase);
+                y_place(3, f1, ybase);
             } else {
                 const float *yin = p.y_in + w.row0 * CH + gc;
                 const uint32_t *tb = p.tbl0 + s * NCOL;             // full entries (tau for the edge mask) from global
@@ -359,9 +383,12 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
         int iter = 0;
         int win = blockIdx.x;
         Win wnext = {0, 0, 0, false};
+        float4 ypre[4];                 // the next window's first 16-column quarter of y, requested one layer ahead
+        bool have_pre = false;
+        const bool preload = !(p.flags & 4);
         if (win < nwin) {
             wnext = window(win);
-            prologue(wnext, ycol(0));
+            prologue(wnext, ycol(0), false, ypre);
             publish();
         }
 #ifdef ZVX_FUSED_PHASES
@@ -379,13 +406,19 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
                 const bool last = l == nl - 1;
                 const uint32_t acc_col = L.accumulate ? ycol(iter) : hcol(iter);
                 const uint32_t gl = (uint32_t)(iter * nl + l);      // completions of acc_full before this one
+                if (has_next && l == nl - 2) {
+                    // the next window's coordinates, and the first half of its y on the way while these warps
+                    // wait for this conv and drain it
+                    wnext = window(win + (int)gridDim.x);
+                    have_pre = preload && wnext.interior && !(p.flags & 1);
+                    if (have_pre) y_loads(wnext, 0, ypre);
+                }
                 if (last && has_next) {
                     // While the last conv of this window accumulates into y, bring in the NEXT window: its
                     // y goes to the (now idle) conv1 accumulator columns, lrelu(y) to buffer 0 (the last
                     // layer reads buffer 1; nlayers is even).  Published after this window's y is read.
                     if (dbg) c_a = clock64();
-                    wnext = window(win + (int)gridDim.x);
-                    prologue(wnext, hcol(iter));
+                    prologue(wnext, hcol(iter), have_pre, ypre);
                     if (dbg) c_pro += clock64() - c_a;
                 }
                 if (dbg) c_a = clock64();
@@ -544,7 +577,10 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
             printf("mrf_fused CH=%d NCOL=%d k=%d nl=%d windows=%d: total %lld  prologue %lld  wait_mma %lld  drain %lld  final %lld  | prologue: loads %lld  wait_st+fence %lld  first prologue (tensor pipe idle) %lld of which loads %lld (cycles, CTA 0 warp 0)\n",
                    CH, NCOL, p.L[0].k, nl, iter, clock64() - c_t0, c_pro, c_wait, c_drain, c_final, c_ld, c_st, c_first, c_ld_first);
 #endif
-    } else if (warp == EPI_WARPS) {
+    } else {
+    // one instruction for the whole last warpgroup (.aligned), then the roles split
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::REGS_AUX));
+    if (warp == EPI_WARPS) {
         // =================== MMA issuer ===================
         const uint32_t leader = elect_one();
         const uint32_t idesc  = make_idesc_mn(128, NCOL);
@@ -603,7 +639,7 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
         }
         if (dbg && lane == 0)
             printf("mrf_fused MMA warp: total %lld  wait_activations %lld  wait_weights %lld (cycles, CTA 0)\n", clock64() - c_t0, c_act, c_w);
-    } else {
+    } else if (warp == EPI_WARPS + 1) {
         // =================== weight loader + L2 prefetcher ===================
         int it = 0;
 #pragma unroll 1
@@ -644,6 +680,7 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
             __syncwarp();
         }
     }
+    }   // last warpgroup (its other two warps idle: they only exist so that the warpgroup is complete)
 
     tc_fence_before_sync();
     __syncthreads();
