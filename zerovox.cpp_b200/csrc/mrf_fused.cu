@@ -276,12 +276,29 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
         // conv, where these warps idle anyway), quarter q + 1 before quarter q is placed, so that no L2 round trip
         // is exposed.
         auto y_loads = [&](const Win &w, int qc, float4 (&f)[4]) {
-            const float *yq = p.y_in + (w.row0 + (size_t)w.tw) * CH + c4;
+            const float *yq = p.y_in + ((ptrdiff_t)w.row0 + w.tw) * CH + c4;
             const int col0 = colw + 16 * qc;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int tau = S * (col0 + 8 * (i >> 1) + 2 * (lane & 3) + (i & 1)) + sQ;
-                f[i] = tau < G::WP ? __ldg(reinterpret_cast<const float4 *>(yq + (size_t)tau * CH)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const bool ok = tau < G::WP && (unsigned)(w.tw + tau) < (unsigned)w.T;      // inside the window and the utterance
+                f[i] = ok ? __ldg(reinterpret_cast<const float4 *>(yq + (ptrdiff_t)tau * CH)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        // Windows that touch an utterance edge take the same data path; afterwards the rows of the time steps outside
+        // the utterance are overwritten with zeros (the convolution's zero padding, SURVEY.md H-d): typically a few
+        // hundred 16-byte stores per CTA instead of a scalar pass over the whole window.  buf_off: the buffer just
+        // written, d: the dilation its layout belongs to.
+        auto zero_outside = [&](uint32_t buf_off, int d, int tw_, int T_) {
+            const int lo = max(0, -tw_), hi = min(G::WP, T_ - tw_);         // time steps [lo, hi) of the window are inside
+            const int ninv = lo + (G::WP - hi);
+            asm volatile("bar.sync 1, %0;" ::"n"(C::EPI) : "memory");          // every row has been written by its owner
+            for (int i = tid; i < ninv * G::GROUPS; i += C::EPI) {
+                const int g = i % G::GROUPS;
+                int tau = i / G::GROUPS;
+                if (tau >= lo) tau += hi - lo;
+                const int unit = mrf::dest_unit(tau, d, G::WP, S, G::GROUPS, NCOL);
+                *reinterpret_cast<uint4 *>(smem + buf_off + (size_t)g * LBO_B + (size_t)unit * 16) = make_uint4(0u, 0u, 0u, 0u);
             }
         };
         auto y_place = [&](int qc, const float4 (&f)[4], uint32_t ybase) {
@@ -309,7 +326,7 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
             }
         };
         auto prologue = [&](const Win &w, uint32_t ybase, bool preloaded, float4 (&f0)[4]) {
-            if (w.interior && !(p.flags & 1)) {
+            if (!(p.flags & 1)) {
 #ifdef ZVX_FUSED_PHASES
                 if (dbg) c_l0 = clock64();
 #endif
@@ -330,6 +347,7 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
                 y_loads(w, 3, f1);
                 y_place(2, f0, ybase);
                 y_place(3, f1, ybase);
+                if (!w.interior) zero_outside(OFF_BUF0, p.L[0].d, w.tw, w.T);
             } else {
                 const float *yin = p.y_in + w.row0 * CH + gc;
                 const uint32_t *tb = p.tbl0 + s * NCOL;             // full entries (tau for the edge mask) from global
@@ -393,6 +411,10 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
         }
 #ifdef ZVX_FUSED_PHASES
         const long long c_first = dbg ? clock64() - c_t0 : 0, c_ld_first = c_ld;
+        // flags bit 3: every CTA reports its run time and how many of its windows touched an utterance edge
+        const bool dbg_cta = (p.flags & 8) && warp == 0 && lane == 0;
+        const long long c_cta0 = dbg_cta ? clock64() : 0;
+        int n_edge = 0;
 #endif
 #pragma unroll 1
         for (; win < nwin; win += gridDim.x, ++iter) {
@@ -400,6 +422,9 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
             const int tw = w.tw, T = w.T;
             const bool interior = w.interior;
             const bool has_next = win + (int)gridDim.x < nwin;
+#ifdef ZVX_FUSED_PHASES
+            n_edge += interior ? 0 : 1;
+#endif
 #pragma unroll 1
             for (int l = 0; l < nl; ++l) {
                 const mrf::Layer &L = p.L[l];
@@ -410,7 +435,7 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
                     // the next window's coordinates, and the first half of its y on the way while these warps
                     // wait for this conv and drain it
                     wnext = window(win + (int)gridDim.x);
-                    have_pre = preload && wnext.interior && !(p.flags & 1);
+                    have_pre = preload && !(p.flags & 1);
                     if (have_pre) y_loads(wnext, 0, ypre);
                 }
                 if (last && has_next) {
@@ -428,7 +453,7 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
                 if (!last) {
                     const uint32_t obuf_off = (l & 1) ? OFF_BUF0 : OFF_BUF1;
                     const float slope = L.out_slope;
-                    if (interior) {
+                    if (!(p.flags & 1)) {
 #pragma unroll 1
                         for (int lh = 0; lh < 2; ++lh) {
                             const int rb  = quarter * 32 + lh * 16;
@@ -452,15 +477,21 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
                                 const uint32_t e = tb[8 * (2 * pr + (mi >> 1)) + r8];
                                 stmatrix_x4_trans(gbase + e * 16u, f[0], f[1], f[2], f[3]);
                             }
-                            if (lh == 0) {
+                            if (lh == 0 && interior) {
                                 // rows [rb, rb + 16) of every lane quarter = the even K-steps of the next layer's
                                 // operand: its MMAs over those start while the odd half is still being drained
                                 fence_proxy_async_smem();
                                 publish_half();
                             }
                         }
-                        fence_proxy_async_smem();
-                        publish_rest();
+                        if (interior) {
+                            fence_proxy_async_smem();
+                            publish_rest();
+                        } else {
+                            zero_outside(obuf_off, p.L[l + 1].d, tw, T);
+                            fence_proxy_async_smem();
+                            publish();
+                        }
                     } else {
                         const float bias = __ldg(L.bias + oc);
                         const uint32_t *tb = L.tbl + s * NCOL;              // full entries from global
@@ -487,7 +518,7 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
                     // final: y (+ running branch sum) (* 1/num_blocks) -> global fp32.  Both 32-column
                     // batches are pulled out of tensor memory first, then the next window is published
                     // (its first conv may overwrite these columns), then the global traffic follows.
-                    if (interior) {
+                    if (!(p.flags & 1)) {
                         // fragment layout again: this thread's 4 adjacent channels x 16 columns leave as float4
                         uint32_t r0[32], r1[32];
                         tmem_ld_16x256b_x8_nowait(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc_col + (uint32_t)colw, r0);
@@ -496,7 +527,7 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
                         const float4 b4 = make_float4(__ldg(L.bias + rq), __ldg(L.bias + rq + 8), __ldg(L.bias + rq + 16), __ldg(L.bias + rq + 24));
                         tmem_wait_ld();
                         if (has_next) publish();
-                        const size_t base = (w.row0 + (size_t)tw) * CH + c4;
+                        const ptrdiff_t base = ((ptrdiff_t)w.row0 + tw) * CH + c4;
                         float *oq = p.out ? p.out + base : nullptr;
                         uint16_t *hq = p.out16 ? p.out16 + base : nullptr;
                         const float *aq = p.acc_in ? p.acc_in + base : nullptr;
@@ -504,7 +535,7 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
                             const int tau = S * (colw + 8 * (i >> 1) + 2 * (lane & 3) + (i & 1)) + sQ;
-                            if (tau >= p.halo && tau < p.halo + p.valid) {
+                            if (tau >= p.halo && tau < p.halo + p.valid && tw + tau < T) {
                                 const int i0 = 4 * (i >> 1) + (i & 1);
                                 float4 v = make_float4(__fadd_rn(__uint_as_float(r0[i0]), b4.x), __fadd_rn(__uint_as_float(r0[i0 + 2]), b4.y),
                                                        __fadd_rn(__uint_as_float(r1[i0]), b4.z), __fadd_rn(__uint_as_float(r1[i0 + 2]), b4.w));
@@ -573,6 +604,7 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
             }
         }
 #ifdef ZVX_FUSED_PHASES
+        if (dbg_cta) printf("mrf_cta CH=%d NCOL=%d k=%d nl=%d cta=%d windows=%d edge=%d cycles=%lld\n", CH, NCOL, p.L[0].k, nl, (int)blockIdx.x, iter, n_edge, clock64() - c_cta0);
         if (dbg && lane == 0)
             printf("mrf_fused CH=%d NCOL=%d k=%d nl=%d windows=%d: total %lld  prologue %lld  wait_mma %lld  drain %lld  final %lld  | prologue: loads %lld  wait_st+fence %lld  first prologue (tensor pipe idle) %lld of which loads %lld (cycles, CTA 0 warp 0)\n",
                    CH, NCOL, p.L[0].k, nl, iter, clock64() - c_t0, c_pro, c_wait, c_drain, c_final, c_ld, c_st, c_first, c_ld_first);
@@ -601,6 +633,18 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
                 const uint32_t lbo_a = (uint32_t)mrf::tap_blocks(k, S) * CH * 16u;
                 const uint32_t ibuf  = (l & 1) ? buf1 : buf0;
                 const uint32_t dcol  = tmem_base + (L.accumulate ? ycol(iter) : hcol(iter));
+                // Step j = 0 of every K-step: the A window starts at tap block k + S - 2 and moves down one block
+                // per step; the B operand starts at position -c = sub-buffer q0, row ro0 and moves up one position
+                // per step (next sub-buffer; after the last one, the first sub-buffer one row further).  Only the
+                // 14-bit start-address fields of the two descriptors change, by constants: no per-step index
+                // arithmetic in the issuing thread (it was the limit: 140-215 cycles per MMA instead of 128).
+                int q0, ro0;
+                mrf::b_step(k, S, 0, q0, ro0);
+                const uint32_t a_fix = ((lbo_a >> 4) & 0x3FFFu) << 16;
+                const uint32_t b_fix = ((LBO_B >> 4) & 0x3FFFu) << 16;
+                const uint32_t a_off0 = (uint32_t)(k + S - 2) * (CH * 16u);
+                const uint32_t b_off0 = (uint32_t)q0 * G::SUB + (uint32_t)(ro0 * 16) + (uint32_t)mrf::GUARD * 16u;
+                constexpr uint64_t DESC_HI = ((uint64_t)(128u >> 4) | ((uint64_t)1 << 14)) << 32;   // SBO = 128 B, version 1
                 // K-steps in the order even, then odd: the epilogue warps publish the even ones (first 16-lane
                 // half of every lane quarter) before they drain the odd ones
 #pragma unroll 1
@@ -619,15 +663,17 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
                     tc_fence_after_sync();
                     if (dbg) c_w += clock64() - c_a;
                     if (leader) {
-                        const uint32_t a_slot = ring + (uint32_t)slot * slot_bytes;
-                        const uint32_t b_c    = ibuf + (uint32_t)(2 * c) * LBO_B + (uint32_t)mrf::GUARD * 16u;
+                        uint32_t a_lo = (((ring + (uint32_t)slot * slot_bytes + a_off0) & 0x3FFFFu) >> 4) | a_fix;
+                        uint32_t b_lo = (((ibuf + (uint32_t)(2 * c) * LBO_B + b_off0) & 0x3FFFFu) >> 4) | b_fix;
+                        uint32_t acc = (L.accumulate || ci > 0) ? 1u : 0u;
+                        int q = q0;
 #pragma unroll 1
                         for (int j = 0; j < nj; ++j) {
-                            int q, ro;
-                            mrf::b_step(k, S, j, q, ro);
-                            const uint64_t adesc = make_smem_desc(a_slot + (uint32_t)mrf::a_block(k, S, j) * (CH * 16u), lbo_a, 128u);
-                            const uint64_t bdesc = make_smem_desc(b_c + (uint32_t)q * G::SUB + (uint32_t)(ro * 16), LBO_B, 128u);
-                            umma_f16(dcol, adesc, bdesc, idesc, (L.accumulate || ci > 0 || j > 0) ? 1u : 0u);
+                            umma_f16(dcol, DESC_HI | a_lo, DESC_HI | b_lo, idesc, acc);
+                            acc = 1u;
+                            a_lo -= (uint32_t)CH;                           // one tap block = CH rows of 16 bytes
+                            b_lo += (uint32_t)(G::SUB >> 4);
+                            if (++q == S) { q = 0; b_lo -= (uint32_t)(S * (G::SUB >> 4) - 1); }
                         }
                         umma_commit(smem_u32(w_empty + slot));
                     }
