@@ -446,6 +446,10 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
                     prologue(wnext, hcol(iter), have_pre, ypre);
                     if (dbg) c_pro += clock64() - c_a;
                 }
+                // this thread's four biases of the layer (rows g, g+8 of both 16-lane halves of its lane quarter),
+                // requested before the wait: their L2 round trip used to sit between the wait and the first add
+                const int rq = (quarter * 32) % CH + (lane >> 2);
+                const float4 b4 = make_float4(__ldg(L.bias + rq), __ldg(L.bias + rq + 8), __ldg(L.bias + rq + 16), __ldg(L.bias + rq + 24));
                 if (dbg) c_a = clock64();
                 mbar_wait(smem_u32(acc_full), gl & 1u, p.err_flag);
                 tc_fence_after_sync();
@@ -454,12 +458,11 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
                     const uint32_t obuf_off = (l & 1) ? OFF_BUF0 : OFF_BUF1;
                     const float slope = L.out_slope;
                     if (!(p.flags & 1)) {
-#pragma unroll 1
+#pragma unroll
                         for (int lh = 0; lh < 2; ++lh) {
                             const int rb  = quarter * 32 + lh * 16;
                             const int sA  = rb / CH;
-                            const int ocA = rb % CH + (lane >> 2);
-                            const float bA = __ldg(L.bias + ocA), bB = __ldg(L.bias + ocA + 8);
+                            const float bA = lh ? b4.z : b4.x, bB = lh ? b4.w : b4.y;
                             const uint16_t *tb = tbl_s + (l + 1) * TBL_WORDS + sA * NCOL + colw;
                             uint32_t r[32];
                             tmem_ld_16x256b_x8(tmem_base + ((uint32_t)rb << 16) + acc_col + (uint32_t)colw, r);
@@ -523,8 +526,6 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
                         uint32_t r0[32], r1[32];
                         tmem_ld_16x256b_x8_nowait(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc_col + (uint32_t)colw, r0);
                         tmem_ld_16x256b_x8_nowait(tmem_base + ((uint32_t)(quarter * 32 + 16) << 16) + acc_col + (uint32_t)colw, r1);
-                        const int rq = (quarter * 32) % CH + (lane >> 2);
-                        const float4 b4 = make_float4(__ldg(L.bias + rq), __ldg(L.bias + rq + 8), __ldg(L.bias + rq + 16), __ldg(L.bias + rq + 24));
                         tmem_wait_ld();
                         if (has_next) publish();
                         const ptrdiff_t base = ((ptrdiff_t)w.row0 + tw) * CH + c4;
