@@ -76,8 +76,11 @@ def main():
             step(ctx, False)
     acc = [dict() for _ in sides]
     keys = []
-    for _ in range(rounds):
-        for si, (_, ctx) in enumerate(sides):
+    for rnd in range(rounds):
+        order = list(range(len(sides)))
+        order = order[rnd % len(sides):] + order[:rnd % len(sides)]      # rotate: no side always runs first / last
+        for si in order:
+            ctx = sides[si][1]
             per = {}
             for kind, stage, flops, nbytes, ms in step(ctx, True):
                 k = f"{kind}:st={stage}"
@@ -90,7 +93,9 @@ def main():
     print(f"{'median ms over ' + str(rounds) + ' rounds':26s}" + "".join(f"{n:>12s}" for n, _ in sides) + "".join(f"{n + '/' + sides[0][0]:>14s}" for n, _ in sides[1:]))
     for k in keys + ["total"]:
         med = [statistics.median(a.get(k, [0.0])) for a in acc]
-        print(f"{k:26s}" + "".join(f"{m:12.4f}" for m in med) + "".join(f"{(m / med[0] if med[0] else 0):14.3f}" for m in med[1:]))
+        # ratio: median over rounds of the per-round ratio (both sides measured back to back in that round)
+        rat = [statistics.median([x / y for x, y in zip(a.get(k, [0.0]), acc[0].get(k, [1.0])) if y]) for a in acc[1:]]
+        print(f"{k:26s}" + "".join(f"{m:12.4f}" for m in med) + "".join(f"{r:14.3f}" for r in rat))
 
 
 if __name__ == "__main__":

@@ -698,8 +698,13 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
                 const Win wn = window(nw);
                 const int lo = max(wn.tw, 0), hi = min(wn.tw + G::WP, wn.T);
                 const char *ybase = reinterpret_cast<const char *>(p.y_in + (wn.row0 + (size_t)lo) * CH);
-                const int nlines = (hi - lo) * (CH * 4) / 128;
-                for (int i = lane; i < nlines; i += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(ybase + (size_t)i * 128));
+                if (p.prefetch == 2) {
+                    // the window's rows are contiguous: one bulk prefetch request
+                    if (lane == 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ybase), "r"((uint32_t)((hi - lo) * (CH * 4))) : "memory");
+                } else {
+                    const int nlines = (hi - lo) * (CH * 4) / 128;
+                    for (int i = lane; i < nlines; i += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(ybase + (size_t)i * 128));
+                }
                 for (int k = 0; k < 2; ++k) {
                     const float *acc = k ? p.acc_in2 : p.acc_in;
                     if (!acc) continue;

@@ -95,7 +95,7 @@ struct zvx_ctx {
     std::vector<WinCfg> wincfg;                   // window tilings used by the fused chains
     std::map<std::vector<int>, const uint32_t *> tbl_cache;
     int use_fused = 1;
-    int fused_prefetch = 1;
+    int fused_prefetch = -1;                      // -1: automatic (measured: pays only at CH = 32), 0 / 1 / 2 (bulk request): ZVX_FUSED_PREFETCH
     int fused_persistent = 1;
     int fused_flags = 0;
     int conv_persistent = 1;
@@ -1214,7 +1214,7 @@ int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out, int16_t *pcm_
                     fp.win_start = ctx->d_wins + (size_t)fc.wincfg * (ctx->cap_batch + 1);
                     fp.B = ctx->last_B;
                     fp.ncol = fb.ncol;
-                    fp.prefetch = ctx->fused_prefetch;
+                    fp.prefetch = ctx->fused_prefetch >= 0 ? ctx->fused_prefetch : (fb.CH == 32 ? 1 : 0);
                     fp.flags = ctx->fused_flags;
                     fp.resident_ctas = ctx->fused_persistent ? ctx->num_sms * (fb.ncol == 128 ? 2 : 1) : 0;
                     fp.rate = ctx->rates[i + 1];
@@ -1278,7 +1278,7 @@ int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out, int16_t *pcm_
             fp.win_start = ctx->d_wins + (size_t)fc.wincfg * (ctx->cap_batch + 1);
             fp.B = ctx->last_B;
             fp.ncol = deferred_ncol;
-            fp.prefetch = ctx->fused_prefetch;
+            fp.prefetch = ctx->fused_prefetch >= 0 ? ctx->fused_prefetch : (deferred_CH == 32 ? 1 : 0);
             fp.flags = ctx->fused_flags;
             fp.resident_ctas = ctx->fused_persistent ? ctx->num_sms * (deferred_ncol == 128 ? 2 : 1) : 0;
             fp.rate = ctx->rates[i + 1];
