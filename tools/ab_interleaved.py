@@ -88,10 +88,19 @@ def main():
                 if k not in keys:
                     keys.append(k)
             per["total"] = sum(per.values())
+            # whole step, unprofiled, host clock around a synchronous call (kernels of forked streams overlap: the sum
+            # of per-launch times above counts overlapped time twice)
+            import time
+            ts = []
+            for _ in range(2):
+                t0 = time.perf_counter()
+                step(ctx, False)
+                ts.append((time.perf_counter() - t0) * 1e3)
+            per["step (host clock)"] = min(ts)
             for k, v in per.items():
                 acc[si].setdefault(k, []).append(v)
     print(f"{'median ms over ' + str(rounds) + ' rounds':26s}" + "".join(f"{n:>12s}" for n, _ in sides) + "".join(f"{n + '/' + sides[0][0]:>14s}" for n, _ in sides[1:]))
-    for k in keys + ["total"]:
+    for k in keys + ["total", "step (host clock)"]:
         med = [statistics.median(a.get(k, [0.0])) for a in acc]
         # ratio: median over rounds of the per-round ratio (both sides measured back to back in that round)
         rat = [statistics.median([x / y for x, y in zip(a.get(k, [0.0]), acc[0].get(k, [1.0])) if y]) for a in acc[1:]]

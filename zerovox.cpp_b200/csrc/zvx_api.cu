@@ -97,6 +97,7 @@ struct zvx_ctx {
     int use_fused = 1;
     int fused_prefetch = -1;                      // -1: automatic (measured: pays only at CH = 32), 0 / 1 / 2 (bulk request): ZVX_FUSED_PREFETCH
     int fused_persistent = 1;
+    int fused_ncol128_ctas = 2;                   // CTAs per SM of a 128-column launch (1: leaves room for another launch's CTA)
     int fused_flags = 0;
     int conv_persistent = 1;
     float *feat = nullptr; int2 *feat_tab = nullptr; size_t feat_cap = 0, feat_tab_cap = 0;   // length regulator staging
@@ -479,7 +480,7 @@ int build_fused(zvx_ctx *ctx, HostW &hw)
         // price of a larger halo fraction; worth it where the MMA phase per layer is short (CH = 32)
         // columns per window, chosen per residual block below: 128 -> two CTAs per SM (one's epilogue
         // overlaps the other's MMAs) at the price of a larger halo fraction; pays off only for short kernels
-        int ncol128_maxk = CH == 32 ? 3 : 0;      // measured on B200 (profiles/): CH = 32, k = 3 only
+        int ncol128_maxk = 0;                     // measured on B200 (profiles/r02_ab_small_experiments.txt): no longer pays anywhere
         {
             char key[40];
             snprintf(key, sizeof key, "ZVX_NCOL128_MAXK_%d", CH);
@@ -1216,7 +1217,7 @@ int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out, int16_t *pcm_
                     fp.ncol = fb.ncol;
                     fp.prefetch = ctx->fused_prefetch >= 0 ? ctx->fused_prefetch : (fb.CH == 32 ? 1 : 0);
                     fp.flags = ctx->fused_flags;
-                    fp.resident_ctas = ctx->fused_persistent ? ctx->num_sms * (fb.ncol == 128 ? 2 : 1) : 0;
+                    fp.resident_ctas = ctx->fused_persistent ? ctx->num_sms * (fb.ncol == 128 ? ctx->fused_ncol128_ctas : 1) : 0;
                     fp.rate = ctx->rates[i + 1];
                     fp.halo = fc.halo;
                     fp.valid = fc.valid;
@@ -1280,7 +1281,7 @@ int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out, int16_t *pcm_
             fp.ncol = deferred_ncol;
             fp.prefetch = ctx->fused_prefetch >= 0 ? ctx->fused_prefetch : (deferred_CH == 32 ? 1 : 0);
             fp.flags = ctx->fused_flags;
-            fp.resident_ctas = ctx->fused_persistent ? ctx->num_sms * (deferred_ncol == 128 ? 2 : 1) : 0;
+            fp.resident_ctas = ctx->fused_persistent ? ctx->num_sms * (deferred_ncol == 128 ? ctx->fused_ncol128_ctas : 1) : 0;
             fp.rate = ctx->rates[i + 1];
             fp.halo = fc.halo;
             fp.valid = fc.valid;
@@ -1505,6 +1506,7 @@ int zvx_create(zvx_ctx **out, const zvx_config *cfg, const zvx_tensor_desc *weig
     ctx->device = cfg->device;
     if (const char *e = getenv("ZVX_FUSED_MIN_EFF")) ctx->fused_min_eff = atof(e);
     if (const char *e = getenv("ZVX_FUSED_PREFETCH")) ctx->fused_prefetch = atoi(e);
+    if (const char *e = getenv("ZVX_NCOL128_CTAS")) ctx->fused_ncol128_ctas = atoi(e);
     if (const char *e = getenv("ZVX_FUSED_PERSISTENT")) ctx->fused_persistent = atoi(e);
     if (const char *e = getenv("ZVX_FUSED_FLAGS")) ctx->fused_flags = atoi(e);
     if (const char *e = getenv("ZVX_E2E_CHUNKS")) ctx->e2e_chunks = std::max(1, atoi(e));
