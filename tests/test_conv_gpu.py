@@ -114,3 +114,24 @@ def test_utterance_edges_are_zero_padded_independently(ctx):
         single = ctx.test_conv([r], x[o:o + r], w, dilation=5, pad=25, pro_mode=2, pro_slope=0.1)
         assert np.array_equal(single, got[o:o + r])
         o += r
+
+
+def test_cta_pair_kernel_equals_single_cta_kernel(zvx, weights, monkeypatch):
+    """ZVX_CONV_PAIR=1: the one-tile kernel as tcgen05 CTA pairs (.cta_group::2, M = 256, half a weight stage per SM).  Same
+    K order per accumulator, so the result must equal the single-CTA kernel bit for bit -- ragged batch, odd tile count
+    (the padding CTA of the last pair stores nothing), partial last K-chunk (1056 = 16 x 64 + 32)."""
+    from zerovox_cpp_b200 import capi
+    rng = np.random.default_rng(11)
+    rows, c, k = [300, 129, 77], 1056, 3
+    x = rng.standard_normal((sum(rows), c)).astype(np.float16)
+    w = (rng.standard_normal((c, c, k)) / np.sqrt(c * k)).astype(np.float16)
+    b = (rng.standard_normal(c) * 0.1).astype(F32)
+    outs = []
+    for pair in ("0", "1"):
+        monkeypatch.setenv("ZVX_CONV_PAIR", pair)
+        cx = capi.Context(weights, device=0)          # the switch is read at zvx_create
+        outs.append(cx.test_conv(rows, x, w, bias=b, pad=1, pro_mode=0))
+        cx.close()
+    want = _ref(x.astype(F32), w, b, 1, 1, rows)
+    assert np.abs(outs[0] - want).max() <= 5e-5
+    assert np.array_equal(outs[0], outs[1])

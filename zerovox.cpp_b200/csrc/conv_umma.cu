@@ -42,7 +42,7 @@ constexpr int KCHUNK      = 64;
 constexpr int MAX_MT      = 2;
 constexpr int MAX_A_STAGES = 4;
 constexpr int MAX_B_STAGES = 8;
-constexpr int SMEM_HEADER  = 256;
+constexpr int SMEM_HEADER  = 384;
 
 __device__ __forceinline__ uint32_t make_idesc(int N) { return make_idesc_mn(TILE_M, N); }
 
@@ -348,12 +348,29 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams &p, uint32_t trow
 }
 
 // ------------------------------------------------------------------ the kernel
-template <int MODE, int MT>
-__global__ void __launch_bounds__(128 * MT + 64) conv_umma_kernel(const ConvParams p, const __grid_constant__ CUtensorMap a_map)
+// PAIR (PRO_F16 operands staged by TMA, MT = 1): the two CTAs of a cluster of 2 form a tcgen05 CTA pair.  CTA rank 0
+// issues ONE stream of M = 256 MMAs (.cta_group::2): rows 0-127 are its own time tile, rows 128-255 the peer's, and every
+// SM holds -- and fetches from L2 -- only HALF of each weight stage (its NC / 2 output channels; the hardware exchanges
+// the halves between the two SMs).  The one-tile kernel is bound by the weight stream (each CTA re-reads the conv's
+// whole N-chunk of weights for 128 rows: L2 -> SM traffic and the shared-memory writes of the stages); the pair halves
+// both per SM.  Hand-offs: each CTA's TMA / weight copies complete on its own barriers; the peer forwards "my stage has
+// landed" to barriers of rank 0 (a_peer / b_peer), rank 0's tcgen05.commit multicasts "stage free" / "accumulator
+// complete" to both CTAs.
+// threads of a one-tile CTA: 4 MT producer / epilogue warps, MMA warp, loader warp and (MT = 1) four more epilogue warps --
+// the epilogue is a third of a CTA's life, and a second warp per tensor-memory lane quarter takes every other 32-column pass
+constexpr int conv_threads(int MT) { return 128 * MT + 64 + (MT == 1 ? 128 : 0); }
+
+template <int MODE, int MT, bool PAIR = false>
+__global__ void __launch_bounds__(conv_threads(MT)) conv_umma_kernel(const ConvParams p, const __grid_constant__ CUtensorMap a_map)
 {
+    static_assert(!PAIR || (MT == 1 && MODE == PRO_F16), "CTA pairs: one M-tile per CTA, TMA-staged fp16 operand");
     constexpr int N_PRODUCERS = 128 * MT;
     constexpr int MMA_WARP    = 4 * MT;
     constexpr int ROWS_CTA    = TILE_M * MT;
+    // warps MMA_WARP + 2 .. + 5, when the launch has them (ConvParams::epi8): epilogue only
+    const bool EXTRA_EPI      = MT == 1 && blockDim.x > (unsigned)(N_PRODUCERS + 64);
+    const int N_EPI           = N_PRODUCERS + (EXTRA_EPI ? 128 : 0);
+    const int EPI_STEP        = EXTRA_EPI ? 2 : 1;
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t *bars       = reinterpret_cast<uint64_t *>(smem);
     uint64_t *a_full     = bars;                                  // [MAX_A_STAGES]
@@ -362,7 +379,9 @@ __global__ void __launch_bounds__(128 * MT + 64) conv_umma_kernel(const ConvPara
     uint64_t *b_empty    = bars + 2 * MAX_A_STAGES + MAX_B_STAGES;
     uint64_t *acc_full   = bars + 2 * MAX_A_STAGES + 2 * MAX_B_STAGES;
     uint64_t *a_land     = acc_full + 1;                            // [MAX_A_STAGES] TMA mode: the box of a stage has landed
-    uint32_t *tmem_slot  = reinterpret_cast<uint32_t *>(smem + 240);
+    uint64_t *a_peer     = a_land + MAX_A_STAGES;                   // [MAX_A_STAGES] pair, rank 0: the peer's A stage is ready
+    uint64_t *b_peer     = a_peer + MAX_A_STAGES;                   // [MAX_B_STAGES] pair, rank 0: the peer's weight half has landed
+    uint32_t *tmem_slot  = reinterpret_cast<uint32_t *>(smem + 336);
 
     const int tid  = threadIdx.x;
     const int warp = tid >> 5;
@@ -375,19 +394,21 @@ __global__ void __launch_bounds__(128 * MT + 64) conv_umma_kernel(const ConvPara
     const int nkc    = (Cin + KCHUNK - 1) / KCHUNK;
     const uint32_t lbo_a         = (uint32_t)p.a_rows * 16u;
     const uint32_t a_stage_bytes = (uint32_t)(kc_max >> 3) * lbo_a;
-    const uint32_t lbo_b         = (uint32_t)NC * 16u;
-    const uint32_t b_stage_bytes = (uint32_t)kc_max * NC * 2u;
+    const int NB                 = PAIR ? NC / 2 : NC;            // weight rows (output channels) held by this CTA
+    const uint32_t lbo_b         = (uint32_t)NB * 16u;
+    const uint32_t b_stage_bytes = (uint32_t)kc_max * NB * 2u;
     const uint32_t smem_base     = smem_u32(smem);
     const uint32_t a_base        = smem_base + SMEM_HEADER;
     const uint32_t b_base        = a_base + p.a_stages * a_stage_bytes;
-    const bool tma = MODE == PRO_F16 && p.use_tma;
+    const bool tma = PAIR || (MODE == PRO_F16 && p.use_tma);
 
     // ---- thread-block cluster: CL CTAs = CL time tiles of the same N-chunk share every weight stage.  Each CTA fetches
     //      1/CL of a stage and multicasts it to all of them, so the L2 -> SM weight traffic (the bound of these kernels:
     //      a 128-row tile uses every weight byte once) drops by CL.  CTAs that pad the grid recompute the last tile and
     //      store nothing: they must keep consuming the shared stages. ----
-    const int CL         = p.cluster;
-    const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
+    const int CL         = PAIR ? 1 : p.cluster;
+    const bool clustered = PAIR || CL > 1;
+    const uint32_t crank = clustered ? cluster_ctarank() : 0u;
     const uint16_t cmask = (uint16_t)((1u << CL) - 1u);
     const bool live      = (int)blockIdx.x < p.n_tiles;
 
@@ -412,12 +433,19 @@ __global__ void __launch_bounds__(128 * MT + 64) conv_umma_kernel(const ConvPara
             mbar_init(smem_u32(b_full + s), 1);
             mbar_init(smem_u32(b_empty + s), (uint32_t)CL);       // a stage is free when every CTA of the cluster has used it
         }
+        if (PAIR) {
+            for (int s = 0; s < p.a_stages; ++s) mbar_init(smem_u32(a_peer + s), 1);
+            for (int s = 0; s < p.b_stages; ++s) mbar_init(smem_u32(b_peer + s), 1);
+        }
         mbar_init(smem_u32(acc_full), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == MMA_WARP) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
+    if (warp == MMA_WARP) {
+        if (PAIR) tmem_alloc2(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
+        else tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
+    }
     tc_fence_before_sync();
-    if (CL > 1) cluster_sync_all(); else __syncthreads();        // peers' barriers are initialised before anything is multicast
+    if (clustered) cluster_sync_all(); else __syncthreads();     // peers' barriers are initialised before anything is multicast
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -464,7 +492,10 @@ __global__ void __launch_bounds__(128 * MT + 64) conv_umma_kernel(const ConvPara
                         fence_proxy_async_smem();
                     }
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(a_full + sa));
+                    if (lane == 0) {
+                        if (PAIR && crank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(a_peer + sa), 0u));   // to rank 0's issuer
+                        else mbar_arrive(smem_u32(a_full + sa));
+                    }
                     if (++sa == p.a_stages) { sa = 0; ph ^= 1u; }
                 }
             }
@@ -484,35 +515,54 @@ __global__ void __launch_bounds__(128 * MT + 64) conv_umma_kernel(const ConvPara
             }
         }
 
+    }
+    if (warp < MMA_WARP || (EXTRA_EPI && warp >= MMA_WARP + 2)) {
         // =================== epilogue ===================
         mbar_wait(smem_u32(acc_full), 0u, p.err_flag);
         tc_fence_after_sync();
         // every MMA has completed (acc_full), so the operand stages are dead: their memory is the slab
-        const int  mt    = warp >> 2;                       // M-tile this warp drains
+        const int  ew    = warp < MMA_WARP ? warp : warp - 2;      // epilogue warp index 0 .. 4 MT (+ 4) - 1
+        const int  mt    = warp < MMA_WARP ? warp >> 2 : 0;        // M-tile this warp drains
+        const int  pass0 = warp < MMA_WARP ? 0 : 1;                // the two warps of a lane quarter alternate the passes
         const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)mt * acc_stride;
         // (the stage memory doubles as the transpose slabs: no peer may still be multicasting into it -- every stage this
         //  CTA waited for was the last one its peers sent, and they send nothing after the final K-chunk)
         // statistics partials of the 4 * MT lane quarters sit behind the slabs (also dead stage memory)
-        double2 *stat_all = reinterpret_cast<double2 *>(smem + SMEM_HEADER + (size_t)(4 * MT) * SLAB_BYTES);
+        const int N_SLABS = 4 * MT + (EXTRA_EPI ? 4 : 0);
+        double2 *stat_all = reinterpret_cast<double2 *>(smem + SMEM_HEADER + (size_t)N_SLABS * SLAB_BYTES);
         constexpr bool STATS = MODE == PRO_F16 || MODE == PRO_NORM;      // the decoder convs (conv_umma_plan enforces it)
-        double2 *stat_row = STATS && p.stats_out ? stat_all + (size_t)warp * NC : nullptr;
-        epilogue_tile<STATS>(p, trow, reinterpret_cast<float *>(smem + SMEM_HEADER + (size_t)warp * SLAB_BYTES), lane,
-                      t0 + mt * TILE_M + (warp & 3) * 32, live ? seg_len : 0, seg_row0, nchunk, NC, 0, 1, stat_row);
+        const int quarter_row = warp < MMA_WARP ? warp : (warp & 3);    // both warps of a quarter fill the same row (disjoint columns)
+        double2 *stat_row = STATS && p.stats_out ? stat_all + (size_t)quarter_row * NC : nullptr;
+        epilogue_tile<STATS>(p, trow, reinterpret_cast<float *>(smem + SMEM_HEADER + (size_t)ew * SLAB_BYTES), lane,
+                      t0 + mt * TILE_M + (warp & 3) * 32, live ? seg_len : 0, seg_row0, nchunk, NC, pass0, EPI_STEP, stat_row);
         if (STATS && p.stats_out) {
             // all lane quarters of the tile, summed in a fixed order, one (sum, sum of squares) per output channel
-            asm volatile("bar.sync 1, %0;" ::"r"(N_PRODUCERS) : "memory");
+            asm volatile("bar.sync 1, %0;" ::"r"(N_EPI) : "memory");
+            const int et = warp < MMA_WARP ? tid : tid - 64;
             if (live)
-                for (int c = tid; c < NC; c += N_PRODUCERS) {
+                for (int c = et; c < NC; c += N_EPI) {
                     double a = 0.0, b = 0.0;
 #pragma unroll
                     for (int q = 0; q < 4 * MT; ++q) { const double2 v = stat_all[(size_t)q * NC + c]; a += v.x; b += v.y; }
                     p.stats_out[(size_t)blockIdx.x * p.Cout + (size_t)nchunk * NC + c] = make_double2(a, b);
                 }
         }
+    } else if (warp == MMA_WARP && PAIR && crank != 0) {
+        // =================== pair, rank 1: no MMAs to issue -- tell rank 0 when each weight half has landed ===================
+        const int b_stages = p.b_stages;
+        int sb = 0;
+        uint32_t phb = 0;
+        for (int c = 0; c < nkc; ++c)
+            for (int a = 0; a < ntaps; ++a) {
+                mbar_wait(smem_u32(b_full + sb), phb, p.err_flag);
+                if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(b_peer + sb), 0u));
+                __syncwarp();
+                if (++sb == b_stages) { sb = 0; phb ^= 1u; }
+            }
     } else if (warp == MMA_WARP) {
         // =================== MMA issuer (one elected lane of a converged warp) ===================
         const uint32_t leader = elect_one();
-        const uint32_t idesc = make_idesc(NC);
+        const uint32_t idesc = PAIR ? make_idesc_mn(2 * TILE_M, NC) : make_idesc(NC);
         // descriptors advance by plain additions on the 14-bit start-address field (no carry out of
         // it: shared memory is < 256 KB); stage indices / phases are counted, not divided
         const uint64_t a_kstep = (uint64_t)((2u * lbo_a) >> 4), b_kstep = (uint64_t)((2u * lbo_b) >> 4);
@@ -522,11 +572,13 @@ __global__ void __launch_bounds__(128 * MT + 64) conv_umma_kernel(const ConvPara
         for (int c = 0; c < nkc; ++c) {
             const int ksteps = min(KCHUNK, Cin - c * KCHUNK) >> 4;
             mbar_wait(smem_u32(a_full + sa), pha, p.err_flag);
+            if (PAIR) mbar_wait_cluster(smem_u32(a_peer + sa), pha, p.err_flag);
             if (MODE == PRO_F16) fence_proxy_async_smem();    // cp.async wrote through the generic proxy
             tc_fence_after_sync();
             uint32_t a_tap = a_base + sa * a_stage_bytes;
             for (int a = 0; a < ntaps; ++a, a_tap += tap_bytes) {
                 mbar_wait(smem_u32(b_full + sb), phb, p.err_flag);
+                if (PAIR) mbar_wait_cluster(smem_u32(b_peer + sb), phb, p.err_flag);
                 tc_fence_after_sync();
                 if (leader) {
                     const uint64_t bdesc0 = make_smem_desc(b_base + sb * b_stage_bytes, lbo_b, 128u);
@@ -536,22 +588,30 @@ __global__ void __launch_bounds__(128 * MT + 64) conv_umma_kernel(const ConvPara
                         uint64_t bdesc = bdesc0;
                         uint32_t acc = accum;
                         for (int kk = 0; kk < ksteps; ++kk, adesc += a_kstep, bdesc += b_kstep) {
-                            umma_f16(tmem_base + (uint32_t)mt * acc_stride, adesc, bdesc, idesc, acc);
+                            if (PAIR) umma2_f16(tmem_base, adesc, bdesc, idesc, acc);
+                            else umma_f16(tmem_base + (uint32_t)mt * acc_stride, adesc, bdesc, idesc, acc);
                             acc = 1u;
                         }
                     }
-                    if (CL > 1) umma_commit_multicast(smem_u32(b_empty + sb), cmask);
+                    if (PAIR) umma2_commit(smem_u32(b_empty + sb));
+                    else if (CL > 1) umma_commit_multicast(smem_u32(b_empty + sb), cmask);
                     else umma_commit(smem_u32(b_empty + sb));
                 }
                 accum = 1u;
                 __syncwarp();
                 if (++sb == b_stages) { sb = 0; phb ^= 1u; }
             }
-            if (leader) umma_commit(smem_u32(a_empty + sa));
+            if (leader) {
+                if (PAIR) umma2_commit(smem_u32(a_empty + sa));
+                else umma_commit(smem_u32(a_empty + sa));
+            }
             __syncwarp();
             if (++sa == a_stages) { sa = 0; pha ^= 1u; }
         }
-        if (leader) umma_commit(smem_u32(acc_full));
+        if (leader) {
+            if (PAIR) umma2_commit(smem_u32(acc_full));
+            else umma_commit(smem_u32(acc_full));
+        }
         __syncwarp();
     } else {
         // =================== weight (B operand) loader ===================
@@ -572,6 +632,22 @@ __global__ void __launch_bounds__(128 * MT + 64) conv_umma_kernel(const ConvPara
                 for (int a = 0; a < ntaps; ++a, src += bytes) {
                     // b_empty counts the commits of ALL CTAs of the cluster: the share goes into every peer's stage
                     mbar_wait(smem_u32(b_empty + sb), phb ^ 1u, p.err_flag);
+                    if (PAIR) {
+                        // this CTA's NC / 2 output channels of every 8-channel K group (a packed block is [group][NC][8])
+                        const uint32_t seg = (uint32_t)NB * 16u;
+                        const int groups = min(KCHUNK, Cin - c * KCHUNK) >> 3;
+                        mbar_arrive_expect_tx(smem_u32(b_full + sb), (uint32_t)groups * seg);
+#ifdef ZVX_WHATIF_PAIR_ONECOPY
+                        // timing experiment only (wrong results): the half as ONE contiguous copy
+                        bulk_copy_g2s(b_base + sb * b_stage_bytes, src + crank * (uint32_t)groups * seg, (uint32_t)groups * seg, smem_u32(b_full + sb));
+#else
+                        for (int g = 0; g < groups; ++g)
+                            bulk_copy_g2s(b_base + sb * b_stage_bytes + (uint32_t)g * seg, src + (size_t)g * (2u * seg) + crank * seg, seg,
+                                          smem_u32(b_full + sb));
+#endif
+                        if (++sb == b_stages) { sb = 0; phb ^= 1u; }
+                        continue;
+                    }
                     mbar_arrive_expect_tx(smem_u32(b_full + sb), CL > 1 ? bytes : wbytes);
                     if (CL > 1)
                         bulk_copy_g2s_multicast(b_base + sb * b_stage_bytes + crank * part, src + crank * part, part, smem_u32(b_full + sb), cmask);
@@ -585,10 +661,11 @@ __global__ void __launch_bounds__(128 * MT + 64) conv_umma_kernel(const ConvPara
     }
 
     tc_fence_before_sync();
-    if (CL > 1) cluster_sync_all(); else __syncthreads();        // no CTA exits while a peer may still signal its barriers
+    if (clustered) cluster_sync_all(); else __syncthreads();     // no CTA exits while a peer may still signal its barriers
     if (warp == MMA_WARP) {
         tc_fence_after_sync();
-        tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+        if (PAIR) tmem_dealloc2(tmem_base, (uint32_t)p.tmem_cols);
+        else tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
     }
 }
 
@@ -800,9 +877,10 @@ size_t conv_umma_plan(ConvParams &p, size_t smem_budget)
     // TMA boxes: at most 256 rows, always 8 channel groups (a partial last chunk is zero-filled), rows exactly the box
     if (p.stats_out && p.pro_mode != PRO_F16 && p.pro_mode != PRO_NORM) p.stats_out = nullptr;
     if (p.use_tma && (p.pro_mode != PRO_F16 || need_rows > 256 || p.Cin < KCHUNK || p.ldx % 8 || p.x_ch_off % 8)) p.use_tma = 0;
+    if (p.pair && (!p.use_tma || p.mt != 1 || p.NC % 16 || p.NC < 32)) p.pair = 0;     // pairs: TMA-staged operand, N a multiple of 16
     p.a_rows            = p.use_tma ? need_rows : round_a_rows(need_rows, kc_max);
     const size_t a_stage = (size_t)(kc_max >> 3) * p.a_rows * 16;
-    const size_t b_stage = (size_t)kc_max * p.NC * 2;
+    const size_t b_stage = (size_t)kc_max * p.NC * 2 / (p.pair ? 2 : 1);
     const int nkc        = (p.Cin + KCHUNK - 1) / KCHUNK;
     const int nb_total   = nkc * p.ntaps;
     int as = nkc < 2 ? 1 : 2;
@@ -827,7 +905,7 @@ size_t conv_umma_plan(ConvParams &p, size_t smem_budget)
     p.tmem_cols = cols;
     // the epilogue reuses the stage memory for its transpose slabs (one per producer warp)
     const size_t stages = as * a_stage + bs * b_stage,
-                 slabs = (size_t)4 * p.mt * SLAB_BYTES + (p.stats_out ? (size_t)4 * p.mt * p.NC * sizeof(double2) : 0);
+                 slabs = (size_t)(4 * p.mt + (p.mt == 1 && p.epi8 ? 4 : 0)) * SLAB_BYTES + (p.stats_out ? (size_t)4 * p.mt * p.NC * sizeof(double2) : 0);
     return SMEM_HEADER + (stages > slabs ? stages : slabs);
 }
 
@@ -930,6 +1008,7 @@ static cudaError_t launch_mode(const ConvParams &p, int total_tiles, size_t smem
 {
     ConvParams q = p;
     if (q.cluster != 2 && q.cluster != 4) q.cluster = 1;
+    if (q.pair) q.cluster = 2;
     q.n_tiles = total_tiles;
     dim3 grid((total_tiles + q.cluster - 1) / q.cluster * q.cluster, p.Cout / p.NC, 1);
     CUtensorMap a_map;
@@ -940,7 +1019,10 @@ static cudaError_t launch_mode(const ConvParams &p, int total_tiles, size_t smem
     } else {
         q.use_tma = 0;
     }
-    return launch_clustered(conv_umma_kernel<MODE, MT>, grid, 128 * MT + 64, smem, st, q, a_map);
+    if constexpr (MODE == PRO_F16 && MT == 1) {
+        if (q.pair) return launch_clustered(conv_umma_kernel<MODE, MT, true>, grid, q.epi8 ? conv_threads(MT) : 128 * MT + 64, smem, st, q, a_map);
+    }
+    return launch_clustered(conv_umma_kernel<MODE, MT>, grid, q.epi8 && MT == 1 ? conv_threads(MT) : 128 * MT + 64, smem, st, q, a_map);
 }
 
 template <int MODE>
@@ -950,6 +1032,9 @@ static cudaError_t init_mode()
     const int kMax = 227 * 1024;
     if ((e = cudaFuncSetAttribute(conv_umma_pk_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(conv_umma_kernel<MODE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax)) != cudaSuccess) return e;
+    if constexpr (MODE == PRO_F16) {
+        if ((e = cudaFuncSetAttribute(conv_umma_kernel<MODE, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax)) != cudaSuccess) return e;
+    }
     return cudaFuncSetAttribute(conv_umma_kernel<MODE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
 }
 

@@ -77,6 +77,78 @@ __device__ __forceinline__ void bulk_copy_g2s_multicast(uint32_t dst, const void
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(mask)
                  : "memory");
 }
+// ---- CTA pairs (tcgen05 .cta_group::2): the two CTAs of a cluster of 2 run ONE M = 256 MMA stream issued by rank 0;
+//      each SM reads its own 128 rows of A and its own half of B from its own shared memory ----
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank)        // the same offset in CTA `rank` of the cluster
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)        // arrive on a (possibly remote) CTA's barrier
+{
+#ifdef ZVX_PAIR_STRONG_SCOPE
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+#else
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+#endif
+}
+__device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+#ifdef ZVX_PAIR_STRONG_SCOPE
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+#else
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+#endif
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+// wait for arrivals that come from the peer CTA (acquire at cluster scope)
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, int *err_flag)
+{
+    if (mbar_try_wait_cluster(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait_cluster(bar, parity)) {
+        if (clock64() - t0 > 6000000000LL) {
+            if (err_flag) atomicExch(err_flag, 1);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t smem_dst, uint32_t ncols)      // one warp of EACH CTA of the pair
+{
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// completion of all earlier pair MMAs of this thread arrives on the mbarrier at this offset in both CTAs
+__device__ __forceinline__ void umma2_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3)
+                 : "memory");
+}
 // TMA: one 3-D tile of a tensor map (cuTensorMapEncodeTiled) -> shared memory; out-of-bounds elements arrive as zeros
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void *tmap, int c0, int c1, int c2, uint32_t bar)
 {

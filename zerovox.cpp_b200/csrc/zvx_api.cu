@@ -123,6 +123,8 @@ struct zvx_ctx {
     int conv_tma = 1;       // PRO_F16 operands of the one-tile conv kernel staged by TMA (cp.async.bulk.tensor) instead of cp.async
     int conv_cluster = 1;   // CTAs per cluster of the one-tile conv kernel sharing every weight stage by multicast; measured on
                             // B200 (profiles/r02_conv_cluster_ab.txt): 2 -> +7 %, 4 -> +19 % time on the decoder convs, so off
+    int conv_epi8 = 1;  // see run_conv
+    int conv_pair = 0;  // PRO_F16 convs of the one-tile kernel as tcgen05 CTA pairs (M = 256, half a weight stage per SM)
     int conv_mt2 = 0;   // two M-tiles per CTA: measured slower on B200 while the A producer is the limit (profiles/)
     std::vector<int> tile256_cfg;                 // per rate index: wincfg entry of the 256-row tiling
     int num_sms = 148;
@@ -866,12 +868,16 @@ int run_conv(zvx_ctx *ctx, const ConvCall &cc)
         // persistent kernel whenever there are at least ~2 work items per SM, else one tile per CTA
         // (measured per launch kind, profiles/: it wins on the MRF convs -- long K loops, residual-stream
         // epilogue -- and loses on the short decoder / up-conv launches)
-        if (ctx->conv_persistent && cc.kind == ZVX_K_MRF_CONV && p.mt == 1 && (int64_t)tiles * (L.OC / L.NC) >= (int64_t)2 * ctx->num_sms) {
+        if (ctx->conv_persistent && (cc.kind == ZVX_K_MRF_CONV || (getenv("ZVX_WHATIF_PK_ALL") && cc.kind == ZVX_K_DEC_CONV)) && p.mt == 1 && (int64_t)tiles * (L.OC / L.NC) >= (int64_t)2 * ctx->num_sms) {
             const size_t smem = conv_umma_pk_plan(p, 226 * 1024);
             if (smem > 227 * 1024) return fail(ctx, "conv needs %zu bytes of shared memory", smem);
             CK(ctx, conv_umma_pk_launch(p, tiles, ctx->num_sms, smem, ctx->stream));
         } else {
             p.use_tma = ctx->conv_tma && p.pro_mode == PRO_F16;
+            // a second epilogue warp per lane quarter where the epilogue is a large share of a CTA's life and the launch
+            // is not bound by the number of co-resident CTAs (measured per launch kind, profiles/r02_ab_conv_epilogue.txt)
+            p.epi8 = ctx->conv_epi8 && p.mt == 1 && (cc.kind == ZVX_K_DEC_CONV || (cc.kind == ZVX_K_UPCONV && L.NC >= 128));
+            p.pair = ctx->conv_pair && p.use_tma && p.mt == 1 && tiles >= 2 && (int64_t)L.IC * v.ntaps >= 512;
             p.tma_row0 = 0;
             p.tma_rows = (long long)ctx->last_frames * p.rate_in;
             const size_t smem = conv_umma_plan(p, p.mt == 2 ? 226 * 1024 : (size_t)ctx->conv_smem_kb * 1024);
@@ -1515,6 +1521,8 @@ int zvx_create(zvx_ctx **out, const zvx_config *cfg, const zvx_tensor_desc *weig
     if (const char *e = getenv("ZVX_CONV_MT2")) ctx->conv_mt2 = atoi(e);
     if (const char *e = getenv("ZVX_CONV_CLUSTER")) ctx->conv_cluster = atoi(e);
     if (const char *e = getenv("ZVX_CONV_TMA")) ctx->conv_tma = atoi(e);
+    if (const char *e = getenv("ZVX_CONV_PAIR")) ctx->conv_pair = atoi(e);
+    if (const char *e = getenv("ZVX_CONV_EPI8")) ctx->conv_epi8 = atoi(e);
     if (const char *e = getenv("ZVX_MRF_F16_CHAIN")) ctx->mrf_f16_chain = atoi(e);
     if (const char *e = getenv("ZVX_FUSED_STATS")) ctx->fused_stats = atoi(e);
     if (const char *e = getenv("ZVX_STAGE_HANDOFF")) ctx->stage_handoff = atoi(e);

@@ -89,6 +89,8 @@ struct ConvParams {
     // PRO_F16 operand staged by TMA (cp.async.bulk.tensor.3d, one box = a halo tile of 64 channels) instead of per-thread
     // 16-byte cp.async; the kernel's tensor-map argument describes the [rows][ldx] fp16 buffer as (8 ch, rows, C/8 groups)
     int          use_tma;
+    int          epi8;        // one-tile kernel, MT = 1: four more epilogue warps (a second warp per tensor-memory lane quarter)
+    int          pair;        // one-tile kernel as tcgen05 CTA pairs (.cta_group::2), see conv_umma.cu; needs use_tma
     long long    tma_row0;    // first row of the tensor map inside the buffer (rows are addressed relative to it)
     long long    tma_rows;    // rows of the buffer the tensor map covers
     // ---- smem geometry (host computed) ----
