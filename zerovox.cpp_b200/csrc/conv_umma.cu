@@ -302,7 +302,9 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams &p, uint32_t trow
                                       __uint_as_float(r[4 * q + 3]));
         }
         __syncwarp();
-        double sx[4] = {0.0, 0.0, 0.0, 0.0}, sq[4] = {0.0, 0.0, 0.0, 0.0};
+        // statistics: this thread's (up to) 8 rows of a column are summed in fp32 (8 terms: relative error ~1e-7, far below
+        // the fp16 rounding of the operand the normalised tensor becomes), everything across threads / tiles in double
+        float fx[4] = {0.f, 0.f, 0.f, 0.f}, fq[4] = {0.f, 0.f, 0.f, 0.f};
         if (col_ok) {
             float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
             if (p.bias) bias = __ldg(reinterpret_cast<const float4 *>(p.bias + oc));
@@ -316,9 +318,9 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams &p, uint32_t trow
                     v = make_float4(__fmul_rn(v.x, scale), __fmul_rn(v.y, scale), __fmul_rn(v.z, scale), __fmul_rn(v.w, scale));
                     if (has_o32) *reinterpret_cast<float4 *>(o32_row + (size_t)i * o32_step + oc) = v;
                     if (stat_row) {
-                        const double d0 = (double)v.x, d1 = (double)v.y, d2 = (double)v.z, d3 = (double)v.w;
-                        sx[0] += d0; sx[1] += d1; sx[2] += d2; sx[3] += d3;
-                        sq[0] = fma(d0, d0, sq[0]); sq[1] = fma(d1, d1, sq[1]); sq[2] = fma(d2, d2, sq[2]); sq[3] = fma(d3, d3, sq[3]);
+                        fx[0] = __fadd_rn(fx[0], v.x); fx[1] = __fadd_rn(fx[1], v.y); fx[2] = __fadd_rn(fx[2], v.z); fx[3] = __fadd_rn(fx[3], v.w);
+                        fq[0] = __fmaf_rn(v.x, v.x, fq[0]); fq[1] = __fmaf_rn(v.y, v.y, fq[1]); fq[2] = __fmaf_rn(v.z, v.z, fq[2]);
+                        fq[3] = __fmaf_rn(v.w, v.w, fq[3]);
                     }
                     if (has_o16) {
                         uint2 h;
@@ -330,6 +332,9 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams &p, uint32_t trow
             }
         }
         if (stat_row) {
+            double sx[4], sq[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { sx[k] = (double)fx[k]; sq[k] = (double)fq[k]; }
             // the four lanes l, l+8, l+16, l+24 hold the same columns (row groups 0..3): warp-shuffle reduction in a fixed order
 #pragma unroll
             for (int k = 0; k < 4; ++k) {

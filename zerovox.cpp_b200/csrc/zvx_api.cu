@@ -868,7 +868,7 @@ int run_conv(zvx_ctx *ctx, const ConvCall &cc)
         // persistent kernel whenever there are at least ~2 work items per SM, else one tile per CTA
         // (measured per launch kind, profiles/: it wins on the MRF convs -- long K loops, residual-stream
         // epilogue -- and loses on the short decoder / up-conv launches)
-        if (ctx->conv_persistent && (cc.kind == ZVX_K_MRF_CONV || (getenv("ZVX_WHATIF_PK_ALL") && cc.kind == ZVX_K_DEC_CONV)) && p.mt == 1 && (int64_t)tiles * (L.OC / L.NC) >= (int64_t)2 * ctx->num_sms) {
+        if (ctx->conv_persistent && cc.kind == ZVX_K_MRF_CONV && p.mt == 1 && (int64_t)tiles * (L.OC / L.NC) >= (int64_t)2 * ctx->num_sms) {
             const size_t smem = conv_umma_pk_plan(p, 226 * 1024);
             if (smem > 227 * 1024) return fail(ctx, "conv needs %zu bytes of shared memory", smem);
             CK(ctx, conv_umma_pk_launch(p, tiles, ctx->num_sms, smem, ctx->stream));
