@@ -6,7 +6,10 @@
   configs[4]  single-stream latency: one utterance at L = 400 (5 s) and at L = 1500 (the reference's
               shipped max_seq_len incl. zero tail semantics), p50 / p99 over N runs through the
               host-pointer C ABI (H2D + compute + D2H), i.e. StyleTTSDecoder::eval + HiFiGAN::eval
-(the FS2 encoder of configs[4] stays on the reference's ggml CPU path and is not timed here)."""
+  configs[4] as BASELINE.json words it: the reference's hard-coded sentence through host/_build/zvx_model -- FastSpeech2
+              encoder on the host (the reference's own fs2encoder.cpp + ggml CPU), length regulator + decoder + vocoder on
+              the B200 -- p50 / p99 of encoder, GPU call and total over N runs, in the reference's default mode (1500 frames
+              with the zero tail) and with only the valid frames synthesised."""
 import json
 import os
 import sys
@@ -67,6 +70,33 @@ def main():
                           "audio_s": L / 80.0, "runs": runs, "p50_ms": float(lat[len(lat) // 2]), "p99_ms": float(lat[int(len(lat) * 0.99) - 1]),
                           "min_ms": float(lat[0]), "rtf_inverse_p50": (L / 80.0) / (float(lat[len(lat) // 2]) / 1e3)}))
     ctx.close()
+    # ---- configs[4] including the FastSpeech2 encoder (host) ----
+    import struct
+    import subprocess
+    import tempfile
+    exe = os.path.join(ROOT, "zerovox.cpp_b200", "host", "_build", "zvx_model")
+    gold = os.path.join(ROOT, "tests", "golden", "regulator_default.npz")
+    if os.path.exists(exe) and os.path.exists(gold):
+        g = np.load(gold)
+        full = zvx.synth.write_model(zvx.synth.default_model_path(with_fs2=True), with_fs2=True)
+        with tempfile.TemporaryDirectory() as td:
+            sp = os.path.join(td, "s0.bin")
+            with open(sp, "wb") as f:
+                f.write(struct.pack("<i", 120))
+                f.write(np.ascontiguousarray(g["src"], np.int32).tobytes())
+                f.write(np.ascontiguousarray(g["puncts"], np.int32).tobytes())
+                f.write(np.ascontiguousarray(g["style"], np.float32).tobytes())
+            for mode in (["--reference-default"], []):
+                r = subprocess.run([exe, full, os.path.join(td, "o")] + mode + ["--bench", str(runs), sp], capture_output=True, text=True)
+                if r.returncode != 0:
+                    print(json.dumps({"config": "configs[4] with encoder", "error": r.stderr[-500:]}))
+                    continue
+                j = json.loads(r.stdout.strip().splitlines()[-1])
+                j["config"] = ("configs[4] e2e latency: FS2 encoder on the host (reference's fs2encoder.cpp, ggml CPU) + length regulator, "
+                               "decoder, vocoder on 1xB200, the reference's default sentence (zerovox.cpp:204-314), " + j["mode"])
+                print(json.dumps(j))
+    else:
+        print(json.dumps({"config": "configs[4] with encoder", "skipped": "host/_build/zvx_model or the regulator golden missing"}))
 
 
 if __name__ == "__main__":
