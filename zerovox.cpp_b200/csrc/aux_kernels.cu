@@ -117,47 +117,80 @@ cudaError_t stats_finalize_launch(const double2 *part, int C, const int *tile_st
 // ---------------------------------------------------------------------------------
 // AdaIN style projection for all AdaIN layers at once:  h = fc_w . s + fc_b;
 // gamma1 = 1 + h[:C]; beta = h[C:]   (/root/reference/src/stylettsdec.cpp:177-189).
-// One warp per output row n of the concatenated (sum 2C) x style_dim weight; the row is
-// kept in registers and reused for every utterance of the batch.
+// A small tiled fp32 GEMM: one block = 32 rows of the concatenated (sum 2C) x style_dim weight x 32 utterances, K in
+// chunks of 64 through shared memory; a warp owns 4 rows (read as broadcasts), a lane one utterance.  (Round 1: one warp
+// per row with a shuffle reduction per (row, utterance) -- 0.19 ms per step for 1.1 GFLOP.)
 // ---------------------------------------------------------------------------------
 constexpr int ADAIN_MAX_S = 640;
+constexpr int AF_ROWS = 32, AF_UT = 32, AF_KC = 64, AF_LD = AF_KC + 4;     // + 4 floats: rows stay 16-byte aligned, quarter-warps conflict-free
 
 __global__ void __launch_bounds__(256) adain_fc_kernel(const AdainTable tab, const float *__restrict__ style, int B,
                                                        float *__restrict__ out)
 {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (warp >= tab.total) return;
-    int k = 0, base = 0;
-    while (k < tab.n - 1 && warp >= base + 2 * tab.d[k].C) {
-        base += 2 * tab.d[k].C;
-        ++k;
-    }
-    const AdainDesc d = tab.d[k];
-    const int n = warp - base;                    // row inside this fc: [0, 2C)
+    __shared__ __align__(16) float ws[AF_ROWS][AF_LD];
+    __shared__ __align__(16) float ss[AF_UT][AF_LD];
+    __shared__ const float *rowp[AF_ROWS];
+    __shared__ float rbias[AF_ROWS], radd[AF_ROWS];
+    __shared__ int rout[AF_ROWS];
+    const int tid = threadIdx.x, lane = tid & 31, rg = tid >> 5;
     const int S = tab.style_dim;
-    const float *wrow = d.fc_w + (size_t)n * S;
-    float w[ADAIN_MAX_S / 32];                    // style_dim <= ADAIN_MAX_S
-#pragma unroll
-    for (int q = 0; q < ADAIN_MAX_S / 32; ++q) {
-        const int i = lane + 32 * q;
-        w[q] = i < S ? __ldg(wrow + i) : 0.f;
-    }
-    const float bias = __ldg(d.fc_b + n);
-    for (int u = 0; u < B; ++u) {
-        const float *s = style + (size_t)u * S;
-        float acc = 0.f;
-#pragma unroll
-        for (int q = 0; q < ADAIN_MAX_S / 32; ++q) {
-            const int i = lane + 32 * q;
-            if (i < S) acc = fmaf(w[q], __ldg(s + i), acc);
+    if (tid < AF_ROWS) {
+        const int ng = blockIdx.x * AF_ROWS + tid;
+        rowp[tid] = nullptr;
+        rout[tid] = -1;
+        rbias[tid] = 0.f;
+        radd[tid] = 0.f;
+        if (ng < tab.total) {
+            int k = 0, base = 0;
+            while (k < tab.n - 1 && ng >= base + 2 * tab.d[k].C) {
+                base += 2 * tab.d[k].C;
+                ++k;
+            }
+            const AdainDesc d = tab.d[k];
+            const int n = ng - base;                      // row inside this fc: [0, 2C)
+            rowp[tid] = d.fc_w + (size_t)n * S;
+            rbias[tid] = __ldg(d.fc_b + n);
+            radd[tid] = n < d.C ? 1.0f : 0.0f;            // gamma + one (stylettsdec.cpp:189)
+            rout[tid] = d.out_off + n;
         }
+    }
+    __syncthreads();
+    for (int u0 = 0; u0 < B; u0 += AF_UT) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int k0 = 0; k0 < S; k0 += AF_KC) {
+            for (int i = tid; i < AF_ROWS * AF_KC; i += 256) {
+                const int r = i / AF_KC, c = i % AF_KC;
+                ws[r][c] = (rowp[r] && k0 + c < S) ? __ldg(rowp[r] + k0 + c) : 0.f;
+            }
+            for (int i = tid; i < AF_UT * AF_KC; i += 256) {
+                const int u = i / AF_KC, c = i % AF_KC;
+                ss[u][c] = (u0 + u < B && k0 + c < S) ? __ldg(style + (size_t)(u0 + u) * S + k0 + c) : 0.f;
+            }
+            __syncthreads();
+#pragma unroll 4
+            for (int c = 0; c < AF_KC; c += 4) {
+                const float4 sv = *reinterpret_cast<const float4 *>(&ss[lane][c]);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) {
-            float h = __fadd_rn(acc, bias);
-            if (n < d.C) h = __fadd_rn(h, 1.0f);  // gamma + one (stylettsdec.cpp:189)
-            out[(size_t)u * tab.total + d.out_off + n] = h;
+                for (int r = 0; r < 4; ++r) {
+                    const float4 wv = *reinterpret_cast<const float4 *>(&ws[rg * 4 + r][c]);
+                    acc[r] = fmaf(wv.x, sv.x, acc[r]);
+                    acc[r] = fmaf(wv.y, sv.y, acc[r]);
+                    acc[r] = fmaf(wv.z, sv.z, acc[r]);
+                    acc[r] = fmaf(wv.w, sv.w, acc[r]);
+                }
+            }
+            __syncthreads();
+        }
+        if (u0 + lane < B) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int row = rg * 4 + r;
+                if (rout[row] >= 0) {
+                    float h = __fadd_rn(acc[r], rbias[row]);
+                    if (radd[row] != 0.f) h = __fadd_rn(h, 1.0f);
+                    out[(size_t)(u0 + lane) * tab.total + rout[row]] = h;
+                }
+            }
         }
     }
 }
@@ -165,9 +198,8 @@ __global__ void __launch_bounds__(256) adain_fc_kernel(const AdainTable tab, con
 cudaError_t adain_fc_launch(const AdainTable &tab, const float *style, int B, float *out, cudaStream_t st)
 {
     if (tab.style_dim > ADAIN_MAX_S) return cudaErrorInvalidValue;
-    const int warps_per_block = 8;
-    const int blocks = (tab.total + warps_per_block - 1) / warps_per_block;
-    adain_fc_kernel<<<blocks, warps_per_block * 32, 0, st>>>(tab, style, B, out);
+    const int blocks = (tab.total + AF_ROWS - 1) / AF_ROWS;
+    adain_fc_kernel<<<blocks, 256, 0, st>>>(tab, style, B, out);
     return cudaGetLastError();
 }
 
