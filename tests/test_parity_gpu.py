@@ -276,3 +276,20 @@ def test_pipelined_submit_wait_equals_synchronous_call(ctx, zvx):
     for r in range(3):
         for a, b in zip(outs[r], ref[r]):
             assert np.array_equal(a, b)
+
+
+def test_edge_windows_vector_path_equals_scalar_path(ctx, zvx, weights, monkeypatch):
+    """Round 2: windows of the fused MRF kernel that touch an utterance edge take the vector data path and have the rows
+    outside the utterance zeroed afterwards (mrf_fused.cu, zero_outside).  ZVX_FUSED_FLAGS=1 forces the per-element scalar
+    path (explicit zero masking per layer) for every window: same arithmetic, so a ragged batch -- first / last windows,
+    utterances shorter than one window, lengths around window multiples -- must come out bit for bit the same."""
+    from zerovox_cpp_b200 import capi
+    Ls = [1, 2, 5, 17, 48, 63, 64, 65, 130, 257]
+    mels = [zvx.synth.make_inputs(L, seed=40 + i)[0][:, :80].copy() * 0.3 - 4.0 for i, L in enumerate(Ls)]
+    want = ctx.vocode_batch(mels)
+    monkeypatch.setenv("ZVX_FUSED_FLAGS", "1")
+    cx = capi.Context(weights, device=0)          # the switch is read at zvx_create
+    got = cx.vocode_batch(mels)
+    cx.close()
+    for L, a, b in zip(Ls, want, got):
+        assert a.shape == (L * 300,) and np.array_equal(a, b), L
