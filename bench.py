@@ -420,7 +420,7 @@ def main():
                      "gbs": round(v[2] / (v[3] / 1000.0) / 1e9, 1) if v[3] > 0 and v[2] > 0 else None}
                  for k, v in sorted(by.items())}
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath))
     per_stage = {k: round(v[1] / (v[3] / 1000.0) / 1e12, 1) for k, v in sorted(by.items()) if k.startswith("mrf_conv") and v[3] > 0}
