@@ -331,6 +331,40 @@ __global__ void __launch_bounds__(256) sum3_act_f16_kernel(const float4 *__restr
     }
 }
 
+// the same for fp16 branch tensors (8 elements per thread and step)
+__global__ void __launch_bounds__(256) sum3h_act_f16_kernel(const uint4 *__restrict__ a, const uint4 *__restrict__ b,
+                                                            const uint4 *__restrict__ c, float scale, float slope, size_t n8,
+                                                            uint4 *__restrict__ y16)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 va = a[i], vb = b[i], vc = c[i];
+        const uint32_t wa[4] = {va.x, va.y, va.z, va.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w}, wc[4] = {vc.x, vc.y, vc.z, vc.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 fa = __half22float2(*reinterpret_cast<const __half2 *>(&wa[k]));
+            const float2 fb = __half22float2(*reinterpret_cast<const __half2 *>(&wb[k]));
+            const float2 fc = __half22float2(*reinterpret_cast<const __half2 *>(&wc[k]));
+            const __half2 h = __floats2half2_rn(lrelu_f(__fmul_rn(__fadd_rn(__fadd_rn(fa.x, fb.x), fc.x), scale), slope),
+                                                lrelu_f(__fmul_rn(__fadd_rn(__fadd_rn(fa.y, fb.y), fc.y), scale), slope));
+            o[k] = *reinterpret_cast<const uint32_t *>(&h);
+        }
+        y16[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+cudaError_t sum3h_act_f16_launch(const __half *a, const __half *b, const __half *c, float scale, float slope, size_t n, __half *y16,
+                                 cudaStream_t st)
+{
+    if (n % 8) return cudaErrorInvalidValue;
+    const size_t n8 = n / 8;
+    int blocks = (int)std::min<size_t>((n8 + 255) / 256, (size_t)148 * 8);
+    if (blocks < 1) blocks = 1;
+    sum3h_act_f16_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const uint4 *>(a), reinterpret_cast<const uint4 *>(b),
+                                                reinterpret_cast<const uint4 *>(c), scale, slope, n8, reinterpret_cast<uint4 *>(y16));
+    return cudaGetLastError();
+}
+
 cudaError_t sum3_act_f16_launch(const float *a, const float *b, const float *c, float scale, float slope, size_t n, __half *y16,
                                 cudaStream_t st)
 {
@@ -408,7 +442,7 @@ constexpr int OC_MAX_K = 16;
 
 // Generic shape: weights staged in shared memory.
 __global__ void __launch_bounds__(128) out_conv_kernel(const float *__restrict__ x, const float *__restrict__ x2,
-                                                       const float *__restrict__ x3, const __half *__restrict__ x16, float sum_scale, int C, int K,
+                                                       const float *__restrict__ x3, const __half *__restrict__ x16, const int halves, float sum_scale, int C, int K,
                                                        const __half *__restrict__ w_raw, const float *__restrict__ bias,
                                                        float slope, const int *__restrict__ seg_start,
                                                        const int *__restrict__ tile_start, int B, int rate,
@@ -437,8 +471,15 @@ __global__ void __launch_bounds__(128) out_conv_kernel(const float *__restrict__
             if (x16) {
                 v = __half2float(x16[(row0 + t) * C + c]);          // already averaged, activated and rounded by the producer
             } else {
-                float xv = x[(row0 + t) * C + c];
-                if (x2) xv = __fmul_rn(__fadd_rn(__fadd_rn(xv, x2[(row0 + t) * C + c]), x3[(row0 + t) * C + c]), sum_scale);
+                float xv;
+                if (halves) {       // the three branch tensors arrive as fp16
+                    const size_t e = (row0 + t) * C + c;
+                    xv = __fmul_rn(__fadd_rn(__fadd_rn(__half2float(reinterpret_cast<const __half *>(x)[e]), __half2float(reinterpret_cast<const __half *>(x2)[e])),
+                                             __half2float(reinterpret_cast<const __half *>(x3)[e])), sum_scale);
+                } else {
+                    xv = x[(row0 + t) * C + c];
+                    if (x2) xv = __fmul_rn(__fadd_rn(__fadd_rn(xv, x2[(row0 + t) * C + c]), x3[(row0 + t) * C + c]), sum_scale);
+                }
                 v = __half2float(__float2half_rn(lrelu_f(xv, slope)));
             }
         }
@@ -462,7 +503,7 @@ __global__ void __launch_bounds__(128) out_conv_kernel(const float *__restrict__
 struct OutConvW { float w[7 * 32]; float bias; };      // [k][c]
 
 __global__ void __launch_bounds__(128) out_conv_32x7_kernel(const float *__restrict__ x, const float *__restrict__ x2,
-                                                            const float *__restrict__ x3, const __half *__restrict__ x16, float sum_scale,
+                                                            const float *__restrict__ x3, const __half *__restrict__ x16, const int halves, float sum_scale,
                                                             const OutConvW W, float slope,
                                                             const int *__restrict__ seg_start,
                                                             const int *__restrict__ tile_start, int B, int rate,
@@ -493,7 +534,22 @@ __global__ void __launch_bounds__(128) out_conv_32x7_kernel(const float *__restr
             }
             continue;
         }
-        if (t >= 0 && t < seg_len) {
+        if (halves) {
+            // the three branch tensors arrive as fp16 (6 instead of 12 bytes per element)
+            if (t >= 0 && t < seg_len) {
+                const size_t e = (row0 + t) * C + c4;
+                const uint2 qa = *reinterpret_cast<const uint2 *>(reinterpret_cast<const __half *>(x) + e);
+                const uint2 qb = *reinterpret_cast<const uint2 *>(reinterpret_cast<const __half *>(x2) + e);
+                const uint2 qc = *reinterpret_cast<const uint2 *>(reinterpret_cast<const __half *>(x3) + e);
+                const float2 a0 = __half22float2(*reinterpret_cast<const __half2 *>(&qa.x)), a1 = __half22float2(*reinterpret_cast<const __half2 *>(&qa.y));
+                const float2 b0 = __half22float2(*reinterpret_cast<const __half2 *>(&qb.x)), b1 = __half22float2(*reinterpret_cast<const __half2 *>(&qb.y));
+                const float2 c0 = __half22float2(*reinterpret_cast<const __half2 *>(&qc.x)), c1 = __half22float2(*reinterpret_cast<const __half2 *>(&qc.y));
+                v.x = __fmul_rn(__fadd_rn(__fadd_rn(a0.x, b0.x), c0.x), sum_scale);
+                v.y = __fmul_rn(__fadd_rn(__fadd_rn(a0.y, b0.y), c0.y), sum_scale);
+                v.z = __fmul_rn(__fadd_rn(__fadd_rn(a1.x, b1.x), c1.x), sum_scale);
+                v.w = __fmul_rn(__fadd_rn(__fadd_rn(a1.y, b1.y), c1.y), sum_scale);
+            }
+        } else if (t >= 0 && t < seg_len) {
             v = *reinterpret_cast<const float4 *>(x + (row0 + t) * C + c4);
             if (x2) {
                 // branch sum / average of the last MRF stage (hifigan.cpp:300-315), same order as the reference
@@ -527,7 +583,7 @@ __global__ void __launch_bounds__(128) out_conv_32x7_kernel(const float *__restr
     store_sample(tanhf(__fadd_rn(__fadd_rn(acc0, acc1), W.bias)), row0 + t, wav, pcm);
 }
 
-cudaError_t out_conv_launch(const float *x, const float *x2, const float *x3, const __half *x16, float sum_scale, int C, int K, const __half *w_raw, const float *bias, const float *w_host_kc,
+cudaError_t out_conv_launch(const float *x, const float *x2, const float *x3, const __half *x16, int halves, float sum_scale, int C, int K, const __half *w_raw, const float *bias, const float *w_host_kc,
                             float bias_host, float slope, const int *seg_start, const int *tile_start, int B, int rate,
                             int total_tiles, float *wav, int16_t *pcm, cudaStream_t st)
 {
@@ -535,12 +591,12 @@ cudaError_t out_conv_launch(const float *x, const float *x2, const float *x3, co
         OutConvW W;
         for (int i = 0; i < 7 * 32; ++i) W.w[i] = w_host_kc[i];
         W.bias = bias_host;
-        out_conv_32x7_kernel<<<total_tiles, 128, 0, st>>>(x, x2, x3, x16, sum_scale, W, slope, seg_start, tile_start, B, rate, wav, pcm);
+        out_conv_32x7_kernel<<<total_tiles, 128, 0, st>>>(x, x2, x3, x16, halves, sum_scale, W, slope, seg_start, tile_start, B, rate, wav, pcm);
         return cudaGetLastError();
     }
     if (C > OC_MAX_C || K > OC_MAX_K) return cudaErrorInvalidValue;
     const size_t smem = (OC_MAX_K * OC_MAX_C + (128 + OC_MAX_K) * (OC_MAX_C + 1)) * sizeof(float);
-    out_conv_kernel<<<total_tiles, 128, smem, st>>>(x, x2, x3, x16, sum_scale, C, K, w_raw, bias, slope, seg_start, tile_start, B, rate, wav, pcm);
+    out_conv_kernel<<<total_tiles, 128, smem, st>>>(x, x2, x3, x16, halves, sum_scale, C, K, w_raw, bias, slope, seg_start, tile_start, B, rate, wav, pcm);
     return cudaGetLastError();
 }
 

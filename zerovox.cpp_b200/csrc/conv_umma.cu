@@ -129,6 +129,48 @@ __device__ __forceinline__ void produce_chunk(const ConvParams &p, const TileCoo
                 if (rho0 + q * rstep < need_rows)
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst[q]), "l"(src[q]), "r"(nbytes[q]) : "memory");
         }
+    } else if (MODE == PRO_SUM3H) {
+        // three fp16 sources per element (branch outputs of the fused MRF blocks): 4 rows x 3 x 16 bytes in flight
+        const __half *h1 = reinterpret_cast<const __half *>(p.x), *h2 = reinterpret_cast<const __half *>(p.x2),
+                     *h3 = reinterpret_cast<const __half *>(p.x3);
+        for (int rho0 = r0; rho0 < need_rows; rho0 += 4 * rstep) {
+            uint4 q[4][3];
+            bool ok[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int rho  = rho0 + k * rstep;
+                const int t_in = tc.t0 + p.tap_off0 + rho;
+                ok[k] = rho < need_rows && t_in >= 0 && t_in < tc.seg_len;
+                const size_t e = (tc.seg_row0 + (size_t)(ok[k] ? t_in : 0)) * (size_t)p.ldx + p.x_ch_off + ch;
+                if (ok[k]) {
+                    q[k][0] = *reinterpret_cast<const uint4 *>(h1 + e);
+                    q[k][1] = *reinterpret_cast<const uint4 *>(h2 + e);
+                    q[k][2] = *reinterpret_cast<const uint4 *>(h3 + e);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int rho = rho0 + k * rstep;
+                if (rho >= need_rows) break;
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                if (ok[k]) {
+                    const uint32_t wa[4] = {q[k][0].x, q[k][0].y, q[k][0].z, q[k][0].w};
+                    const uint32_t wb[4] = {q[k][1].x, q[k][1].y, q[k][1].z, q[k][1].w};
+                    const uint32_t wc[4] = {q[k][2].x, q[k][2].y, q[k][2].z, q[k][2].w};
+                    uint32_t o[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&wa[i]));
+                        const float2 b = __half22float2(*reinterpret_cast<const __half2 *>(&wb[i]));
+                        const float2 c = __half22float2(*reinterpret_cast<const __half2 *>(&wc[i]));
+                        o[i] = pack_half2(lrelu_f(__fmul_rn(__fadd_rn(__fadd_rn(a.x, b.x), c.x), p.sum_scale), p.pro_slope),
+                                          lrelu_f(__fmul_rn(__fadd_rn(__fadd_rn(a.y, b.y), c.y), p.sum_scale), p.pro_slope));
+                    }
+                    v = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+                *reinterpret_cast<uint4 *>(dstp + (size_t)rho * 16) = v;
+            }
+        }
     } else if (MODE == PRO_SUM3) {
         // three fp32 sources per element: smaller batches (2 rows x 3 sources x 2 float4 in flight)
         const float *x1 = reinterpret_cast<const float *>(p.x);
@@ -955,6 +997,7 @@ cudaError_t conv_umma_pk_launch(const ConvParams &p, int total_tiles, int num_sm
         case PRO_NORM:  return launch_pk<PRO_NORM>(p, total_tiles, num_sms, smem, st);
         case PRO_MEL:   return launch_pk<PRO_MEL>(p, total_tiles, num_sms, smem, st);
         case PRO_SUM3:  return launch_pk<PRO_SUM3>(p, total_tiles, num_sms, smem, st);
+        case PRO_SUM3H: return launch_pk<PRO_SUM3H>(p, total_tiles, num_sms, smem, st);
     }
     return cudaErrorInvalidValue;
 }
@@ -1052,6 +1095,7 @@ cudaError_t conv_umma_init()
     if ((e = init_mode<PRO_NORM>()) != cudaSuccess) return e;
     if ((e = init_mode<PRO_MEL>()) != cudaSuccess) return e;
     if ((e = init_mode<PRO_SUM3>()) != cudaSuccess) return e;
+    if ((e = init_mode<PRO_SUM3H>()) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
@@ -1072,6 +1116,7 @@ cudaError_t conv_umma_launch(const ConvParams &p, int total_tiles, size_t smem, 
         case PRO_NORM:  return launch_mt<PRO_NORM>(p, total_tiles, smem, st);
         case PRO_MEL:   return launch_mt<PRO_MEL>(p, total_tiles, smem, st);
         case PRO_SUM3:  return launch_mt<PRO_SUM3>(p, total_tiles, smem, st);
+        case PRO_SUM3H: return launch_mt<PRO_SUM3H>(p, total_tiles, smem, st);
     }
     return cudaErrorInvalidValue;
 }

@@ -123,6 +123,7 @@ struct zvx_ctx {
     int conv_tma = 1;       // PRO_F16 operands of the one-tile conv kernel staged by TMA (cp.async.bulk.tensor) instead of cp.async
     int conv_cluster = 1;   // CTAs per cluster of the one-tile conv kernel sharing every weight stage by multicast; measured on
                             // B200 (profiles/r02_conv_cluster_ab.txt): 2 -> +7 %, 4 -> +19 % time on the decoder convs, so off
+    int branch_f16 = 0; // fused MRF blocks write their outputs as fp16, the consumer sums three fp16 tensors (see run_vocoder)
     int conv_epi8 = 1;  // see run_conv
     int conv_pair = 0;  // PRO_F16 convs of the one-tile kernel as tcgen05 CTA pairs (M = 256, half a weight stage per SM)
     int conv_mt2 = 0;   // two M-tiles per CTA: measured slower on B200 while the A producer is the limit (profiles/)
@@ -806,7 +807,7 @@ struct ConvCall {
     const ConvLayer *L = nullptr;
     int variant = 0;
     const void *x = nullptr; int ldx = 0, x_ch_off = 0;
-    const float *x2 = nullptr, *x3 = nullptr; float sum_scale = 0.f;   // PRO_SUM3
+    const float *x2 = nullptr, *x3 = nullptr; float sum_scale = 0.f; bool sum3_half = false;   // PRO_SUM3 (sum3_half: fp16 sources)
     int rate_idx = 0;          // index into ctx->rates of the INPUT rate
     int pro_mode = PRO_CVT; float pro_slope = 0.f;
     const float *mu = nullptr, *rstd = nullptr; int stat_stride = 0;
@@ -837,7 +838,7 @@ int run_conv(zvx_ctx *ctx, const ConvCall &cc)
     p.ntaps = v.ntaps; p.tap_off0 = v.tap_off0; p.tap_step = v.tap_step;
     p.w_packed = v.packed; p.w_raw = L.raw; p.w_taps_total = L.K; p.w_tap0 = v.w_tap0; p.w_tap_stride = v.w_tap_stride;
     p.Cout = L.OC; p.NC = L.NC;
-    p.pro_mode = cc.pro_mode; p.pro_slope = cc.pro_slope;
+    p.pro_mode = (cc.pro_mode == PRO_SUM3 && cc.sum3_half) ? PRO_SUM3H : cc.pro_mode; p.pro_slope = cc.pro_slope;
     p.p_mu = cc.mu; p.p_rstd = cc.rstd; p.p_stat_stride = cc.stat_stride;
     p.p_g = cc.g; p.p_b = cc.b; p.p_gb_stride = cc.gb_stride;
     p.bias = cc.use_bias ? L.bias : nullptr;
@@ -1104,6 +1105,7 @@ int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out, int16_t *pcm_
     }
     const float *vin = ctx->v0, *vin2 = nullptr, *vin3 = nullptr;   // vin2/vin3: stage output still split in 3 branches
     const __half *vin16 = nullptr;                                  // stage output handed over as ONE ready-made fp16 operand
+    bool vin_half = false;                                          // vin / vin2 / vin3 are fp16 tensors (ZVX_BRANCH_F16)
     float *vout[2] = {ctx->VA, ctx->VB};
     const float third = (float)(1.0 / (float)nb);
     const bool fork_ok = ctx->fork_branches && ctx->fork_stream[0] && ctx->fkY1[0] && !ctx->prof && ctx->debug_stop < 0 && !ctx->use_ref_kernels;
@@ -1122,7 +1124,7 @@ int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out, int16_t *pcm_
             ConvCall u; u.kind = ZVX_K_UPCONV; u.stage = i; u.L = &ctx->upf[i]; u.x = vin; u.ldx = cin; u.rate_idx = i;
             u.pro_mode = PRO_LRELU; u.pro_slope = 0.1f; u.out32 = ctx->U; u.ldo32 = s * ch; u.out_mul = 1;
             if (vin16) { u.x = vin16; u.pro_mode = PRO_F16; }
-            else if (vin2) { u.pro_mode = PRO_SUM3; u.x2 = vin2; u.x3 = vin3; u.sum_scale = third; }
+            else if (vin2) { u.pro_mode = PRO_SUM3; u.x2 = vin2; u.x3 = vin3; u.sum_scale = third; u.sum3_half = vin_half; }
             u.flops = 2.0 * (double)ctx->last_frames * ctx->rates[i] * s * ch * cin * (ctx->up[i].K / s);
             if (chain) { u.out16 = ctx->U16; u.ldo16 = s * ch; u.out16_slope = 0.1f; }
             if (run_conv(ctx, u)) return 1;
@@ -1133,7 +1135,11 @@ int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out, int16_t *pcm_
                 const size_t n = (size_t)ctx->last_frames * ctx->rates[i] * cin;
                 ctx->launches++;
                 if (prof_begin(ctx, ZVX_K_NORM_AFFINE, i, 0.0, 14.0 * (double)n)) return 1;
-                CK(ctx, sum3_act_f16_launch(vin, vin2, vin3, third, 0.1f, n, ctx->H16, ctx->stream));
+                if (vin_half)
+                    CK(ctx, sum3h_act_f16_launch(reinterpret_cast<const __half *>(vin), reinterpret_cast<const __half *>(vin2),
+                                                 reinterpret_cast<const __half *>(vin3), third, 0.1f, n, ctx->H16, ctx->stream));
+                else
+                    CK(ctx, sum3_act_f16_launch(vin, vin2, vin3, third, 0.1f, n, ctx->H16, ctx->stream));
                 if (prof_end(ctx)) return 1;
             }
             // the s output phases are independent launches (disjoint rows of U): dealt round-robin to the three streams
@@ -1146,7 +1152,7 @@ int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out, int16_t *pcm_
                 u.pro_mode = PRO_LRELU; u.pro_slope = 0.1f; u.out32 = ctx->U; u.ldo32 = ch; u.out_mul = s;
                 if (vin16) { u.x = vin16; u.pro_mode = PRO_F16; }
                 else if (pre) { u.x = ctx->H16; u.pro_mode = PRO_F16; }
-                else if (vin2) { u.pro_mode = PRO_SUM3; u.x2 = vin2; u.x3 = vin3; u.sum_scale = third; }
+                else if (vin2) { u.pro_mode = PRO_SUM3; u.x2 = vin2; u.x3 = vin3; u.sum_scale = third; u.sum3_half = vin_half; }
                 if (chain) { u.out16 = ctx->U16; u.ldo16 = ch; u.out16_slope = 0.1f; }
                 const int lane_id = fork_ok ? phi % 3 : 0;
                 if (lane_id > 0) {
@@ -1175,6 +1181,10 @@ int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out, int16_t *pcm_
         // other blocks, sums the three outputs in the reference's order and emits the consumer's fp16 operand
         bool handoff = split && ctx->stage_handoff && ctx->S16[0] && ctx->use_fused && ctx->debug_stop < 0;
         for (int j = 0; j < nb; ++j) handoff = handoff && ctx->fused[(size_t)i * nb + j].CH != 0;
+        // fp16 branch outputs: every block of the stage is a fused chain -> its final phase writes y_j as fp16 and the consumer
+        // sums three fp16 tensors (6 instead of 12 bytes per element; the sum is rounded to fp16 right after anyway)
+        bool half_out = split && ctx->branch_f16 && !handoff && ctx->use_fused && ctx->debug_stop < 0;
+        for (int j = 0; j < nb; ++j) half_out = half_out && ctx->fused[(size_t)i * nb + j].CH != 0;
         const FusedChain *deferred = nullptr;
         const float *deferred_yin = nullptr;
         int deferred_CH = 0, deferred_ncol = 0;
@@ -1230,6 +1240,9 @@ int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out, int16_t *pcm_
                     fp.err_flag = ctx->d_err;
                     if (!lastc) {
                         fp.out = tmp[q & 1];
+                    } else if (split && half_out) {
+                        fp.out16 = reinterpret_cast<uint16_t *>(branch_out[j]);     // y_j as fp16; summed by the consumer
+                        fp.out16_slope = 1.0f;                                       // max(x, 1 * x) = x
                     } else if (split) {
                         fp.out = branch_out[j];                        // y_j; summed by the consumer
                     } else if (j == 0 && nb > 1) {
@@ -1244,7 +1257,7 @@ int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out, int16_t *pcm_
                     if (prof_begin(ctx, ZVX_K_MRF_CONV, i, rows * fc.flops_per_row, 0.0)) return 1;
                     CK(ctx, mrf_fused_launch(fb.CH, fp, ctx->total_wins[fc.wincfg], ctx->stream));
                     if (prof_end(ctx)) return 1;
-                    yin = fp.out;
+                    yin = fp.out;                                      // (only chains that are not the last feed another one)
                 }
                 continue;
             }
@@ -1305,8 +1318,9 @@ int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out, int16_t *pcm_
             if (prof_end(ctx)) return 1;
             vin = vin2 = vin3 = nullptr;
             vin16 = ctx->S16[i & 1];
-        } else if (split) { vin = branch_out[0]; vin2 = branch_out[1]; vin3 = branch_out[2]; vin16 = nullptr; ctx->stage_is_split[i] = 1; }
-        else { vin = vout[i & 1]; vin2 = vin3 = nullptr; vin16 = nullptr; }
+            vin_half = false;
+        } else if (split) { vin = branch_out[0]; vin2 = branch_out[1]; vin3 = branch_out[2]; vin16 = nullptr; vin_half = half_out; ctx->stage_is_split[i] = half_out ? 2 : 1; }
+        else { vin = vout[i & 1]; vin2 = vin3 = nullptr; vin16 = nullptr; vin_half = false; }
     }
     if (ctx->debug_stop >= 0) return 0;
     // leaky_relu(0.01) -> output_conv -> tanh (hifigan.cpp:324-345)
@@ -1318,7 +1332,7 @@ int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out, int16_t *pcm_
                        rows * (ctx->chans[last] + 1) * sizeof(float)))
             return 1;
     }
-    CK(ctx, out_conv_launch(vin, vin2, vin3, vin16, third, ctx->chans[last], ctx->output_conv.K, ctx->output_conv.raw, ctx->output_conv.bias,
+    CK(ctx, out_conv_launch(vin, vin2, vin3, vin16, vin_half ? 1 : 0, third, ctx->chans[last], ctx->output_conv.K, ctx->output_conv.raw, ctx->output_conv.bias,
                             ctx->out_w_kc.empty() ? nullptr : ctx->out_w_kc.data(), ctx->out_b_host, 0.01f,
                             ctx->d_seg, ctx->d_tiles + (size_t)last * (ctx->cap_batch + 1), ctx->last_B, ctx->rates[last],
                             ctx->total_tiles[last], wav_out, pcm_out, ctx->stream));
@@ -1523,6 +1537,7 @@ int zvx_create(zvx_ctx **out, const zvx_config *cfg, const zvx_tensor_desc *weig
     if (const char *e = getenv("ZVX_CONV_TMA")) ctx->conv_tma = atoi(e);
     if (const char *e = getenv("ZVX_CONV_PAIR")) ctx->conv_pair = atoi(e);
     if (const char *e = getenv("ZVX_CONV_EPI8")) ctx->conv_epi8 = atoi(e);
+    if (const char *e = getenv("ZVX_BRANCH_F16")) ctx->branch_f16 = atoi(e);
     if (const char *e = getenv("ZVX_MRF_F16_CHAIN")) ctx->mrf_f16_chain = atoi(e);
     if (const char *e = getenv("ZVX_FUSED_STATS")) ctx->fused_stats = atoi(e);
     if (const char *e = getenv("ZVX_STAGE_HANDOFF")) ctx->stage_handoff = atoi(e);
@@ -2184,6 +2199,15 @@ int zvx_debug_fetch(zvx_ctx *ctx, const char *what, float *dst, int64_t n)
             // the stage output is still split into its three branches: combine like the consumer does
             if (n > have) return fail(ctx, "debug tensor '%s' has %lld floats, asked for %lld", what, (long long)have, (long long)n);
             CK(ctx, cudaStreamSynchronize(ctx->stream));
+            if (ctx->stage_is_split[i] == 2) {           // fp16 branch tensors
+                std::vector<__half> h0((size_t)n), h1((size_t)n), h2((size_t)n);
+                CK(ctx, cudaMemcpy(h0.data(), ctx->CS, sizeof(__half) * n, cudaMemcpyDeviceToHost));
+                CK(ctx, cudaMemcpy(h1.data(), ctx->VA, sizeof(__half) * n, cudaMemcpyDeviceToHost));
+                CK(ctx, cudaMemcpy(h2.data(), ctx->VB, sizeof(__half) * n, cudaMemcpyDeviceToHost));
+                const float third = (float)(1.0 / 3.0);
+                for (int64_t q = 0; q < n; ++q) dst[q] = ((__half2float(h0[q]) + __half2float(h1[q])) + __half2float(h2[q])) * third;
+                return 0;
+            }
             std::vector<float> b1((size_t)n), b2((size_t)n);
             CK(ctx, cudaMemcpy(dst, ctx->CS, sizeof(float) * n, cudaMemcpyDeviceToHost));
             CK(ctx, cudaMemcpy(b1.data(), ctx->VA, sizeof(float) * n, cudaMemcpyDeviceToHost));

@@ -27,6 +27,7 @@ enum ProMode : int {
     PRO_LRELU = 2,   // leaky_relu(x, slope) -> fp16              (hifigan.cpp:108,281,324)
     PRO_NORM  = 3,   // ((x-mu)*rstd)*g + b -> leaky_relu(slope)  (stylettsdec.cpp:94-104,191-197,253)
     PRO_MEL   = 4,   // (x - mean) / scale                        (hifigan.cpp:242-243)
+    PRO_SUM3H = 6,   // PRO_SUM3 with fp16 sources (own kernel instantiation: the fp32 variant's register budget decides its occupancy)
     PRO_SUM3  = 5,   // leaky_relu(((x + x2) + x3) * sum_scale, slope): the MRF branch sum / average of
                      // hifigan.cpp:300-315 applied by the CONSUMER of the three residual-block outputs
 };

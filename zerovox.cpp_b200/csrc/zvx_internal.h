@@ -63,6 +63,8 @@ cudaError_t norm_act_f16_launch(const float *x, int ldx, int ch_off, int C, cons
 
 cudaError_t sum3_act_f16_launch(const float *a, const float *b, const float *c, float scale, float slope, size_t n, __half *y16,
                                 cudaStream_t st);
+cudaError_t sum3h_act_f16_launch(const __half *a, const __half *b, const __half *c, float scale, float slope, size_t n, __half *y16,
+                                 cudaStream_t st);
 cudaError_t length_regulate_launch(const float *feat, const int2 *tab, int n_phonemes, int D, float *out, cudaStream_t st);
 cudaError_t cvt_f16_launch(const float *x, int ldx, int ch_off, int C, size_t rows, __half *y16, cudaStream_t st);
 
@@ -70,7 +72,8 @@ cudaError_t cvt_f16_launch(const float *x, int ldx, int ch_off, int C, size_t ro
 // w_host_kc: host copy of the weights as fp32 [K][C] (constant-bank fast path for C = 32, K = 7), may be null
 // x2 / x3 non-null: input = ((x + x2) + x3) * sum_scale (MRF branch average applied by the consumer)
 // x16 non-null: the input arrives averaged, activated and rounded to fp16 (stage hand-off of the fused MRF kernel)
-cudaError_t out_conv_launch(const float *x, const float *x2, const float *x3, const __half *x16, float sum_scale, int C, int K, const __half *w_raw, const float *bias, const float *w_host_kc,
+// halves != 0: x / x2 / x3 point to fp16 tensors (branch outputs written as fp16 by the fused MRF blocks)
+cudaError_t out_conv_launch(const float *x, const float *x2, const float *x3, const __half *x16, int halves, float sum_scale, int C, int K, const __half *w_raw, const float *bias, const float *w_host_kc,
                             float bias_host, float slope, const int *seg_start, const int *tile_start, int B, int rate,
                             int total_tiles, float *wav, int16_t *pcm, cudaStream_t st);
 
