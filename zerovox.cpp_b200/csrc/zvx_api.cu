@@ -126,6 +126,7 @@ struct zvx_ctx {
     int branch_f16 = 0; // fused MRF blocks write their outputs as fp16, the consumer sums three fp16 tensors (see run_vocoder)
     int conv_epi8 = 1;  // see run_conv
     int conv_pair = 0;  // PRO_F16 convs of the one-tile kernel as tcgen05 CTA pairs (M = 256, half a weight stage per SM)
+    int upconv_mt2 = 1; // two M-tiles per CTA for up-convs with NC <= 96 (ZVX_UPCONV_MT2)
     int conv_mt2 = 0;   // two M-tiles per CTA: measured slower on B200 while the A producer is the limit (profiles/)
     std::vector<int> tile256_cfg;                 // per rate index: wincfg entry of the 256-row tiling
     int num_sms = 148;
@@ -853,7 +854,10 @@ int run_conv(zvx_ctx *ctx, const ConvCall &cc)
     int tiles = ctx->total_tiles[cc.rate_idx];
     // two M-tiles per CTA (each weight stage feeds 256 rows) whenever that still fills the GPU
     p.mt = 1;
-    if (!ctx->use_ref_kernels && ctx->conv_mt2 && cc.rate_idx < (int)ctx->tile256_cfg.size() &&
+    // (measured per launch kind, profiles/r02_ab_conv_epilogue_and_pairs.txt: it pays only for the narrow up-conv of the last stage --
+    //  NC = 96, two taps, a streaming kernel whose per-CTA set-up is a third of a CTA's life -- and costs 17-36 % elsewhere)
+    const bool mt2_here = ctx->conv_mt2 || (ctx->upconv_mt2 && cc.kind == ZVX_K_UPCONV && L.NC <= 96);
+    if (!ctx->use_ref_kernels && mt2_here && cc.rate_idx < (int)ctx->tile256_cfg.size() &&
         (int64_t)tiles * (L.OC / L.NC) >= (int64_t)3 * ctx->num_sms) {
         const int w = ctx->tile256_cfg[cc.rate_idx];
         p.mt = 2;
@@ -1533,6 +1537,7 @@ int zvx_create(zvx_ctx **out, const zvx_config *cfg, const zvx_tensor_desc *weig
     if (const char *e = getenv("ZVX_DEC_PREPASS")) ctx->dec_prepass = atoi(e);
     if (const char *e = getenv("ZVX_BRANCH_SUM_IN_CONSUMER")) ctx->branch_sum_in_consumer = atoi(e);
     if (const char *e = getenv("ZVX_CONV_MT2")) ctx->conv_mt2 = atoi(e);
+    if (const char *e = getenv("ZVX_UPCONV_MT2")) ctx->upconv_mt2 = atoi(e);
     if (const char *e = getenv("ZVX_CONV_CLUSTER")) ctx->conv_cluster = atoi(e);
     if (const char *e = getenv("ZVX_CONV_TMA")) ctx->conv_tma = atoi(e);
     if (const char *e = getenv("ZVX_CONV_PAIR")) ctx->conv_pair = atoi(e);
