@@ -528,35 +528,55 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
                         tmem_ld_16x256b_x8_nowait(tmem_base + ((uint32_t)(quarter * 32 + 16) << 16) + acc_col + (uint32_t)colw, r1);
                         tmem_wait_ld();
                         if (has_next) publish();
-                        const ptrdiff_t base = ((ptrdiff_t)w.row0 + tw) * CH + c4;
+                        // time of this thread's column i: tau0 + S * (8 (i / 2) + (i & 1)); inside the window's valid range and
+                        // the utterance iff tau - lo < span (one unsigned compare, addresses = one pointer + constants)
+                        const int tau0 = S * (colw + 2 * (lane & 3)) + sQ;
+                        const int lo = p.halo;
+                        const unsigned span = (unsigned)(min(p.halo + p.valid, T - tw) - lo);
+                        const ptrdiff_t base = ((ptrdiff_t)w.row0 + tw + tau0) * CH + c4;
+                        if (p.out && !p.out16 && !p.acc_in && !p.has_scale) {
+                            // the common case: y (+ bias) leaves as fp32, nothing else
+                            float *oq = p.out + base;
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                const int dt = S * (8 * (i >> 1) + (i & 1));
+                                if ((unsigned)(tau0 + dt - lo) < span) {
+                                    const int i0 = 4 * (i >> 1) + (i & 1);
+                                    *reinterpret_cast<float4 *>(oq + dt * CH) =
+                                        make_float4(__fadd_rn(__uint_as_float(r0[i0]), b4.x), __fadd_rn(__uint_as_float(r0[i0 + 2]), b4.y),
+                                                    __fadd_rn(__uint_as_float(r1[i0]), b4.z), __fadd_rn(__uint_as_float(r1[i0 + 2]), b4.w));
+                                }
+                            }
+                        } else {
                         float *oq = p.out ? p.out + base : nullptr;
                         uint16_t *hq = p.out16 ? p.out16 + base : nullptr;
                         const float *aq = p.acc_in ? p.acc_in + base : nullptr;
                         const float *aq2 = p.acc_in2 ? p.acc_in2 + base : nullptr;
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
-                            const int tau = S * (colw + 8 * (i >> 1) + 2 * (lane & 3) + (i & 1)) + sQ;
-                            if (tau >= p.halo && tau < p.halo + p.valid && tw + tau < T) {
+                            const int dt = S * (8 * (i >> 1) + (i & 1));
+                            if ((unsigned)(tau0 + dt - lo) < span) {
                                 const int i0 = 4 * (i >> 1) + (i & 1);
                                 float4 v = make_float4(__fadd_rn(__uint_as_float(r0[i0]), b4.x), __fadd_rn(__uint_as_float(r0[i0 + 2]), b4.y),
                                                        __fadd_rn(__uint_as_float(r1[i0]), b4.z), __fadd_rn(__uint_as_float(r1[i0 + 2]), b4.w));
                                 if (aq) {
-                                    float4 a = *reinterpret_cast<const float4 *>(aq + (size_t)tau * CH);
+                                    float4 a = *reinterpret_cast<const float4 *>(aq + dt * CH);
                                     if (aq2) {       // (y_0 + y_1) + y_2: the reference's order (hifigan.cpp:300-311)
-                                        const float4 a2 = *reinterpret_cast<const float4 *>(aq2 + (size_t)tau * CH);
+                                        const float4 a2 = *reinterpret_cast<const float4 *>(aq2 + dt * CH);
                                         a = make_float4(__fadd_rn(a.x, a2.x), __fadd_rn(a.y, a2.y), __fadd_rn(a.z, a2.z), __fadd_rn(a.w, a2.w));
                                     }
                                     v = make_float4(__fadd_rn(a.x, v.x), __fadd_rn(a.y, v.y), __fadd_rn(a.z, v.z), __fadd_rn(a.w, v.w));
                                 }
                                 if (p.has_scale) v = make_float4(__fmul_rn(v.x, p.scale), __fmul_rn(v.y, p.scale), __fmul_rn(v.z, p.scale), __fmul_rn(v.w, p.scale));
-                                if (oq) *reinterpret_cast<float4 *>(oq + (size_t)tau * CH) = v;
+                                if (oq) *reinterpret_cast<float4 *>(oq + dt * CH) = v;
                                 if (hq) {
                                     uint2 h;
                                     h.x = pack_h2(lrelu_max(v.x, p.out16_slope), lrelu_max(v.y, p.out16_slope));
                                     h.y = pack_h2(lrelu_max(v.z, p.out16_slope), lrelu_max(v.w, p.out16_slope));
-                                    *reinterpret_cast<uint2 *>(hq + (size_t)tau * CH) = h;
+                                    *reinterpret_cast<uint2 *>(hq + dt * CH) = h;
                                 }
                             }
+                        }
                         }
                     } else {
                     const float bias = __ldg(L.bias + oc);
