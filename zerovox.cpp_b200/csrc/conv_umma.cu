@@ -680,18 +680,10 @@ __global__ void __launch_bounds__(conv_threads(MT)) conv_umma_kernel(const ConvP
                     // b_empty counts the commits of ALL CTAs of the cluster: the share goes into every peer's stage
                     mbar_wait(smem_u32(b_empty + sb), phb ^ 1u, p.err_flag);
                     if (PAIR) {
-                        // this CTA's NC / 2 output channels of every 8-channel K group (a packed block is [group][NC][8])
-                        const uint32_t seg = (uint32_t)NB * 16u;
-                        const int groups = min(KCHUNK, Cin - c * KCHUNK) >> 3;
-                        mbar_arrive_expect_tx(smem_u32(b_full + sb), (uint32_t)groups * seg);
-#ifdef ZVX_WHATIF_PAIR_ONECOPY
-                        // timing experiment only (wrong results): the half as ONE contiguous copy
-                        bulk_copy_g2s(b_base + sb * b_stage_bytes, src + crank * (uint32_t)groups * seg, (uint32_t)groups * seg, smem_u32(b_full + sb));
-#else
-                        for (int g = 0; g < groups; ++g)
-                            bulk_copy_g2s(b_base + sb * b_stage_bytes + (uint32_t)g * seg, src + (size_t)g * (2u * seg) + crank * seg, seg,
-                                          smem_u32(b_full + sb));
-#endif
+                        // this CTA's half of the block (p.w_packed is the pair layout: [half][group][NC / 2][8]): one copy
+                        const uint32_t half_bytes = bytes / 2u;
+                        mbar_arrive_expect_tx(smem_u32(b_full + sb), half_bytes);
+                        bulk_copy_g2s(b_base + sb * b_stage_bytes, src + crank * half_bytes, half_bytes, smem_u32(b_full + sb));
                         if (++sb == b_stages) { sb = 0; phb ^= 1u; }
                         continue;
                     }

@@ -35,6 +35,7 @@ struct DevTensor {
 
 struct ConvVariant {
     __half *packed = nullptr;
+    __half *packed_pair = nullptr;   // the same blocks with each CTA's half of the output channels contiguous (CTA-pair kernel), or null
     int ntaps = 0, w_tap0 = 0, w_tap_stride = 1, tap_off0 = 0, tap_step = 1, out_add = 0;
 };
 
@@ -271,6 +272,26 @@ int pack_variant(zvx_ctx *ctx, const std::vector<__half> &raw, int OC, int IC, i
         }
     if (dev_alloc(ctx, &v.packed, pk.size())) return 1;
     CK(ctx, cudaMemcpy(v.packed, pk.data(), pk.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    // CTA pairs (conv_umma.cu, PAIR): CTA r of a pair holds output channels [r NC/2, (r+1) NC/2) of every block; laid out
+    // [half][kc/8][NC/2][8] its share of a weight stage is ONE bulk copy (8 copies of 1.4 KB per stage made the loader the limit)
+    if (ctx->conv_pair && NC % 16 == 0 && NC >= 32 && (int64_t)IC * v.ntaps >= 512) {
+        std::vector<__half> pp(pk.size());
+        size_t o2 = 0, blk = 0;
+        for (int n = 0; n < OC / NC; ++n)
+            for (int c0 = 0; c0 < IC; c0 += 64) {
+                const int kc = std::min(64, IC - c0);
+                for (int a = 0; a < v.ntaps; ++a) {
+                    for (int r = 0; r < 2; ++r)
+                        for (int g = 0; g < kc / 8; ++g)
+                            for (int nn = 0; nn < NC / 2; ++nn)
+                                for (int e = 0; e < 8; ++e)
+                                    pp[o2++] = pk[blk + ((size_t)g * NC + (size_t)r * (NC / 2) + nn) * 8 + e];
+                    blk += (size_t)kc * NC;
+                }
+            }
+        if (dev_alloc(ctx, &v.packed_pair, pp.size())) return 1;
+        CK(ctx, cudaMemcpy(v.packed_pair, pp.data(), pp.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    }
     return 0;
 }
 
@@ -882,11 +903,12 @@ int run_conv(zvx_ctx *ctx, const ConvCall &cc)
             // a second epilogue warp per lane quarter where the epilogue is a large share of a CTA's life and the launch
             // is not bound by the number of co-resident CTAs (measured per launch kind, profiles/r02_ab_conv_epilogue.txt)
             p.epi8 = ctx->conv_epi8 && p.mt == 1 && (cc.kind == ZVX_K_DEC_CONV || (cc.kind == ZVX_K_UPCONV && L.NC >= 128));
-            p.pair = ctx->conv_pair && p.use_tma && p.mt == 1 && tiles >= 2 && (int64_t)L.IC * v.ntaps >= 512;
+            p.pair = ctx->conv_pair && cc.kind == ZVX_K_DEC_CONV && v.packed_pair && p.use_tma && p.mt == 1 && tiles >= 2;
             p.tma_row0 = 0;
             p.tma_rows = (long long)ctx->last_frames * p.rate_in;
             const size_t smem = conv_umma_plan(p, p.mt == 2 ? 226 * 1024 : (size_t)ctx->conv_smem_kb * 1024);
             if (smem > 227 * 1024) return fail(ctx, "conv needs %zu bytes of shared memory", smem);
+            if (p.pair) p.w_packed = v.packed_pair;          // (conv_umma_plan clears the flag when the launch does not qualify)
             p.cluster = 1;
             if (ctx->conv_cluster > 1 && tiles >= 2 * ctx->conv_cluster && (int64_t)L.IC * v.ntaps >= 512) {
                 p.cluster = ctx->conv_cluster;
