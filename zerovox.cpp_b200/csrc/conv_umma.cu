@@ -39,7 +39,6 @@ namespace zvx {
 
 constexpr int TILE_M      = 128;
 constexpr int KCHUNK      = 64;
-constexpr int MAX_MT      = 2;
 constexpr int MAX_A_STAGES = 4;
 constexpr int MAX_B_STAGES = 8;
 constexpr int SMEM_HEADER  = 384;

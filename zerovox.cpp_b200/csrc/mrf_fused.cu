@@ -76,30 +76,6 @@ __device__ __forceinline__ void tmem_ld_16x256b_x8(uint32_t taddr, uint32_t (&r)
     tmem_ld_16x256b_x8_nowait(taddr, r);
     tmem_wait_ld();
 }
-__device__ __forceinline__ void tmem_st_16x256b_x8(uint32_t taddr, const uint32_t (&r)[32])
-{
-    asm volatile(
-        "tcgen05.st.sync.aligned.16x256b.x8.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
-        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
-        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
-        "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
-        "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-        : "memory");
-}
-
-// 16 lanes x 32 columns (column groups cg = 0..3), same per-thread layout as the x8 form
-__device__ __forceinline__ void tmem_st_16x256b_x4(uint32_t taddr, const uint32_t (&r)[16])
-{
-    asm volatile(
-        "tcgen05.st.sync.aligned.16x256b.x4.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
-        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
-        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-        : "memory");
-}
-
 // 16 lanes x 16 columns (column groups cg = 0..1)
 __device__ __forceinline__ void tmem_st_16x256b_x2(uint32_t taddr, const uint32_t (&r)[8])
 {
@@ -397,7 +373,8 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
         };
 
         // -DZVX_FUSED_PHASES + flags bit 1: cycle counts per phase of CTA 0 / warp 0, printed at exit
-        long long c_pro = 0, c_wait = 0, c_drain = 0, c_final = 0, c_t0 = dbg ? clock64() : 0, c_a = 0;
+        long long c_pro = 0, c_wait = 0, c_drain = 0, c_final = 0, c_a = 0;
+        [[maybe_unused]] const long long c_t0 = dbg ? clock64() : 0;
         int iter = 0;
         int win = blockIdx.x;
         Win wnext = {0, 0, 0, false};

@@ -399,7 +399,7 @@ int make_upconv_fused(zvx_ctx *ctx, HostW &hw, const std::string &prefix, int s,
     }
     F.OC = OCF; F.IC = L.IC; F.K = KF; F.NC = pick_nc(OCF);
     if (F.NC == 0) return 0;
-    const __half *d_raw; const float *d_bias;
+    const __half *d_raw = nullptr; const float *d_bias = nullptr;
     if (upload_vec(ctx, rf, &d_raw) || upload_vec(ctx, bf, &d_bias)) return 1;
     F.raw = d_raw; F.bias = d_bias;
     ConvVariant fv;
@@ -462,7 +462,7 @@ int build_decoder(zvx_ctx *ctx, HostW &hw)
         for (int k = 1; k <= 2; ++k) {
             const int C = k == 1 ? b.cin : b.cout;
             snprintf(nm, sizeof nm, "_mel_decoder.decode.%d.norm%d.fc", i, k);
-            const float *fw, *fb;
+            const float *fw = nullptr, *fb = nullptr;
             if (f32_ptr(ctx, std::string(nm) + ".w", (int64_t)2 * C * S, &fw) || f32_ptr(ctx, std::string(nm) + ".b", 2 * C, &fb)) return 1;
             AdainDesc &d = ctx->adain.d[ctx->adain.n];
             d.fc_w = fw;
@@ -1413,17 +1413,6 @@ int run_graphed(zvx_ctx *ctx, int kind, int L, F body)
     if (ctx->graphs.size() >= 16) { cudaGraphExecDestroy(ctx->graphs.front().exec); ctx->graphs.erase(ctx->graphs.begin()); }
     ctx->graphs.push_back({kind, L, flags, exec, ctx->launches - l0});
     CK(ctx, cudaGraphLaunch(exec, ctx->stream));
-    return 0;
-}
-
-int ensure_pinned(zvx_ctx *ctx, float **buf, size_t *cap, size_t n)
-{
-    if (n <= *cap) return 0;
-    if (*buf) cudaFreeHost(*buf);
-    *buf = nullptr;
-    *cap = 0;
-    CK(ctx, cudaMallocHost(buf, n * sizeof(float)));
-    *cap = n;
     return 0;
 }
 
