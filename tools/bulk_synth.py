@@ -7,7 +7,10 @@ the GPUs of one box.  Launch with torchrun (one rank per GPU) or plain python fo
 
 Every rank computes the same longest-processing-time-first assignment from the length list alone
 (zerovox.cpp_b200/sharding.py), synthesises its shard in launch batches of <= 256 utterances and <= 36000 frames through the
-host-pointer C ABI (zvx_synth_batch: H2D + decoder + vocoder + D2H), and rank 0 prints one JSON line.
+host-pointer C ABI -- every batch is SUBMITTED (zvx_synth_batch_submit: H2D + decoder + vocoder + D2H enqueued, the copies of
+one batch run under the kernels of its neighbours) and the rank waits once at the end (zvx_synth_batch_wait); the waveforms land
+in one pinned buffer that holds the whole shard -- and rank 0 prints one JSON line.  (`--sync`: one synchronous zvx_synth_batch
+per launch batch, as in round 1.)
 No collective is on the data path; NCCL is used only for the start barrier and the max-over-ranks time."""
 import json
 import os
@@ -25,7 +28,9 @@ from zerovox_cpp_b200 import capi  # noqa: E402
 
 
 def main():
-    n_utt = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    sync_mode = "--sync" in sys.argv
+    n_utt = int(args[0]) if args else 4096
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -46,38 +51,43 @@ def main():
     g = torch.Generator().manual_seed(99 + rank)
     enc_pool = torch.randn(maxL, ctx.dim_in, generator=g).pin_memory().numpy()
     sty = (0.05 * torch.randn(ctx.style_dim, generator=g)).numpy()
-    # pinned output pool, double-buffered so that a consumer could read batch i while batch i+1 is produced
-    wav_pool = [torch.empty(40000 * ctx.hop + maxL * ctx.hop, dtype=torch.float32).pin_memory() for _ in range(2)]
+    # pinned output buffer for the whole shard: every batch's waveforms have their own place, so nothing has to be consumed
+    # before the next batch may be submitted
+    my_frames = int(sum(int(lengths[i]) for i in mine))
+    wav_all = torch.empty(my_frames * ctx.hop, dtype=torch.float32).pin_memory()
     import ctypes
     vp = ctypes.c_void_p
-    turn = [0]
+    keep = []
 
-    def run_batch(idx):
+    def run_batch(idx, frame0, submit):
         B = len(idx)
-        pool = wav_pool[turn[0] & 1]
-        turn[0] += 1
         Ls = [int(lengths[i]) for i in idx]
         offs = np.concatenate([[0], np.cumsum(Ls)]).astype(np.int64)
         pe = (vp * B)(*[enc_pool.ctypes.data] * B)          # every utterance reads a prefix of the same pinned pool
         ps = (vp * B)(*[sty.ctypes.data] * B)
-        pw = (vp * B)(*[pool.data_ptr() + int(offs[b]) * ctx.hop * 4 for b in range(B)])
-        ctx.synth_batch_ptrs(B, pe, ps, (ctypes.c_int32 * B)(*Ls), None, pw)
-        return None, [pool.numpy()[: Ls[0] * ctx.hop]]
+        pw = (vp * B)(*[wav_all.data_ptr() + (frame0 + int(offs[b])) * ctx.hop * 4 for b in range(B)])
+        La = (ctypes.c_int32 * B)(*Ls)
+        if submit:
+            keep.append((pe, ps, pw, La))                    # the arrays must outlive the call (the library reads them at submit)
+            ctx.synth_batch_submit_ptrs(B, pe, ps, La, pw)
+        else:
+            ctx.synth_batch_ptrs(B, pe, ps, La, None, pw)
+        return int(offs[-1])
 
     ctx.reserve(36000 + maxL, 256)
-    run_batch(batches[0])                                   # warm-up (workspace, lanes)
-    run_batch(batches[-1])
+    run_batch(batches[0], 0, False)                          # warm-up (workspace, lanes)
+    run_batch(batches[-1], 0, False)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     frames = 0
-    check = 0.0
     for b in batches:
-        _, wavs = run_batch(b)
-        frames += int(sum(int(lengths[i]) for i in b))
-        check += float(np.abs(wavs[0][::997]).sum())
+        frames += run_batch(b, frames, not sync_mode)
+    if not sync_mode:
+        ctx.synth_batch_wait()
     dt = time.perf_counter() - t0
+    check = float(np.abs(wav_all.numpy()[::9973]).sum())
     if world > 1:
         t = torch.tensor([dt, float(frames)], dtype=torch.float64, device="cuda")
         tmax = t.clone()
@@ -85,7 +95,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         dt, frames = float(tmax[0]), float(t[1])
     if rank == 0:
-        print(json.dumps({"config": "configs[3] utterance-sharded bulk synthesis, pinned host buffers in and out through zvx_synth_batch",
+        print(json.dumps({"config": "configs[3] utterance-sharded bulk synthesis, pinned host buffers in and out through " +
+                                    ("zvx_synth_batch (one synchronous call per launch batch)" if sync_mode else "zvx_synth_batch_submit / _wait (all launch batches in flight)"),
                           "utterances": n_utt, "n_gpus": world, "audio_s": frames / 80.0, "seconds": dt,
                           "audio_s_per_s": frames / 80.0 / dt, "batches_rank0": len(batches), "checksum_rank0": check}))
     ctx.close()
