@@ -249,7 +249,7 @@ cudaError_t norm_affine_launch(const float *x, int ldx, int C, const int *seg_st
 // bottleneck (profiles/).  One pass here (10 B of HBM traffic per element) lets the convs load
 // ready-made fp16 operands.
 // ---------------------------------------------------------------------------------
-constexpr int NA_ROWS = 32;      // rows per block
+constexpr int NA_ROWS = 8;       // rows per block (small: a half batch is only ~30 x 25 chunks of 32 rows, too few blocks to fill 148 SMs)
 
 // grid (ceil(max_len / NA_ROWS), B), block = C/8 threads (one 8-channel group each, <= 256): a thread
 // keeps its group's mean / rstd / gain / shift in registers and streams over the rows of its chunk;
