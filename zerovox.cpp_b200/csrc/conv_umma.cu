@@ -407,7 +407,8 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams &p, uint32_t trow
 constexpr int conv_threads(int MT) { return 128 * MT + 64 + (MT == 1 ? 128 : 0); }
 
 template <int MODE, int MT, bool PAIR = false>
-__global__ void __launch_bounds__(conv_threads(MT)) conv_umma_kernel(const ConvParams p, const __grid_constant__ CUtensorMap a_map)
+__global__ void __launch_bounds__(conv_threads(MT)) conv_umma_kernel(const ConvParams p, const __grid_constant__ CUtensorMap a_map,
+                                                                     const __grid_constant__ CUtensorMap b_map)
 {
     static_assert(!PAIR || (MT == 1 && MODE == PRO_F16), "CTA pairs: one M-tile per CTA, TMA-staged fp16 operand");
     constexpr int N_PRODUCERS = 128 * MT;
@@ -437,7 +438,11 @@ __global__ void __launch_bounds__(conv_threads(MT)) conv_umma_kernel(const ConvP
     const int NC     = p.NC;
     const int ntaps  = p.ntaps;
     const int kc_max = Cin < KCHUNK ? Cin : KCHUNK;
-    const int nkc    = (Cin + KCHUNK - 1) / KCHUNK;
+    const int nkc_a  = (Cin + KCHUNK - 1) / KCHUNK;                // K-chunks of the conv itself (ntaps taps each)
+    const int nkc    = nkc_a + (p.Cin_b + KCHUNK - 1) / KCHUNK;    // + K-chunks of the folded 1-tap source (ConvParams::xb)
+    // channels / taps of K-chunk c, and the stage row its first tap starts at (the folded source reads the output row itself)
+    auto chunk_kc   = [&](int c) { return c < nkc_a ? min(KCHUNK, Cin - c * KCHUNK) : min(KCHUNK, p.Cin_b - (c - nkc_a) * KCHUNK); };
+    auto chunk_taps = [&](int c) { return c < nkc_a ? ntaps : 1; };
     const uint32_t lbo_a         = (uint32_t)p.a_rows * 16u;
     const uint32_t a_stage_bytes = (uint32_t)(kc_max >> 3) * lbo_a;
     const int NB                 = PAIR ? NC / 2 : NC;            // weight rows (output channels) held by this CTA
@@ -475,6 +480,7 @@ __global__ void __launch_bounds__(conv_threads(MT)) conv_umma_kernel(const ConvP
             mbar_init(smem_u32(a_land + s), 1);
         }
         if (tma) tma_prefetch_desc(&a_map);
+        if (tma && p.Cin_b) tma_prefetch_desc(&b_map);
         for (int s = 0; s < p.b_stages; ++s) {
             mbar_init(smem_u32(b_full + s), 1);
             mbar_init(smem_u32(b_empty + s), (uint32_t)CL);       // a stage is free when every CTA of the cluster has used it
@@ -515,7 +521,8 @@ __global__ void __launch_bounds__(conv_threads(MT)) conv_umma_kernel(const ConvP
                     for (int c = 0; c < nkc; ++c) {
                         mbar_wait(smem_u32(a_empty + sa), ph ^ 1u, p.err_flag);
                         mbar_arrive_expect_tx(smem_u32(a_land + sa), box_bytes);
-                        tma_load_3d(a_base + sa * a_stage_bytes, &a_map, 0, gr, c * (KCHUNK / 8), smem_u32(a_land + sa));
+                        if (c < nkc_a) tma_load_3d(a_base + sa * a_stage_bytes, &a_map, 0, gr, c * (KCHUNK / 8), smem_u32(a_land + sa));
+                        else tma_load_3d(a_base + sa * a_stage_bytes, &b_map, 0, gr, (c - nkc_a) * (KCHUNK / 8), smem_u32(a_land + sa));
                         if (++sa == p.a_stages) { sa = 0; ph ^= 1u; }
                     }
                 }
@@ -599,7 +606,7 @@ __global__ void __launch_bounds__(conv_threads(MT)) conv_umma_kernel(const ConvP
         int sb = 0;
         uint32_t phb = 0;
         for (int c = 0; c < nkc; ++c)
-            for (int a = 0; a < ntaps; ++a) {
+            for (int a = 0; a < chunk_taps(c); ++a) {
                 mbar_wait(smem_u32(b_full + sb), phb, p.err_flag);
                 if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(b_peer + sb), 0u));
                 __syncwarp();
@@ -616,13 +623,15 @@ __global__ void __launch_bounds__(conv_threads(MT)) conv_umma_kernel(const ConvP
         int sa = 0, sb = 0;
         uint32_t pha = 0, phb = 0, accum = 0;
         for (int c = 0; c < nkc; ++c) {
-            const int ksteps = min(KCHUNK, Cin - c * KCHUNK) >> 4;
+            const int ksteps = chunk_kc(c) >> 4;
+            const int ctaps = chunk_taps(c);
             mbar_wait(smem_u32(a_full + sa), pha, p.err_flag);
             if (PAIR) mbar_wait_cluster(smem_u32(a_peer + sa), pha, p.err_flag);
             if (MODE == PRO_F16) fence_proxy_async_smem();    // cp.async wrote through the generic proxy
             tc_fence_after_sync();
-            uint32_t a_tap = a_base + sa * a_stage_bytes;
-            for (int a = 0; a < ntaps; ++a, a_tap += tap_bytes) {
+            // (the folded 1-tap source reads the output row: stage row -tap_off0)
+            uint32_t a_tap = a_base + sa * a_stage_bytes + (c < nkc_a ? 0u : (uint32_t)(-p.tap_off0) * 16u);
+            for (int a = 0; a < ctaps; ++a, a_tap += tap_bytes) {
                 mbar_wait(smem_u32(b_full + sb), phb, p.err_flag);
                 if (PAIR) mbar_wait_cluster(smem_u32(b_peer + sb), phb, p.err_flag);
                 tc_fence_after_sync();
@@ -663,19 +672,19 @@ __global__ void __launch_bounds__(conv_threads(MT)) conv_umma_kernel(const ConvP
         // =================== weight (B operand) loader ===================
         if (lane == 0) {
             // the packed blocks of one N-chunk are consecutive in (K-chunk, tap) order
-            const uint8_t *src = reinterpret_cast<const uint8_t *>(p.w_packed + (size_t)nchunk * ((size_t)Cin * ntaps * NC));
+            const uint8_t *src = reinterpret_cast<const uint8_t *>(p.w_packed + (size_t)nchunk * (((size_t)Cin * ntaps + (size_t)p.Cin_b) * NC));
             const int b_stages = p.b_stages;
             int sb = 0;
             uint32_t phb = 0;
             for (int c = 0; c < nkc; ++c) {
-                const uint32_t bytes = (uint32_t)min(KCHUNK, Cin - c * KCHUNK) * NC * 2u;
+                const uint32_t bytes = (uint32_t)chunk_kc(c) * NC * 2u;
                 const uint32_t part = bytes / (uint32_t)CL;          // this CTA's share of the stage (a multiple of 16 bytes)
 #ifdef ZVX_WHATIF_HALF_WEIGHTS
                 const uint32_t wbytes = (bytes / 32u) * 16u;         // timing experiment only (wrong results): half the weight stream
 #else
                 const uint32_t wbytes = bytes;
 #endif
-                for (int a = 0; a < ntaps; ++a, src += bytes) {
+                for (int a = 0; a < chunk_taps(c); ++a, src += bytes) {
                     // b_empty counts the commits of ALL CTAs of the cluster: the share goes into every peer's stage
                     mbar_wait(smem_u32(b_empty + sb), phb ^ 1u, p.err_flag);
                     if (PAIR) {
@@ -919,8 +928,10 @@ size_t conv_umma_plan(ConvParams &p, size_t smem_budget)
     p.a_rows            = p.use_tma ? need_rows : round_a_rows(need_rows, kc_max);
     const size_t a_stage = (size_t)(kc_max >> 3) * p.a_rows * 16;
     const size_t b_stage = (size_t)kc_max * p.NC * 2 / (p.pair ? 2 : 1);
-    const int nkc        = (p.Cin + KCHUNK - 1) / KCHUNK;
-    const int nb_total   = nkc * p.ntaps;
+    if (p.Cin_b && (!p.use_tma || p.Cin_b < KCHUNK || p.Cin_b % 8 || p.ldxb % 8)) p.Cin_b = -1;      // cannot fold: the caller must check
+    const int nkc_b      = p.Cin_b > 0 ? (p.Cin_b + KCHUNK - 1) / KCHUNK : 0;
+    const int nkc        = (p.Cin + KCHUNK - 1) / KCHUNK + nkc_b;
+    const int nb_total   = (nkc - nkc_b) * p.ntaps + nkc_b;
     int as = nkc < 2 ? 1 : 2;
     int bs = nb_total < 2 ? 1 : 2;
     // grow B first (weights are the longer stream), then A, while it fits
@@ -995,10 +1006,11 @@ cudaError_t conv_umma_pk_launch(const ConvParams &p, int total_tiles, int num_sm
 
 // launch with a thread-block cluster of p.cluster CTAs along x (1: plain launch)
 template <typename K>
-static cudaError_t launch_clustered(K kernel, dim3 grid, int threads, size_t smem, cudaStream_t st, const ConvParams &p, const CUtensorMap &a_map)
+static cudaError_t launch_clustered(K kernel, dim3 grid, int threads, size_t smem, cudaStream_t st, const ConvParams &p, const CUtensorMap &a_map,
+                                    const CUtensorMap &b_map)
 {
     if (p.cluster <= 1) {
-        kernel<<<grid, threads, smem, st>>>(p, a_map);
+        kernel<<<grid, threads, smem, st>>>(p, a_map, b_map);
         return cudaGetLastError();
     }
     cudaLaunchConfig_t cfg = {};
@@ -1013,13 +1025,13 @@ static cudaError_t launch_clustered(K kernel, dim3 grid, int threads, size_t sme
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kernel, p, a_map);
+    return cudaLaunchKernelEx(&cfg, kernel, p, a_map, b_map);
 }
 
 // Tensor map of a PRO_F16 operand buffer for the TMA-staged A tiles: the [rows][ldx] fp16 matrix (first channel x_ch_off)
 // seen as (8 channels, rows, C/8 channel groups) with strides (2, 2 ldx, 16) bytes, box (8, box_rows, 8), no swizzle:
 // a box lands as [group][row][8 channels] = the K-major no-swizzle operand layout with LBO = box_rows * 16 bytes.
-static cudaError_t make_a_map(const ConvParams &p, long long rows_total, CUtensorMap *out)
+static cudaError_t make_a_map(const ConvParams &p, long long rows_total, CUtensorMap *out, bool second = false)
 {
     typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1032,9 +1044,12 @@ static cudaError_t make_a_map(const ConvParams &p, long long rows_total, CUtenso
         if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) return cudaErrorNotSupported;
         encode = reinterpret_cast<encode_fn>(fn);
     }
-    void *base = const_cast<__half *>(reinterpret_cast<const __half *>(p.x) + (size_t)p.tma_row0 * p.ldx + p.x_ch_off);
-    const cuuint64_t dims[3] = {8, (cuuint64_t)rows_total, (cuuint64_t)(p.Cin / 8)};
-    const cuuint64_t strides[2] = {(cuuint64_t)p.ldx * 2, 16};
+    // (second: the folded 1-tap source ConvParams::xb, same rows, same box)
+    const int ld = second ? p.ldxb : p.ldx, cin = second ? p.Cin_b : p.Cin;
+    void *base = second ? const_cast<__half *>(reinterpret_cast<const __half *>(p.xb) + (size_t)p.tma_row0 * ld)
+                        : const_cast<__half *>(reinterpret_cast<const __half *>(p.x) + (size_t)p.tma_row0 * ld + p.x_ch_off);
+    const cuuint64_t dims[3] = {8, (cuuint64_t)rows_total, (cuuint64_t)(cin / 8)};
+    const cuuint64_t strides[2] = {(cuuint64_t)ld * 2, 16};
     const cuuint32_t box[3] = {8, (cuuint32_t)p.a_rows, 8};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -1050,18 +1065,21 @@ static cudaError_t launch_mode(const ConvParams &p, int total_tiles, size_t smem
     if (q.pair) q.cluster = 2;
     q.n_tiles = total_tiles;
     dim3 grid((total_tiles + q.cluster - 1) / q.cluster * q.cluster, p.Cout / p.NC, 1);
-    CUtensorMap a_map;
+    CUtensorMap a_map, b_map;
     memset(&a_map, 0, sizeof a_map);
+    memset(&b_map, 0, sizeof b_map);
     if (MODE == PRO_F16 && q.use_tma) {
-        const cudaError_t e = make_a_map(q, q.tma_rows, &a_map);
+        cudaError_t e = make_a_map(q, q.tma_rows, &a_map);
         if (e != cudaSuccess) return e;
+        if (q.Cin_b > 0 && (e = make_a_map(q, q.tma_rows, &b_map, true)) != cudaSuccess) return e;
     } else {
+        if (q.Cin_b > 0) return cudaErrorInvalidValue;       // the folded source exists in TMA mode only (the caller checks conv_umma_plan)
         q.use_tma = 0;
     }
     if constexpr (MODE == PRO_F16 && MT == 1) {
-        if (q.pair) return launch_clustered(conv_umma_kernel<MODE, MT, true>, grid, q.epi8 ? conv_threads(MT) : 128 * MT + 64, smem, st, q, a_map);
+        if (q.pair) return launch_clustered(conv_umma_kernel<MODE, MT, true>, grid, q.epi8 ? conv_threads(MT) : 128 * MT + 64, smem, st, q, a_map, b_map);
     }
-    return launch_clustered(conv_umma_kernel<MODE, MT>, grid, q.epi8 && MT == 1 ? conv_threads(MT) : 128 * MT + 64, smem, st, q, a_map);
+    return launch_clustered(conv_umma_kernel<MODE, MT>, grid, q.epi8 && MT == 1 ? conv_threads(MT) : 128 * MT + 64, smem, st, q, a_map, b_map);
 }
 
 template <int MODE>

@@ -40,6 +40,8 @@ struct ConvVariant {
 };
 
 struct ConvLayer {
+    __half *packed_fold = nullptr;   // decoder conv2 with its block's learned 1x1 shortcut folded in: per N-chunk this conv's blocks, then the
+    int fold_ic = 0;                 // shortcut's (fold_ic input channels, one tap); see ConvParams::xb
     int OC = 0, IC = 0, K = 0, NC = 0;
     const __half *raw = nullptr;
     const float  *bias = nullptr;
@@ -125,6 +127,7 @@ struct zvx_ctx {
     int conv_cluster = 1;   // CTAs per cluster of the one-tile conv kernel sharing every weight stage by multicast; measured on
                             // B200 (profiles/r02_conv_cluster_ab.txt): 2 -> +7 %, 4 -> +19 % time on the decoder convs, so off
     int branch_f16 = 0; // fused MRF blocks write their outputs as fp16, the consumer sums three fp16 tensors (see run_vocoder)
+    int conv_fold = 1;  // decoder: the learned 1x1 shortcut of a block is computed by the block's conv2 (extra K-chunks), ZVX_CONV_FOLD
     int conv_epi8 = 1;  // see run_conv
     int conv_pair = 0;  // PRO_F16 convs of the one-tile kernel as tcgen05 CTA pairs (M = 256, half a weight stage per SM)
     int upconv_mt2 = 1; // two M-tiles per CTA for up-convs with NC <= 96 (ZVX_UPCONV_MT2)
@@ -296,7 +299,37 @@ int pack_variant(zvx_ctx *ctx, const std::vector<__half> &raw, int OC, int IC, i
 }
 
 // host copies of raw conv weights are needed for packing
+struct HostW;
+int pack_fold(zvx_ctx *ctx, const std::vector<__half> &raw, const std::vector<__half> &raw_sc, ConvLayer &L, int IC_sc);
 struct HostW { std::map<std::string, std::vector<__half>> h; std::map<std::string, std::vector<float>> f; };
+
+// conv2 (OC, IC, K) followed, per N-chunk, by the 1x1 shortcut (OC, IC_sc, 1): the order the kernel's weight loader walks
+int pack_fold(zvx_ctx *ctx, const std::vector<__half> &raw, const std::vector<__half> &raw_sc, ConvLayer &L, int IC_sc)
+{
+    const int OC = L.OC, IC = L.IC, K = L.K, NC = L.NC;
+    if ((int)raw.size() != OC * IC * K || (int)raw_sc.size() != OC * IC_sc) return fail(ctx, "fold: unexpected weight sizes");
+    std::vector<__half> pk((size_t)OC * ((size_t)IC * K + IC_sc));
+    size_t o = 0;
+    for (int n = 0; n < OC / NC; ++n) {
+        for (int c0 = 0; c0 < IC; c0 += 64) {
+            const int kc = std::min(64, IC - c0);
+            for (int tap = 0; tap < K; ++tap)
+                for (int g = 0; g < kc / 8; ++g)
+                    for (int nn = 0; nn < NC; ++nn)
+                        for (int e = 0; e < 8; ++e) pk[o++] = raw[((size_t)(n * NC + nn) * IC + (c0 + g * 8 + e)) * K + tap];
+        }
+        for (int c0 = 0; c0 < IC_sc; c0 += 64) {
+            const int kc = std::min(64, IC_sc - c0);
+            for (int g = 0; g < kc / 8; ++g)
+                for (int nn = 0; nn < NC; ++nn)
+                    for (int e = 0; e < 8; ++e) pk[o++] = raw_sc[(size_t)(n * NC + nn) * IC_sc + (c0 + g * 8 + e)];
+        }
+    }
+    if (dev_alloc(ctx, &L.packed_fold, pk.size())) return 1;
+    CK(ctx, cudaMemcpy(L.packed_fold, pk.data(), pk.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    L.fold_ic = IC_sc;
+    return 0;
+}
 
 int make_conv(zvx_ctx *ctx, HostW &hw, const std::string &prefix, bool with_bias, int dilation, ConvLayer &L,
               int force_pad = -1)
@@ -433,6 +466,7 @@ int build_decoder(zvx_ctx *ctx, HostW &hw)
         if (make_conv(ctx, hw, p + ".conv1", true, 1, b.conv1)) return 1;
         if (make_conv(ctx, hw, p + ".conv2", true, 1, b.conv2)) return 1;
         if (b.learned_sc && make_conv(ctx, hw, p + ".conv1x1", false, 1, b.conv1x1)) return 1;
+        if (b.learned_sc && ctx->conv_fold && b.cin >= 64 && b.cin % 8 == 0 && pack_fold(ctx, hw.h[p + ".conv2.w"], hw.h[p + ".conv1x1.w"], b.conv2, b.cin)) return 1;
         if (f32_ptr(ctx, p + ".norm1.w", b.cin, &b.n1w) || f32_ptr(ctx, p + ".norm1.b", b.cin, &b.n1b) ||
             f32_ptr(ctx, p + ".norm2.w", b.cin, &b.n2w) || f32_ptr(ctx, p + ".norm2.b", b.cin, &b.n2b))
             return 1;
@@ -457,6 +491,7 @@ int build_decoder(zvx_ctx *ctx, HostW &hw)
         if (make_conv(ctx, hw, p + ".conv1", true, 1, b.conv1)) return 1;
         if (make_conv(ctx, hw, p + ".conv2", true, 1, b.conv2)) return 1;
         if (b.learned_sc && make_conv(ctx, hw, p + ".conv1x1", false, 1, b.conv1x1)) return 1;
+        if (b.learned_sc && ctx->conv_fold && b.cin >= 64 && b.cin % 8 == 0 && pack_fold(ctx, hw.h[p + ".conv2.w"], hw.h[p + ".conv1x1.w"], b.conv2, b.cin)) return 1;
         if (b.conv1.IC != b.cin || b.conv1.OC != b.cout || b.conv2.IC != b.cout || b.conv2.OC != b.cout)
             return fail(ctx, "%s: conv shapes do not match AdainResBlk1d(%d,%d)", nm, b.cin, b.cout);
         for (int k = 1; k <= 2; ++k) {
@@ -843,6 +878,7 @@ struct ConvCall {
     int out_mul = 1;
     double flops = 0.0;        // algorithmic FLOPs of the launch when they differ from 2*rows*OC*IC*taps
     bool stats = false;        // the epilogue also emits the per-tile statistics partials of the output (ctx->stat_part)
+    const void *xb = nullptr; int ldxb = 0;   // fold: fp16 source of the layer's folded 1x1 shortcut (ConvLayer::packed_fold)
 };
 
 int run_conv(zvx_ctx *ctx, const ConvCall &cc)
@@ -872,6 +908,11 @@ int run_conv(zvx_ctx *ctx, const ConvCall &cc)
     p.out_mul = cc.out_mul; p.out_add = v.out_add;
     p.stats_out = cc.stats ? ctx->stat_part : nullptr;
     p.err_flag = ctx->d_err;
+    const bool fold = cc.xb != nullptr;
+    if (fold) {
+        if (!L.packed_fold || cc.pro_mode != PRO_F16) return fail(ctx, "conv: folded shortcut without packed weights / fp16 operand");
+        p.xb = cc.xb; p.ldxb = cc.ldxb; p.Cin_b = L.fold_ic; p.w_packed = L.packed_fold;
+    }
     int tiles = ctx->total_tiles[cc.rate_idx];
     // two M-tiles per CTA (each weight stage feeds 256 rows) whenever that still fills the GPU
     p.mt = 1;
@@ -887,7 +928,7 @@ int run_conv(zvx_ctx *ctx, const ConvCall &cc)
     }
     ctx->launches++;
     const double rows = (double)ctx->last_frames * p.rate_in;
-    if (prof_begin(ctx, cc.kind, cc.stage, cc.flops > 0.0 ? cc.flops : 2.0 * rows * L.OC * L.IC * v.ntaps, 0.0)) return 1;
+    if (prof_begin(ctx, cc.kind, cc.stage, cc.flops > 0.0 ? cc.flops : 2.0 * rows * L.OC * ((double)L.IC * v.ntaps + (fold ? L.fold_ic : 0)), 0.0)) return 1;
     if (ctx->use_ref_kernels) {
         CK(ctx, conv_ref_launch(p, tiles, ctx->stream));
     } else {
@@ -908,6 +949,8 @@ int run_conv(zvx_ctx *ctx, const ConvCall &cc)
             p.tma_rows = (long long)ctx->last_frames * p.rate_in;
             const size_t smem = conv_umma_plan(p, p.mt == 2 ? 226 * 1024 : (size_t)ctx->conv_smem_kb * 1024);
             if (smem > 227 * 1024) return fail(ctx, "conv needs %zu bytes of shared memory", smem);
+            if (fold && p.Cin_b <= 0) return fail(ctx, "conv: the launch cannot fold its shortcut (needs the TMA-staged fp16 operand)");
+            if (p.pair && fold) p.pair = 0;                   // (the pair layout of the folded weights is not built)
             if (p.pair) p.w_packed = v.packed_pair;          // (conv_umma_plan clears the flag when the launch does not qualify)
             p.cluster = 1;
             if (ctx->conv_cluster > 1 && tiles >= 2 * ctx->conv_cluster && (int64_t)L.IC * v.ntaps >= 512) {
@@ -1010,6 +1053,12 @@ int run_decoder(zvx_ctx *ctx, float *mel_out)
         return 0;
     };
 
+    // The learned 1x1 shortcut folded into the block's conv2 (ConvParams::xb): its weights follow conv2's in ConvLayer::packed_fold,
+    // its operand is the fp16 copy of the block input; no shortcut launch, no `sc` round trip.
+    auto fold_ok = [&](const ConvLayer &conv2) {
+        return ctx->conv_fold && conv2.packed_fold && ctx->dec_prepass && !ctx->use_ref_kernels && ctx->conv_tma && !ctx->conv_mt2;
+    };
+
     // InstanceNorm statistics (ggml_norm, ggml-cpu.c:6880-6929; call sites stylettsdec.cpp:94-98,119-123,191): the conv that
     // WRITES a tensor leaves per-tile sums in its epilogue and a small finalize launch turns them into mean / rstd right
     // before the consumer; only tensors no conv of this schedule produced (enc_in, the asr_res branch) take the stand-alone pass
@@ -1023,7 +1072,12 @@ int run_decoder(zvx_ctx *ctx, float *mel_out)
     for (int i = 0; i < 2; ++i) {
         ResBlkW &b = ctx->enc[i];
         const float *sc = x; int ldsc = ldx;
-        if (b.learned_sc) {
+        const void *fold_x = nullptr; int fold_ld = 0;
+        if (b.learned_sc && fold_ok(b.conv2)) {
+            ConvCall s; s.L = &b.conv1x1; s.x = x; s.ldx = ldx; s.pro_mode = PRO_CVT;
+            if (use_raw_f16(ctx, s, true)) return 1;             // i == 0: x is enc_in; the copy is reused by asr_res below
+            fold_x = s.x; fold_ld = s.ldx; sc = nullptr; ldsc = 0;
+        } else if (b.learned_sc) {
             ConvCall s; s.L = &b.conv1x1; s.x = x; s.ldx = ldx; s.pro_mode = PRO_CVT; s.use_bias = false;
             s.out32 = ctx->sc; s.ldo32 = b.cout;
             if (forked([&]() -> int {
@@ -1042,8 +1096,9 @@ int run_decoder(zvx_ctx *ctx, float *mel_out)
         ConvCall c2; c2.L = &b.conv2; c2.x = enc_h[i]; c2.ldx = b.cin; c2.pro_mode = PRO_NORM; c2.pro_slope = 0.2f;
         c2.mu = ctx->mu; c2.rstd = ctx->rstd; c2.stat_stride = b.cin; c2.g = b.n2w; c2.b = b.n2b; c2.gb_stride = 0;
         c2.res = sc; c2.ldres = ldsc; c2.scale = inv_sqrt2;
+        c2.xb = fold_x; c2.ldxb = fold_ld;
         c2.out32 = enc_out[i]; c2.ldo32 = enc_ld[i]; c2.stats = fs;
-        if (b.learned_sc && join()) return 1;
+        if (b.learned_sc && !fold_x && join()) return 1;
         if (run_norm_conv(ctx, c2)) return 1;
         x = enc_out[i]; ldx = enc_ld[i];
     }
@@ -1076,7 +1131,12 @@ int run_decoder(zvx_ctx *ctx, float *mel_out)
         const AdainDesc &a1 = ctx->adain.d[b.ada1], &a2 = ctx->adain.d[b.ada2];
         float *h = b.cout == BN ? ctx->h1056 : ctx->h528;
         const float *sc = din[i]; int ldsc = dinl[i];
-        if (b.learned_sc) {
+        const void *fold_x = nullptr; int fold_ld = 0;
+        if (b.learned_sc && fold_ok(b.conv2)) {
+            ConvCall s; s.L = &b.conv1x1; s.x = din[i]; s.ldx = dinl[i]; s.pro_mode = PRO_CVT;
+            if (use_raw_f16(ctx, s, true)) return 1;
+            fold_x = s.x; fold_ld = s.ldx; sc = nullptr; ldsc = 0;
+        } else if (b.learned_sc) {
             ConvCall s; s.L = &b.conv1x1; s.x = din[i]; s.ldx = dinl[i]; s.pro_mode = PRO_CVT; s.use_bias = false;
             s.out32 = ctx->sc; s.ldo32 = b.cout;
             if (forked([&]() -> int {
@@ -1097,8 +1157,9 @@ int run_decoder(zvx_ctx *ctx, float *mel_out)
         c2.mu = ctx->mu; c2.rstd = ctx->rstd; c2.stat_stride = b.cout;
         c2.g = ctx->adain_gb + a2.out_off; c2.b = ctx->adain_gb + a2.out_off + a2.C; c2.gb_stride = ctx->adain.total;
         c2.res = sc; c2.ldres = ldsc; c2.scale = inv_sqrt2;
+        c2.xb = fold_x; c2.ldxb = fold_ld;
         c2.out32 = dout[i]; c2.ldo32 = doutl[i]; c2.stats = fs && i < 4;
-        if (b.learned_sc && join()) return 1;
+        if (b.learned_sc && !fold_x && join()) return 1;
         if (run_norm_conv(ctx, c2)) return 1;
     }
     // ---- to_out (stylettsdec.cpp:432-441) ----
@@ -1553,6 +1614,7 @@ int zvx_create(zvx_ctx **out, const zvx_config *cfg, const zvx_tensor_desc *weig
     if (const char *e = getenv("ZVX_CONV_TMA")) ctx->conv_tma = atoi(e);
     if (const char *e = getenv("ZVX_CONV_PAIR")) ctx->conv_pair = atoi(e);
     if (const char *e = getenv("ZVX_CONV_EPI8")) ctx->conv_epi8 = atoi(e);
+    if (const char *e = getenv("ZVX_CONV_FOLD")) ctx->conv_fold = atoi(e);
     if (const char *e = getenv("ZVX_BRANCH_F16")) ctx->branch_f16 = atoi(e);
     if (const char *e = getenv("ZVX_MRF_F16_CHAIN")) ctx->mrf_f16_chain = atoi(e);
     if (const char *e = getenv("ZVX_FUSED_STATS")) ctx->fused_stats = atoi(e);

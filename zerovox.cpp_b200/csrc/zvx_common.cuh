@@ -89,6 +89,12 @@ struct ConvParams {
     double2     *stats_out;   // [n_tiles][Cout] or null
     // PRO_F16 operand staged by TMA (cp.async.bulk.tensor.3d, one box = a halo tile of 64 channels) instead of per-thread
     // 16-byte cp.async; the kernel's tensor-map argument describes the [rows][ldx] fp16 buffer as (8 ch, rows, C/8 groups)
+    // Second operand source folded into the same accumulator (TMA mode only): Cin_b more input channels read from the fp16
+    // matrix xb with ONE tap at the output row -- the learned 1x1 shortcut of a decoder block computed by the block's conv2
+    // (D = W2 . h + Wsc . x, stylettsdec.cpp:286-301).  The packed weights of an N-chunk are followed by the shortcut's blocks.
+    const void  *xb;
+    int          ldxb;
+    int          Cin_b;       // 0: none
     int          use_tma;
     int          epi8;        // one-tile kernel, MT = 1: four more epilogue warps (a second warp per tensor-memory lane quarter)
     int          pair;        // one-tile kernel as tcgen05 CTA pairs (.cta_group::2), see conv_umma.cu; needs use_tma
