@@ -258,7 +258,8 @@ __global__ void __launch_bounds__(256) norm_act_f16_kernel(const float *__restri
                                                            const int *__restrict__ seg_start,
                                                            const float *__restrict__ mu, const float *__restrict__ rstd,
                                                            const float *__restrict__ g, const float *__restrict__ b,
-                                                           int gb_stride, float slope, __half *__restrict__ y16)
+                                                           int gb_stride, float slope, __half *__restrict__ y16,
+                                                           __half *__restrict__ raw16)
 {
     const int u = blockIdx.y;
     const size_t r0 = (size_t)seg_start[u] + (size_t)blockIdx.x * NA_ROWS;
@@ -290,6 +291,11 @@ __global__ void __launch_bounds__(256) norm_act_f16_kernel(const float *__restri
 #pragma unroll
             for (int q = 0; q < 8; ++q) h[q] = __float2half_rn(prologue_apply(PRO_NORM, xv[q], slope, pc[q]));
             *reinterpret_cast<uint4 *>(y16 + (r + k) * C + c) = *reinterpret_cast<const uint4 *>(h);
+            if (raw16) {        // the plain fp16 copy of the same rows (operand of the block's folded 1x1 shortcut): saves its own pass
+#pragma unroll
+                for (int q = 0; q < 8; ++q) h[q] = __float2half_rn(xv[q]);
+                *reinterpret_cast<uint4 *>(raw16 + (r + k) * C + c) = *reinterpret_cast<const uint4 *>(h);
+            }
         }
     }
 }
@@ -412,12 +418,12 @@ cudaError_t cvt_f16_launch(const float *x, int ldx, int ch_off, int C, size_t ro
 
 cudaError_t norm_act_f16_launch(const float *x, int ldx, int ch_off, int C, const int *seg_start, int B, int max_len,
                                 const float *mu, const float *rstd, const float *g, const float *b, int gb_stride, float slope,
-                                __half *y16, cudaStream_t st)
+                                __half *y16, __half *raw16, cudaStream_t st)
 {
     if (C % 8 || C / 8 > 256) return cudaErrorInvalidValue;
     dim3 grid((max_len + NA_ROWS - 1) / NA_ROWS, B);
     const int threads = ((C / 8 + 31) / 32) * 32;
-    norm_act_f16_kernel<<<grid, threads, 0, st>>>(x, ldx, ch_off, C, seg_start, mu, rstd, g, b, gb_stride, slope, y16);
+    norm_act_f16_kernel<<<grid, threads, 0, st>>>(x, ldx, ch_off, C, seg_start, mu, rstd, g, b, gb_stride, slope, y16, raw16);
     return cudaGetLastError();
 }
 

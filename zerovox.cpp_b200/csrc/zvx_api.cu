@@ -878,6 +878,7 @@ struct ConvCall {
     int out_mul = 1;
     double flops = 0.0;        // algorithmic FLOPs of the launch when they differ from 2*rows*OC*IC*taps
     bool stats = false;        // the epilogue also emits the per-tile statistics partials of the output (ctx->stat_part)
+    __half *raw16_out = nullptr;              // run_norm_conv: the norm pass also writes the plain fp16 copy of its input here
     const void *xb = nullptr; int ldxb = 0;   // fold: fp16 source of the layer's folded 1x1 shortcut (ConvLayer::packed_fold)
 };
 
@@ -992,7 +993,7 @@ int run_norm_conv(zvx_ctx *ctx, ConvCall cc)
     ctx->launches++;
     if (prof_begin(ctx, ZVX_K_NORM_AFFINE, 0, 0.0, 6.0 * (double)ctx->last_frames * C)) return 1;
     CK(ctx, norm_act_f16_launch(reinterpret_cast<const float *>(cc.x), cc.ldx, cc.x_ch_off, C, ctx->d_seg, ctx->last_B, ctx->last_max_len,
-                                cc.mu, cc.rstd, cc.g, cc.b, cc.gb_stride, cc.pro_slope, ctx->X16, ctx->stream));
+                                cc.mu, cc.rstd, cc.g, cc.b, cc.gb_stride, cc.pro_slope, ctx->X16, cc.raw16_out, ctx->stream));
     if (prof_end(ctx)) return 1;
     cc.x = ctx->X16; cc.ldx = C; cc.x_ch_off = 0; cc.pro_mode = PRO_F16;
     cc.mu = cc.rstd = cc.g = cc.b = nullptr;
@@ -1074,9 +1075,8 @@ int run_decoder(zvx_ctx *ctx, float *mel_out)
         const float *sc = x; int ldsc = ldx;
         const void *fold_x = nullptr; int fold_ld = 0;
         if (b.learned_sc && fold_ok(b.conv2)) {
-            ConvCall s; s.L = &b.conv1x1; s.x = x; s.ldx = ldx; s.pro_mode = PRO_CVT;
-            if (use_raw_f16(ctx, s, true)) return 1;             // i == 0: x is enc_in; the copy is reused by asr_res below
-            fold_x = s.x; fold_ld = s.ldx; sc = nullptr; ldsc = 0;
+            // the fp16 copy of the block input is written by conv1's norm pass below (i == 0: x is enc_in; the copy is reused by asr_res)
+            fold_x = ctx->R16; fold_ld = b.cin; sc = nullptr; ldsc = 0;
         } else if (b.learned_sc) {
             ConvCall s; s.L = &b.conv1x1; s.x = x; s.ldx = ldx; s.pro_mode = PRO_CVT; s.use_bias = false;
             s.out32 = ctx->sc; s.ldo32 = b.cout;
@@ -1091,6 +1091,7 @@ int run_decoder(zvx_ctx *ctx, float *mel_out)
         ConvCall c1; c1.L = &b.conv1; c1.x = x; c1.ldx = ldx; c1.pro_mode = PRO_NORM; c1.pro_slope = 0.2f;
         c1.mu = ctx->mu; c1.rstd = ctx->rstd; c1.stat_stride = b.cin; c1.g = b.n1w; c1.b = b.n1b; c1.gb_stride = 0;
         c1.out32 = enc_h[i]; c1.ldo32 = b.cin; c1.stats = fs;
+        if (fold_x) c1.raw16_out = ctx->R16;
         if (run_norm_conv(ctx, c1)) return 1;
         if (fs ? run_stats_finalize(ctx, b.cin, 0) : run_stats(ctx, enc_h[i], b.cin, 0, b.cin)) return 1;
         ConvCall c2; c2.L = &b.conv2; c2.x = enc_h[i]; c2.ldx = b.cin; c2.pro_mode = PRO_NORM; c2.pro_slope = 0.2f;
@@ -1133,9 +1134,7 @@ int run_decoder(zvx_ctx *ctx, float *mel_out)
         const float *sc = din[i]; int ldsc = dinl[i];
         const void *fold_x = nullptr; int fold_ld = 0;
         if (b.learned_sc && fold_ok(b.conv2)) {
-            ConvCall s; s.L = &b.conv1x1; s.x = din[i]; s.ldx = dinl[i]; s.pro_mode = PRO_CVT;
-            if (use_raw_f16(ctx, s, true)) return 1;
-            fold_x = s.x; fold_ld = s.ldx; sc = nullptr; ldsc = 0;
+            fold_x = ctx->R16; fold_ld = b.cin; sc = nullptr; ldsc = 0;      // written by conv1's norm pass below
         } else if (b.learned_sc) {
             ConvCall s; s.L = &b.conv1x1; s.x = din[i]; s.ldx = dinl[i]; s.pro_mode = PRO_CVT; s.use_bias = false;
             s.out32 = ctx->sc; s.ldo32 = b.cout;
@@ -1151,6 +1150,7 @@ int run_decoder(zvx_ctx *ctx, float *mel_out)
         c1.mu = ctx->mu; c1.rstd = ctx->rstd; c1.stat_stride = b.cin;
         c1.g = ctx->adain_gb + a1.out_off; c1.b = ctx->adain_gb + a1.out_off + a1.C; c1.gb_stride = ctx->adain.total;
         c1.out32 = h; c1.ldo32 = b.cout; c1.stats = fs;
+        if (fold_x) c1.raw16_out = ctx->R16;
         if (run_norm_conv(ctx, c1)) return 1;
         if (fs ? run_stats_finalize(ctx, b.cout, 0) : run_stats(ctx, h, b.cout, 0, b.cout)) return 1;
         ConvCall c2; c2.L = &b.conv2; c2.x = h; c2.ldx = b.cout; c2.pro_mode = PRO_NORM; c2.pro_slope = 0.2f;

@@ -59,7 +59,7 @@ cudaError_t norm_affine_launch(const float *x, int ldx, int C, const int *seg_st
 // y16 = fp16(lrelu(((x-mu)*rstd)*g + b, slope)) for an [rows][C] slice; stats / affine per utterance
 cudaError_t norm_act_f16_launch(const float *x, int ldx, int ch_off, int C, const int *seg_start, int B, int max_len,
                                 const float *mu, const float *rstd, const float *g, const float *b, int gb_stride, float slope,
-                                __half *y16, cudaStream_t st);
+                                __half *y16, __half *raw16 /* optional plain fp16 copy of x */, cudaStream_t st);
 
 cudaError_t sum3_act_f16_launch(const float *a, const float *b, const float *c, float scale, float slope, size_t n, __half *y16,
                                 cudaStream_t st);
