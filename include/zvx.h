@@ -67,7 +67,15 @@ void zvx_default_config(zvx_config *cfg);
 int zvx_create(zvx_ctx **out, const zvx_config *cfg, const zvx_tensor_desc *weights, int32_t n_weights);
 void zvx_destroy(zvx_ctx *ctx);
 
-/* Message of the last failure on ctx (or of the last failed zvx_create when ctx == NULL). */
+/* Message of the last failure on ctx (or of the last failed zvx_create when ctx == NULL).
+ *
+ * Fatal device faults.  Every barrier wait inside the kernels is bounded (about 3 s of SM clocks): a pipeline
+ * that stops making progress sets a flag in device memory and executes `trap`, so a bug cannot hang the GPU.
+ * Like any device-side fault the trap invalidates the CUDA primary context of the PROCESS: the failing call and
+ * every later call on any zvx_ctx return non-zero with "... unspecified launch failure ... (fatal: the CUDA
+ * context is lost, restart the process)", and only a new process can use the GPU again.  The reference has no
+ * analogue (ggml CPU graphs cannot time out); a host that must survive this runs the library in a worker
+ * process. */
 const char *zvx_last_error(const zvx_ctx *ctx);
 
 /* Replaces StyleTTSDecoder::eval            /root/reference/src/stylettsdec.cpp:457-470

@@ -1428,7 +1428,11 @@ int run_vocoder(zvx_ctx *ctx, const float *mel_in, float *wav_out, int16_t *pcm_
 
 int check_device_error(zvx_ctx *ctx)
 {
-    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    // A bounded barrier wait that expired traps (ptx_sm100.cuh: mbar_wait): the synchronise below then reports a
+    // sticky launch failure and the primary context is gone -- say so, the caller cannot recover in this process.
+    const cudaError_t es = cudaStreamSynchronize(ctx->stream);
+    if (es != cudaSuccess)
+        return fail(ctx, "cudaStreamSynchronize failed: %s (fatal: the CUDA context is lost, restart the process)", cudaGetErrorString(es));
     int flag = 0;
     CK(ctx, cudaMemcpy(&flag, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost));
     if (flag) return fail(ctx, "device pipeline timeout flag set");
