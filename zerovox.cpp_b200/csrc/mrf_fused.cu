@@ -109,10 +109,37 @@ struct FCfg {
     static constexpr size_t   SMEM_BUDGET = NCOL == 128 ? 112 * 1024 : 227 * 1024;
 };
 
+// Windows that touch an utterance edge: after a buffer has been written, the rows of the time steps outside the
+// utterance are overwritten with zeros (the convolution's zero padding).  buf: the buffer just written, d: the dilation
+// its layout belongs to.  Called by all epilogue threads; not inlined (three call sites between hot code).
 template <int CH, int NCOL>
+__device__ __noinline__ void zero_outside_rows(uint8_t *buf, int d, int tw, int T, int tid)
+{
+    using C = FCfg<CH, NCOL>;
+    using G = typename C::G;
+    const int lo = max(0, -tw), hi = min(G::WP, T - tw);         // time steps [lo, hi) of the window are inside
+    const int ninv = lo + (G::WP - hi);
+    asm volatile("bar.sync 1, %0;" ::"n"(C::EPI) : "memory");          // every row has been written by its owner
+    for (int i = tid; i < ninv * G::GROUPS; i += C::EPI) {
+        const int g = i % G::GROUPS;
+        int tau = i / G::GROUPS;
+        if (tau >= lo) tau += hi - lo;
+        const int unit = mrf::dest_unit(tau, d, G::WP, G::S, G::GROUPS, NCOL);
+        *reinterpret_cast<uint4 *>(buf + (size_t)g * G::LBO_B + (size_t)unit * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
+// FULL = false is the product instantiation: only the vector data path and the plain fp32 output (what every default
+// launch uses).  FULL = true additionally carries the scalar reference path (flags bit 0, kept for the tests) and the
+// general output phase (running branch sum / scale / fp16 hand-off).  They are separate kernels because the cold paths
+// sit BETWEEN the hot ones in the instruction stream: the full kernel is 142 KB of SASS, the hot loop of the lean one
+// fits the 32 KB instruction cache.
+template <int CH, int NCOL, bool FULL>
 __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
     mrf_fused_kernel(const mrf::Params p, const int nslots, const uint32_t slot_bytes)
 {
+    // compile-time false in the lean kernel
+    const bool scalar_path = FULL && (p.flags & 1);
     using C = FCfg<CH, NCOL>;
     using G = typename C::G;
     constexpr int S = G::S;
@@ -251,32 +278,27 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
         // pipelined: quarter 0 is requested by the caller one layer ahead (before the wait for the second-to-last
         // conv, where these warps idle anyway), quarter q + 1 before quarter q is placed, so that no L2 round trip
         // is exposed.
+        // Addressing: tau = tauT + (compile-time offset); inside the window and the utterance iff tau - lo < span (one
+        // unsigned compare), address = one per-window pointer + constant -- the loads are inlined five times and the
+        // hot loop has to fit the instruction cache.
+        const int tauT = S * (colw + 2 * (lane & 3)) + sQ;
         auto y_loads = [&](const Win &w, int qc, float4 (&f)[4]) {
-            const float *yq = p.y_in + ((ptrdiff_t)w.row0 + w.tw) * CH + c4;
-            const int col0 = colw + 16 * qc;
+            const int lo = max(0, -w.tw);
+            const unsigned span = (unsigned)(min(G::WP, w.T - w.tw) - lo);
+            const float *yq = p.y_in + ((ptrdiff_t)w.row0 + w.tw + tauT) * CH + c4;
+            const int tl = tauT - lo;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int tau = S * (col0 + 8 * (i >> 1) + 2 * (lane & 3) + (i & 1)) + sQ;
-                const bool ok = tau < G::WP && (unsigned)(w.tw + tau) < (unsigned)w.T;      // inside the window and the utterance
-                f[i] = ok ? __ldg(reinterpret_cast<const float4 *>(yq + (ptrdiff_t)tau * CH)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const int dt = S * (16 * qc + 8 * (i >> 1) + (i & 1));
+                f[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if ((unsigned)(tl + dt) < span) f[i] = __ldg(reinterpret_cast<const float4 *>(yq + dt * CH));
             }
         };
         // Windows that touch an utterance edge take the same data path; afterwards the rows of the time steps outside
         // the utterance are overwritten with zeros (the convolution's zero padding, SURVEY.md H-d): typically a few
         // hundred 16-byte stores per CTA instead of a scalar pass over the whole window.  buf_off: the buffer just
         // written, d: the dilation its layout belongs to.
-        auto zero_outside = [&](uint32_t buf_off, int d, int tw_, int T_) {
-            const int lo = max(0, -tw_), hi = min(G::WP, T_ - tw_);         // time steps [lo, hi) of the window are inside
-            const int ninv = lo + (G::WP - hi);
-            asm volatile("bar.sync 1, %0;" ::"n"(C::EPI) : "memory");          // every row has been written by its owner
-            for (int i = tid; i < ninv * G::GROUPS; i += C::EPI) {
-                const int g = i % G::GROUPS;
-                int tau = i / G::GROUPS;
-                if (tau >= lo) tau += hi - lo;
-                const int unit = mrf::dest_unit(tau, d, G::WP, S, G::GROUPS, NCOL);
-                *reinterpret_cast<uint4 *>(smem + buf_off + (size_t)g * LBO_B + (size_t)unit * 16) = make_uint4(0u, 0u, 0u, 0u);
-            }
-        };
+        auto zero_outside = [&](uint32_t buf_off, int d, int tw_, int T_) { zero_outside_rows<CH, NCOL>(smem + buf_off, d, tw_, T_, tid); };
         auto y_place = [&](int qc, const float4 (&f)[4], uint32_t ybase) {
             const int col0 = colw + 16 * qc;
             const uint16_t *tb = tbl_s + sQ * NCOL + col0;
@@ -302,7 +324,7 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
             }
         };
         auto prologue = [&](const Win &w, uint32_t ybase, bool preloaded, float4 (&f0)[4]) {
-            if (!(p.flags & 1)) {
+            if (!scalar_path) {
 #ifdef ZVX_FUSED_PHASES
                 if (dbg) c_l0 = clock64();
 #endif
@@ -374,6 +396,7 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
 
         // -DZVX_FUSED_PHASES + flags bit 1: cycle counts per phase of CTA 0 / warp 0, printed at exit
         long long c_pro = 0, c_wait = 0, c_drain = 0, c_final = 0, c_a = 0;
+        [[maybe_unused]] long long c_top = 0, c_layers = 0;
         [[maybe_unused]] const long long c_t0 = dbg ? clock64() : 0;
         int iter = 0;
         int win = blockIdx.x;
@@ -408,13 +431,19 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
                 const bool last = l == nl - 1;
                 const uint32_t acc_col = L.accumulate ? ycol(iter) : hcol(iter);
                 const uint32_t gl = (uint32_t)(iter * nl + l);      // completions of acc_full before this one
+#ifdef ZVX_FUSED_PHASES
+                const long long c_it0 = dbg ? clock64() : 0;
+#endif
                 if (has_next && l == nl - 2) {
                     // the next window's coordinates, and the first half of its y on the way while these warps
                     // wait for this conv and drain it
                     wnext = window(win + (int)gridDim.x);
-                    have_pre = preload && !(p.flags & 1);
+                    have_pre = preload && !scalar_path;
                     if (have_pre) y_loads(wnext, 0, ypre);
                 }
+#ifdef ZVX_FUSED_PHASES
+                if (dbg) c_top += clock64() - c_it0;
+#endif
                 if (last && has_next) {
                     // While the last conv of this window accumulates into y, bring in the NEXT window: its
                     // y goes to the (now idle) conv1 accumulator columns, lrelu(y) to buffer 0 (the last
@@ -434,8 +463,8 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
                 if (!last) {
                     const uint32_t obuf_off = (l & 1) ? OFF_BUF0 : OFF_BUF1;
                     const float slope = L.out_slope;
-                    if (!(p.flags & 1)) {
-#pragma unroll
+                    if (!scalar_path) {
+#pragma unroll 1
                         for (int lh = 0; lh < 2; ++lh) {
                             const int rb  = quarter * 32 + lh * 16;
                             const int sA  = rb / CH;
@@ -498,7 +527,7 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
                     // final: y (+ running branch sum) (* 1/num_blocks) -> global fp32.  Both 32-column
                     // batches are pulled out of tensor memory first, then the next window is published
                     // (its first conv may overwrite these columns), then the global traffic follows.
-                    if (!(p.flags & 1)) {
+                    if (!scalar_path) {
                         // fragment layout again: this thread's 4 adjacent channels x 16 columns leave as float4
                         uint32_t r0[32], r1[32];
                         tmem_ld_16x256b_x8_nowait(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc_col + (uint32_t)colw, r0);
@@ -511,7 +540,7 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
                         const int lo = p.halo;
                         const unsigned span = (unsigned)(min(p.halo + p.valid, T - tw) - lo);
                         const ptrdiff_t base = ((ptrdiff_t)w.row0 + tw + tau0) * CH + c4;
-                        if (p.out && !p.out16 && !p.acc_in && !p.has_scale) {
+                        if (!FULL || (p.out && !p.out16 && !p.acc_in && !p.has_scale)) {
                             // the common case: y (+ bias) leaves as fp32, nothing else
                             float *oq = p.out + base;
 #pragma unroll
@@ -599,13 +628,16 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
                     }
                     if (dbg) c_final += clock64() - c_a;
                 }
+#ifdef ZVX_FUSED_PHASES
+                if (dbg) c_layers += clock64() - c_it0;
+#endif
             }
         }
 #ifdef ZVX_FUSED_PHASES
         if (dbg_cta) printf("mrf_cta CH=%d NCOL=%d k=%d nl=%d cta=%d windows=%d edge=%d cycles=%lld\n", CH, NCOL, p.L[0].k, nl, (int)blockIdx.x, iter, n_edge, clock64() - c_cta0);
         if (dbg && lane == 0)
-            printf("mrf_fused CH=%d NCOL=%d k=%d nl=%d windows=%d: total %lld  prologue %lld  wait_mma %lld  drain %lld  final %lld  | prologue: loads %lld  wait_st+fence %lld  first prologue (tensor pipe idle) %lld of which loads %lld (cycles, CTA 0 warp 0)\n",
-                   CH, NCOL, p.L[0].k, nl, iter, clock64() - c_t0, c_pro, c_wait, c_drain, c_final, c_ld, c_st, c_first, c_ld_first);
+            printf("mrf_fused CH=%d NCOL=%d k=%d nl=%d windows=%d: total %lld  prologue %lld  wait_mma %lld  drain %lld  final %lld  | prologue: loads %lld  wait_st+fence %lld  first prologue (tensor pipe idle) %lld of which loads %lld | layer iterations %lld of which next-window lookup + preload issue %lld (cycles, CTA 0 warp 0)\n",
+                   CH, NCOL, p.L[0].k, nl, iter, clock64() - c_t0, c_pro, c_wait, c_drain, c_final, c_ld, c_st, c_first, c_ld_first, c_layers, c_top);
 #endif
     } else {
     // one instruction for the whole last warpgroup (.aligned), then the roles split
@@ -754,14 +786,18 @@ cudaError_t launch_cfg(const mrf::Params &p, int total_windows, cudaStream_t st)
     const int grid = total_windows < resident ? total_windows : resident;
     mrf::Params q = p;
     q.total_windows = total_windows;
-    mrf_fused_kernel<CH, NCOL><<<grid, C::THREADS, smem, st>>>(q, nslots, slot);
+    const bool lean = !(p.flags & 1) && p.out && !p.out16 && !p.acc_in && !p.has_scale && !(p.flags & 16);
+    if (lean) mrf_fused_kernel<CH, NCOL, false><<<grid, C::THREADS, smem, st>>>(q, nslots, slot);
+    else      mrf_fused_kernel<CH, NCOL, true><<<grid, C::THREADS, smem, st>>>(q, nslots, slot);
     return cudaGetLastError();
 }
 
 template <int CH, int NCOL>
 cudaError_t init_cfg()
 {
-    return cudaFuncSetAttribute(mrf_fused_kernel<CH, NCOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FCfg<CH, NCOL>::SMEM_BUDGET);
+    const cudaError_t e = cudaFuncSetAttribute(mrf_fused_kernel<CH, NCOL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FCfg<CH, NCOL>::SMEM_BUDGET);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(mrf_fused_kernel<CH, NCOL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FCfg<CH, NCOL>::SMEM_BUDGET);
 }
 
 }  // namespace
