@@ -154,6 +154,12 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
     uint64_t *act_ready = bars + 2 * F_MAX_SLOTS + 1;   // a layer's whole input is in shared memory
     uint64_t *act_half  = bars + 2 * F_MAX_SLOTS + 2;   // ... its even 16-channel K-steps are (see the MMA issuer)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 256);
+#ifdef ZVX_FUSED_PHASES
+    // hand-off chain timestamps of CTA 0 (clock64 is per SM: comparable between warps): [0] commit of a layer issued,
+    // [1] last epilogue warp published the first half, [2] ... the second half, [3] epilogue warp 0 woke on acc_full
+    unsigned long long *ts = reinterpret_cast<unsigned long long *>(smem + 320);
+    if (threadIdx.x < 4) ts[threadIdx.x] = 0ull;
+#endif
     const uint32_t OFF_TBL = F_HEADER + C::seg_bytes(p.B);
     const int *seg_s    = reinterpret_cast<const int *>(smem + F_HEADER);      // [B + 1] seg_start, [B + 1] win_start
     const bool seg_in_smem = C::seg_bytes(p.B) != 0;
@@ -396,7 +402,7 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
 
         // -DZVX_FUSED_PHASES + flags bit 1: cycle counts per phase of CTA 0 / warp 0, printed at exit
         long long c_pro = 0, c_wait = 0, c_drain = 0, c_final = 0, c_a = 0;
-        [[maybe_unused]] long long c_top = 0, c_layers = 0;
+        [[maybe_unused]] long long c_top = 0, c_layers = 0, c_d3 = 0;
         [[maybe_unused]] const long long c_t0 = dbg ? clock64() : 0;
         int iter = 0;
         int win = blockIdx.x;
@@ -460,6 +466,9 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
                 mbar_wait(smem_u32(acc_full), gl & 1u, p.err_flag);
                 tc_fence_after_sync();
                 if (dbg) { const long long c_b = clock64(); c_wait += c_b - c_a; c_a = c_b; }
+#ifdef ZVX_FUSED_PHASES
+                if (dbg && lane == 0) { ts[3] = (unsigned long long)c_a; c_d3 += c_a - (long long)ts[0]; }
+#endif
                 if (!last) {
                     const uint32_t obuf_off = (l & 1) ? OFF_BUF0 : OFF_BUF1;
                     const float slope = L.out_slope;
@@ -490,11 +499,17 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
                                 // rows [rb, rb + 16) of every lane quarter = the even K-steps of the next layer's
                                 // operand: its MMAs over those start while the odd half is still being drained
                                 fence_proxy_async_smem();
+#ifdef ZVX_FUSED_PHASES
+                                if ((p.flags & 2) && blockIdx.x == 0 && lane == 0) atomicMax(&ts[1], (unsigned long long)clock64());
+#endif
                                 publish_half();
                             }
                         }
                         if (interior) {
                             fence_proxy_async_smem();
+#ifdef ZVX_FUSED_PHASES
+                            if ((p.flags & 2) && blockIdx.x == 0 && lane == 0) atomicMax(&ts[2], (unsigned long long)clock64());
+#endif
                             publish_rest();
                         } else {
                             zero_outside(obuf_off, p.L[l + 1].d, tw, T);
@@ -635,6 +650,7 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
         }
 #ifdef ZVX_FUSED_PHASES
         if (dbg_cta) printf("mrf_cta CH=%d NCOL=%d k=%d nl=%d cta=%d windows=%d edge=%d cycles=%lld\n", CH, NCOL, p.L[0].k, nl, (int)blockIdx.x, iter, n_edge, clock64() - c_cta0);
+        if (dbg && lane == 0) printf("mrf_chain commit issued -> epilogue awake %lld (cycles, summed over all layers of CTA 0)\n", c_d3);
         if (dbg && lane == 0)
             printf("mrf_fused CH=%d NCOL=%d k=%d nl=%d windows=%d: total %lld  prologue %lld  wait_mma %lld  drain %lld  final %lld  | prologue: loads %lld  wait_st+fence %lld  first prologue (tensor pipe idle) %lld of which loads %lld | layer iterations %lld of which next-window lookup + preload issue %lld (cycles, CTA 0 warp 0)\n",
                    CH, NCOL, p.L[0].k, nl, iter, clock64() - c_t0, c_pro, c_wait, c_drain, c_final, c_ld, c_st, c_first, c_ld_first, c_layers, c_top);
@@ -652,9 +668,13 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
         constexpr bool dbg = false;
 #endif
         long long c_act = 0, c_w = 0, c_a = 0, c_t0 = dbg ? clock64() : 0;
+        [[maybe_unused]] long long c_d1 = 0, c_d2 = 0, c_d4 = 0, c_d5 = 0, c_d6 = 0, c_d7 = 0, c_n = 0, t_half = 0, t_ready = 0;
         int it = 0, iter = 0;
 #pragma unroll 1
         for (int win = blockIdx.x; win < nwin; win += gridDim.x, ++iter) {
+#ifdef ZVX_FUSED_PHASES
+            const bool interior_dbg = dbg && window(win).interior;
+#endif
 #pragma unroll 1
             for (int l = 0; l < nl; ++l) {
                 const mrf::Layer &L = p.L[l];
@@ -685,6 +705,22 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
                         mbar_wait(smem_u32(ci == 0 ? act_half : act_ready), (uint32_t)(iter * nl + l) & 1u, p.err_flag);
                         tc_fence_after_sync();
                         if (dbg) c_act += clock64() - c_a;
+#ifdef ZVX_FUSED_PHASES
+                        if (dbg && l > 0 && interior_dbg) {
+                            const long long now = clock64();
+                            if (ci == 0) {
+                                c_d4 += (long long)ts[1] - (long long)ts[3];      // acc_full wake -> first half published
+                                c_d5 += now - (long long)ts[1];                   // ... -> this warp awake
+                                c_n += 1;
+                                t_half = now;
+                            } else {
+                                c_d1 += now - t_half;                             // even K-steps issued + wait for the second half
+                                c_d6 += (long long)ts[2] - (long long)ts[1];      // second half drained
+                                c_d7 += now - (long long)ts[2];
+                                t_ready = now;
+                            }
+                        }
+#endif
                     }
                     const int slot = it % nslots;
                     const uint32_t ph = (uint32_t)(it / nslots) & 1u;
@@ -710,9 +746,21 @@ __global__ void __launch_bounds__(FCfg<CH, NCOL>::THREADS, FCfg<CH, NCOL>::CTAS)
                     __syncwarp();
                 }
                 if (leader) umma_commit(smem_u32(acc_full));
+#ifdef ZVX_FUSED_PHASES
+                if (dbg) {
+                    const long long now = clock64();
+                    if (lane == 0) ts[0] = (unsigned long long)now;
+                    if (l > 0 && interior_dbg) c_d2 += now - t_ready;            // odd K-steps issued
+                }
+#endif
                 __syncwarp();
             }
         }
+#ifdef ZVX_FUSED_PHASES
+        if (dbg && lane == 0)
+            printf("mrf_chain per hand-off (layers 1.., %lld samples): awake->half published %lld | ->MMA warp awake %lld | even K issue + wait %lld (second half drained after %lld, +%lld to wake) | odd K issue %lld\n",
+                   c_n, c_d4 / max(c_n, 1LL), c_d5 / max(c_n, 1LL), c_d1 / max(c_n, 1LL), c_d6 / max(c_n, 1LL), c_d7 / max(c_n, 1LL), c_d2 / max(c_n, 1LL));
+#endif
         if (dbg && lane == 0)
             printf("mrf_fused MMA warp: total %lld  wait_activations %lld  wait_weights %lld (cycles, CTA 0)\n", clock64() - c_t0, c_act, c_w);
     } else if (warp == EPI_WARPS + 1) {
