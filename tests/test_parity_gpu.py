@@ -312,3 +312,28 @@ def test_folded_shortcut_matches_separate_shortcut_conv(ctx, zvx, weights, monke
     assert mel_fold.shape == mel_sep.shape == (400, 80)
     assert zv_oracle.snr_db(mel_sep, mel_fold) >= 58.0
     assert zv_oracle.snr_db(g["mel"], mel_fold) >= 55.0 and zv_oracle.snr_db(g["mel"], mel_sep) >= 55.0
+
+
+def test_lean_and_full_fused_kernels_agree(ctx, zvx, weights, monkeypatch):
+    """Round 2: default launches of the fused MRF kernel use the lean instantiation (vector data path + plain fp32 output
+    only, mrf_fused.cu `FULL = false`); ZVX_FUSED_FLAGS=16 forces the full kernel for the same work: identical
+    instructions on the data, so bit-identical output.  The options that only the full kernel serves (stage hand-off =
+    the last block sums the branches and emits the consumer's fp16 operand, hifigan.cpp:300-311) must still meet the
+    reference gate."""
+    from zerovox_cpp_b200 import capi
+    g = golden(400)
+    Ls = [5, 130, 400]
+    mels = [g["mel"][:L].copy() for L in Ls]
+    want = ctx.vocode_batch(mels)
+    monkeypatch.setenv("ZVX_FUSED_FLAGS", "16")
+    cx = capi.Context(weights, device=0)          # the switches are read at zvx_create
+    got = cx.vocode_batch(mels)
+    cx.close()
+    for L, a, b in zip(Ls, want, got):
+        assert a.shape == (L * 300,) and np.array_equal(a, b), L
+    monkeypatch.delenv("ZVX_FUSED_FLAGS")
+    monkeypatch.setenv("ZVX_STAGE_HANDOFF", "1")
+    cx = capi.Context(weights, device=0)
+    voc = cx.vocode(g["mel"])
+    cx.close()
+    assert zv_oracle.snr_db(g["wav"], voc) >= 60.0 and np.abs(voc - g["wav"]).max() <= 1e-3
